@@ -1,0 +1,201 @@
+/* include/nalo_gpu.h — C ABI of the B200-native photometric-alignment path (libnalo_gpu.so).
+ *
+ * The reference (huziqi/NALO-SLAM, a DSO fork) has no plugin/FFI layer: the hot path is reached through
+ * C++ member calls on objects owned by dso::FullSystem. Each entry point below names the reference
+ * member function it replaces (file:line under /root/reference/src). A header-only C++ shim that puts the
+ * reference's class interfaces back on top of this ABI is include/nalo_shim.hpp; INTEGRATION.md shows the
+ * call-site changes a maintainer would make.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative NALO_E_* code on failure; nalo_last_error() gives text.
+ *    No C++ exception crosses the boundary. There is NO CPU fallback: without a CUDA device every call fails.
+ *  - a context owns one CUDA stream, `max_frames` frame slots (image pyramids) and NALO_MAX_TRACKERS tracker
+ *    states (the reference keeps two CoarseTracker instances, FullSystem.cpp:1094-1098). A context is not
+ *    thread-safe; distinct contexts are independent.
+ *  - poses are Sophus::SE3d in memory order: double[7] = {qx,qy,qz,qw,tx,ty,tz}; AffLight = double[2] {a,b}.
+ *  - images are float, row-major, 0..255 (ImageAndExposure::image, util/ImageAndExposure.h:34-74).
+ *  - pyramid level l has size (w>>l, h>>l); the level count is given at creation.
+ *  - host pointers may be pageable or pinned (nalo_host_alloc); "_dev" variants take device pointers.
+ */
+#ifndef NALO_GPU_H_
+#define NALO_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NALO_MAX_LEVELS 6     /* PYR_LEVELS, util/settings.h:52 */
+#define NALO_TRACK_LEVELS 5   /* trackNewestCoarse asserts coarsestLvl < 5, CoarseTracker.cpp:1083 */
+#define NALO_MAX_TRACKERS 2
+#define NALO_MAX_HYPOTHESES 64
+#define NALO_BA_RECORD_WORDS 76 /* one residual record = 304 bytes, layout below */
+#define NALO_BA_MAX_FRAMES 8
+
+enum {
+  NALO_OK = 0,
+  NALO_E_CUDA = -1,      /* CUDA runtime error (text in nalo_last_error) */
+  NALO_E_ARG = -2,       /* bad argument */
+  NALO_E_STATE = -3,     /* call order violated (e.g. track before set_ref) */
+  NALO_E_NODEVICE = -4   /* no CUDA device: the product path has no CPU fallback */
+};
+
+typedef struct nalo_ctx nalo_ctx;
+
+/* Settings read by the path (util/settings.cpp:110-157). Defaults = nalo_default_params(). */
+typedef struct NaloParams {
+  float huberTH;                    /* setting_huberTH = 9 */
+  float coarseCutoffTH;             /* setting_coarseCutoffTH = 20 */
+  float affineOptModeA;             /* 1e12; mode=1 sets 0; <0 fixes a */
+  float affineOptModeB;             /* 1e8 ; mode=1 sets 0; <0 fixes b */
+  float minGradHistCut;             /* 0.5 */
+  float minGradHistAdd;             /* 7 */
+  float gradDownweightPerLevel;     /* 0.75 */
+  int selectDirectionDistribution;  /* true */
+  float reTrackThreshold;           /* 1.5 */
+} NaloParams;
+
+/* Per-call statistics of the tracker (not in the reference; used by bench.py for iters/s, residuals/s). */
+typedef struct NaloTrackStats {
+  long long residuals;  /* points evaluated by calcRes, summed over all evaluations */
+  int evals;            /* number of calcRes evaluations (fused with calcGS) */
+  int iters;            /* LM iterations (CoarseTracker.cpp:1133 loop bodies) */
+  int launches;         /* CUDA kernels launched by the call */
+} NaloTrackStats;
+
+void nalo_default_params(NaloParams* p);
+const char* nalo_version(void);
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int nalo_create(int w, int h, int levels, int device, int max_frames, nalo_ctx** out);
+int nalo_destroy(nalo_ctx* ctx);
+const char* nalo_last_error(const nalo_ctx* ctx); /* ctx may be NULL: last creation error */
+int nalo_set_params(nalo_ctx* ctx, const NaloParams* p);
+int nalo_get_params(const nalo_ctx* ctx, NaloParams* p);
+int nalo_sync(nalo_ctx* ctx);            /* cudaStreamSynchronize on the context stream */
+void* nalo_stream(nalo_ctx* ctx);        /* the context's cudaStream_t (for event timing by the caller) */
+long long nalo_kernel_launches(const nalo_ctx* ctx); /* kernels launched so far by this context */
+void* nalo_host_alloc(size_t bytes);     /* pinned host memory (cudaHostAlloc) */
+void nalo_host_free(void* p);
+/* Write `bytes` of a scratch buffer larger than L2 (bench hygiene: cold-L2 timing). */
+int nalo_flush_l2(nalo_ctx* ctx);
+
+/* ---- a1: FrameHessian::makeImages (FullSystem/HessianBlocks.cpp:127-190) ------------------------------- */
+/* Builds pyramid + gradients + absSquaredGrad of `color` into frame slot `slot`.
+ * B256: CalibHessian::B (HessianBlocks.h:399) or NULL (= HCalib==0 / setting_gammaWeightsPixelSelect!=1).
+ * dIp_host / absgrad_host (nullable): host copies in the reference layout, all levels concatenated:
+ * dIp = AoS {I,dx,dy} (Eigen::Vector3f), absgrad = float. */
+int nalo_make_images(nalo_ctx* ctx, int slot, const float* color_host, const float* B256, float* dIp_host, float* absgrad_host);
+int nalo_make_images_dev(nalo_ctx* ctx, int slot, const float* color_dev, const float* B256_host);
+int nalo_get_frame(nalo_ctx* ctx, int slot, float* dIp_host, float* absgrad_host);
+
+/* ---- a2-a4: PixelSelector (FullSystem/PixelSelector2.cpp) ---------------------------------------------- */
+/* makeMaps (:144-291). currentPotential is PixelSelector::currentPotential (state carried frame to frame,
+ * initial value 3). map_out: float[w*h] in {0,1,2,4}. Returns the count in *n_out. */
+int nalo_select_pixels(nalo_ctx* ctx, int slot, float density, int recursionsLeft, float thFactor, int* currentPotential_inout,
+                       float* map_out_host, int* n_out);
+/* parity hooks: makeHists (:78-143) and select (:564-707) */
+int nalo_selector_make_hists(nalo_ctx* ctx, int slot, float* ths_out, float* thsSmoothed_out, int* n_blocks_out);
+int nalo_selector_select(nalo_ctx* ctx, int slot, int pot, float thFactor, float* map_out_host, int n3_out[3]);
+
+/* ---- makeK + a5: CoarseTracker::makeK (:116-145), setCoarseTrackingRef/makeCoarseDepthL0 (:382-538,1053-1067) */
+int nalo_make_k(nalo_ctx* ctx, int trk, float fx, float fy, float cx, float cy);
+int nalo_get_k(nalo_ctx* ctx, int trk, float* out13_per_level); /* fx,fy,cx,cy,Ki[9] per level */
+/* step 1 from a sparse list: (u,v,idepth) = PointFrameResidual::centerProjectedTo, hdi = EFPoint::HdiF. */
+int nalo_set_ref_sparse(nalo_ctx* ctx, int trk, int ref_slot, int n, const float* u, const float* v, const float* idepth,
+                        const float* hdi, const double aff_ref[2], float exposure_ref);
+/* dense mode (north-star definition): level-0 sum(idepth*weight) and weight maps. */
+int nalo_set_ref_dense(nalo_ctx* ctx, int trk, int ref_slot, const float* idw0_host, const float* wsum0_host,
+                       const double aff_ref[2], float exposure_ref);
+int nalo_get_ref_count(nalo_ctx* ctx, int trk, int lvl, int* n_out);                     /* pc_n[lvl] */
+int nalo_get_ref_points(nalo_ctx* ctx, int trk, int lvl, float* u, float* v, float* idepth, float* color);
+int nalo_get_ref_depth_maps(nalo_ctx* ctx, int trk, int lvl, float* idepth, float* weightSums);
+
+/* ---- a6/a7 parity hooks: calcRes (:891-1049) and calcGSSSE (:828-885), fused on the device ------------- */
+int nalo_set_new_frame(nalo_ctx* ctx, int trk, int new_slot, float exposure_new);
+/* out6 = Vec6 {E, numTermsInE, shiftT, 0, shiftRT, saturatedRatio}. mask (nullable): pc_n[lvl] bytes,
+ * bit0 = counted in E (projection valid), bit1 = kept in buf_warped (|r| <= cutoff). */
+int nalo_calc_res(nalo_ctx* ctx, int trk, int lvl, const double pose7[7], const double aff2[2], float cutoffTH, double out6[6],
+                  uint8_t* mask_host);
+/* H (8x8 row-major) and b of the evaluation at (pose, aff) with the cutoff of the last nalo_calc_res. */
+int nalo_calc_gs(nalo_ctx* ctx, int trk, int lvl, const double pose7[7], const double aff2[2], double H64[64], double b8[8]);
+
+/* ---- a8: CoarseTracker::trackNewestCoarse (:1073-1259) ------------------------------------------------- */
+/* pose/aff are in-out and written exactly when the reference writes lastToNew_out / aff_g2l_out.
+ * lastRes5 = CoarseTracker::lastResiduals (NaN where not reached), flow3 = lastFlowIndicators. *ok = return value. */
+int nalo_track(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, double pose7_inout[7], double aff2_inout[2],
+               int coarsestLvl, const double minResForAbort5[5], double lastRes5[5], double flow3[3], int* ok,
+               NaloTrackStats* stats /* nullable */);
+
+/* ---- a11: FullSystem::trackNewCoarse (FullSystem.cpp:502-699) ------------------------------------------ */
+/* candidate list (:516-580) from camToWorld of sprelast, slast and the reference KF; returns count in *n_out (<=31) */
+int nalo_motion_candidates(const double sprelast_c2w[7], const double slast_c2w[7], const double lastF_c2w[7], int posesValid,
+                           double* tries_out /* [31][7] */, int* n_out);
+/* Tracks all nHyp candidates concurrently on this GPU (no abort thresholds) and records, per candidate, the
+ * residual after every level pass so the sequential winner rule can be replayed exactly.
+ * pass_lvl/pass_res: [nHyp][6] (level index or -1, sqrt(E/n)); poses/affs in-out per candidate. */
+int nalo_track_multi(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, int nHyp, double* poses7_inout, double* affs2_inout,
+                     int coarsestLvl, int* ok_out, double* lastRes5_out, double* flow3_out, int* pass_lvl_out, double* pass_res_out,
+                     NaloTrackStats* stats);
+/* Winner rule (:583-666) replayed in index order over gathered per-candidate results (pure host function). */
+int nalo_winner_rule(int nHyp, const double* poses7, const double* affs2, const int* ok, const double* flow3, const int* pass_lvl,
+                     const double* pass_res, const double aff_last[2], const double first_try_pose7[7], double lastCoarseRMSE5_inout[5],
+                     float reTrackThreshold, double pose_out7[7], double aff_out2[2], double flow_out3[3], double achievedRes5[5],
+                     int* tries_used, int* haveOneGood);
+
+/* ---- batched independent frame-pair alignments (BASELINE.json config 5) -------------------------------- */
+typedef struct nalo_batch nalo_batch;
+int nalo_batch_create(nalo_ctx* ctx, int capacity, nalo_batch** out);
+int nalo_batch_destroy(nalo_batch* b);
+/* Pair i: reference image + dense level-0 maps + new image (host pointers), intrinsics, reference affine/exposures. */
+int nalo_batch_set_pair(nalo_batch* b, int i, const float* ref_color, const float* idw0, const float* wsum0, const float* new_color,
+                        float fx, float fy, float cx, float cy);
+/* Same, but the pair is synthesised on the device from an analytic scene (bench utility; see synth.py). */
+int nalo_batch_synth_pair(nalo_batch* b, int i, const double* scene_params, int n_scene_params, const double pose_gt7[7],
+                          const double aff_gt2[2], float keep_tau);
+int nalo_batch_track(nalo_batch* b, int first, int count, double* poses7_inout, double* affs2_inout, int coarsestLvl, int* ok_out,
+                     double* lastRes5_out, NaloTrackStats* stats);
+/* device-resident results of the last nalo_batch_track: float64 [count][16] = ok,pose7,aff2,lastRes5,pad (for NCCL gather) */
+void* nalo_batch_results_dev(nalo_batch* b);
+
+/* ---- a9/a10: windowed-BA accumulators ------------------------------------------------------------------
+ * Flattened EnergyFunctional graph. One record per residual (RawResidualJacobian.h:32-61 + EFResidual indices),
+ * 76 32-bit words:
+ *   0..7 resF | 8..19 Jpdxi[2][6] | 20..27 Jpdc[2][4] | 28..29 Jpdd | 30..45 JIdx[2][8] | 46..61 JabF[2][8]
+ *   62..64 JIdx2 (00,01,11) | 65..68 JabJIdx (00,01,10,11) | 69..71 Jab2 (00,01,11)
+ *   72 int32 point index | 73 uint32 host | target<<8 | flags<<16 (bit0 isActive, bit1 isLinearized) | 74,75 zero
+ * Records are sorted by bucket htIDX = host + target*nf; bucket_begin[nf*nf+1] are record offsets.
+ * pt_begin[nPts+1] / pt_res[] list each point's records in EFPoint::residualsAll order. */
+typedef struct NaloBAProblem {
+  int nf, n_pts, n_res;
+  const float* rec;          /* [n_res][76] host */
+  const float* res_toZero;   /* [n_res][8]  host (modes 1,2; may be NULL for mode 0) */
+  const int* bucket_begin;   /* [nf*nf+1] */
+  const int* pt_begin;       /* [n_pts+1] */
+  const int* pt_res;         /* [pt_begin[n_pts]] */
+  const float* deltaF;       /* [n_pts]  EFPoint::deltaF */
+  const float* priorF;       /* [n_pts]  EFPoint::priorF */
+  const float* adHTdeltaF;   /* [nf*nf][8] EnergyFunctional::adHTdeltaF */
+  const float* cDeltaF;      /* [4] */
+} NaloBAProblem;
+typedef struct nalo_ba nalo_ba;
+int nalo_ba_create(nalo_ctx* ctx, int max_res, int max_pts, nalo_ba** out);
+int nalo_ba_destroy(nalo_ba* ba);
+/* Upload (H2D) the flattened problem; device copies stay resident for the accumulate calls. */
+int nalo_ba_upload(nalo_ba* ba, const NaloBAProblem* p);
+/* AccumulatedTopHessianSSE::addPoint<mode> over all points (AccumulatedTopHessian.cpp:39-162).
+ * H_out: [nf*nf][13*13] double (what stitchDoubleInternal calls accH), perPoint: [n_pts][6] {Hdd,bd,Hcd[4]}. */
+int nalo_ba_accumulate_top(nalo_ba* ba, int mode, double* H_out, float* perPoint_out, int* nres_out);
+/* EFResidual::takeDataF (EnergyFunctionalStructs.cpp:39-50): JpJdF from the records, kept on the device. */
+int nalo_ba_take_data(nalo_ba* ba, float* JpJdF_out /* nullable [n_res][8] */);
+/* AccumulatedSCHessianSSE::addPoint over all points (AccumulatedSCHessian.cpp:34-77) using the per-point sums
+ * of the last mode-0 (A) and mode-1/2 (L, optional) top accumulations held on the device. */
+int nalo_ba_accumulate_sc(nalo_ba* ba, int shiftPriorToZero, int useL, double* accD, double* accE, double* accEB, double* accHcc,
+                          double* accbc, float* perPoint_out /* [n_pts][3] HdiF,bdSumF,idepth_hessian */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NALO_GPU_H_ */

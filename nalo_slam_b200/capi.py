@@ -1,0 +1,355 @@
+"""ctypes binding of the C ABI in include/nalo_gpu.h (libnalo_gpu.so, hand-written CUDA for sm_100a).
+
+This is the only way the Python host mirror reaches the device code. There is deliberately NO CPU fallback:
+if the shared library is missing `load()` raises, and if there is no CUDA device `Context()` raises with the
+library's own error text (NALO_E_NODEVICE).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnalo_gpu.so")
+_P = C.c_void_p
+_f32 = np.float32
+
+NALO_OK, NALO_E_CUDA, NALO_E_ARG, NALO_E_STATE, NALO_E_NODEVICE = 0, -1, -2, -3, -4
+BA_RECORD_WORDS = 76
+
+
+class NaloError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"nalo error {code}: {msg}")
+        self.code = code
+
+
+class NaloParams(C.Structure):
+    _fields_ = [
+        ("huberTH", C.c_float),
+        ("coarseCutoffTH", C.c_float),
+        ("affineOptModeA", C.c_float),
+        ("affineOptModeB", C.c_float),
+        ("minGradHistCut", C.c_float),
+        ("minGradHistAdd", C.c_float),
+        ("gradDownweightPerLevel", C.c_float),
+        ("selectDirectionDistribution", C.c_int),
+        ("reTrackThreshold", C.c_float),
+    ]
+
+
+class NaloTrackStats(C.Structure):
+    _fields_ = [("residuals", C.c_longlong), ("evals", C.c_int), ("iters", C.c_int), ("launches", C.c_int)]
+
+
+class NaloBAProblem(C.Structure):
+    _fields_ = [
+        ("nf", C.c_int),
+        ("n_pts", C.c_int),
+        ("n_res", C.c_int),
+        ("rec", _P),
+        ("res_toZero", _P),
+        ("bucket_begin", _P),
+        ("pt_begin", _P),
+        ("pt_res", _P),
+        ("deltaF", _P),
+        ("priorF", _P),
+        ("adHTdeltaF", _P),
+        ("cDeltaF", _P),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load libnalo_gpu.so; raise if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built and there is no CPU fallback. "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'` at the repo root."
+            )
+        L = C.CDLL(LIB_PATH)
+        L.nalo_last_error.restype = C.c_char_p
+        L.nalo_last_error.argtypes = [_P]
+        L.nalo_version.restype = C.c_char_p
+        L.nalo_stream.restype = _P
+        L.nalo_stream.argtypes = [_P]
+        L.nalo_kernel_launches.restype = C.c_longlong
+        L.nalo_kernel_launches.argtypes = [_P]
+        L.nalo_host_alloc.restype = _P
+        L.nalo_host_alloc.argtypes = [C.c_size_t]
+        L.nalo_host_free.argtypes = [_P]
+        L.nalo_batch_results_dev.restype = _P
+        L.nalo_batch_results_dev.argtypes = [_P]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return _P(a)
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_P)
+
+
+def pinned_array(shape, dtype=np.float32):
+    """numpy array backed by cudaHostAlloc'ed (pinned) memory; keeps the allocation alive via .base chain."""
+    L = load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = L.nalo_host_alloc(C.c_size_t(max(n, 16)))
+    if not p:
+        raise MemoryError("nalo_host_alloc failed")
+    buf = (C.c_char * n).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                L.nalo_host_free(_P(self.ptr))
+            except Exception:
+                pass
+
+    _pinned_owners[id(buf)] = (_Owner(p), buf)
+    return arr
+
+
+_pinned_owners = {}
+
+
+def default_params() -> NaloParams:
+    p = NaloParams()
+    load().nalo_default_params(C.byref(p))
+    return p
+
+
+class Context:
+    """One nalo_ctx: a CUDA stream, `max_frames` frame slots and two tracker states on one GPU."""
+
+    def __init__(self, w, h, levels=5, device=0, max_frames=4):
+        self.L = load()
+        self.w, self.h, self.levels = w, h, levels
+        self.sizes = [(w >> l, h >> l) for l in range(levels)]
+        self.tot = sum(a * b for a, b in self.sizes)
+        self.dense_off = np.cumsum([0] + [a * b for a, b in self.sizes])[:-1].tolist()
+        h_ = _P()
+        rc = self.L.nalo_create(C.c_int(w), C.c_int(h), C.c_int(levels), C.c_int(device), C.c_int(max_frames), C.byref(h_))
+        if rc != NALO_OK:
+            raise NaloError(rc, self.L.nalo_last_error(None).decode())
+        self.h_ = h_
+
+    def close(self):
+        if getattr(self, "h_", None):
+            self.L.nalo_destroy(self.h_)
+            self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != NALO_OK:
+            raise NaloError(rc, self.L.nalo_last_error(self.h_).decode())
+
+    # ---- params / plumbing
+    def get_params(self) -> NaloParams:
+        p = NaloParams()
+        self._ck(self.L.nalo_get_params(self.h_, C.byref(p)))
+        return p
+
+    def set_params(self, **kw):
+        p = self.get_params()
+        for k, v in kw.items():
+            setattr(p, k, v)
+        self._ck(self.L.nalo_set_params(self.h_, C.byref(p)))
+
+    def sync(self):
+        self._ck(self.L.nalo_sync(self.h_))
+
+    def stream(self) -> int:
+        return int(self.L.nalo_stream(self.h_) or 0)
+
+    def kernel_launches(self) -> int:
+        return int(self.L.nalo_kernel_launches(self.h_))
+
+    def flush_l2(self):
+        self._ck(self.L.nalo_flush_l2(self.h_))
+
+    # ---- a1
+    def make_images(self, slot, color, B256=None, want_host=False):
+        color = np.ascontiguousarray(color, dtype=_f32).reshape(-1)
+        assert color.size == self.w * self.h
+        B = None if B256 is None else np.ascontiguousarray(B256, dtype=_f32)
+        if want_host:
+            dIp = np.zeros((self.tot, 3), dtype=_f32)
+            ag = np.zeros(self.tot, dtype=_f32)
+            self._ck(self.L.nalo_make_images(self.h_, C.c_int(slot), _ptr(color), _ptr(B), _ptr(dIp), _ptr(ag)))
+            return dIp, ag
+        self._ck(self.L.nalo_make_images(self.h_, C.c_int(slot), _ptr(color), _ptr(B), None, None))
+        return None
+
+    def make_images_dev(self, slot, color_dev_ptr, B256=None):
+        B = None if B256 is None else np.ascontiguousarray(B256, dtype=_f32)
+        self._ck(self.L.nalo_make_images_dev(self.h_, C.c_int(slot), _P(color_dev_ptr), _ptr(B)))
+
+    def get_frame(self, slot):
+        dIp = np.zeros((self.tot, 3), dtype=_f32)
+        ag = np.zeros(self.tot, dtype=_f32)
+        self._ck(self.L.nalo_get_frame(self.h_, C.c_int(slot), _ptr(dIp), _ptr(ag)))
+        return dIp, ag
+
+    # ---- a2-a4
+    def select_pixels(self, slot, density, currentPotential, recursionsLeft=1, thFactor=1.0):
+        m = np.zeros(self.w * self.h, dtype=_f32)
+        pot = C.c_int(currentPotential)
+        n = C.c_int(0)
+        self._ck(self.L.nalo_select_pixels(self.h_, C.c_int(slot), C.c_float(density), C.c_int(recursionsLeft), C.c_float(thFactor), C.byref(pot), _ptr(m), C.byref(n)))
+        return n.value, m, pot.value
+
+    def selector_make_hists(self, slot):
+        cap = (self.w // 32) * (self.h // 32) + 100 + self.w  # generous
+        ths = np.zeros(cap, dtype=_f32)
+        thsS = np.zeros(cap, dtype=_f32)
+        nb = C.c_int(0)
+        self._ck(self.L.nalo_selector_make_hists(self.h_, C.c_int(slot), _ptr(ths), _ptr(thsS), C.byref(nb)))
+        return ths[: nb.value], thsS[: nb.value]
+
+    def selector_select(self, slot, pot, thFactor=1.0):
+        m = np.zeros(self.w * self.h, dtype=_f32)
+        n3 = np.zeros(3, dtype=np.int32)
+        self._ck(self.L.nalo_selector_select(self.h_, C.c_int(slot), C.c_int(pot), C.c_float(thFactor), _ptr(m), _ptr(n3)))
+        return m, n3
+
+    # ---- makeK + a5
+    def make_k(self, trk, fx, fy, cx, cy):
+        self._ck(self.L.nalo_make_k(self.h_, C.c_int(trk), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy)))
+
+    def get_k(self, trk):
+        out = np.zeros((self.levels, 13), dtype=_f32)
+        self._ck(self.L.nalo_get_k(self.h_, C.c_int(trk), _ptr(out)))
+        return out
+
+    def set_ref_sparse(self, trk, ref_slot, u, v, idepth, hdi, aff=(0.0, 0.0), exposure=1.0):
+        u, v, idepth, hdi = (np.ascontiguousarray(a, dtype=_f32) for a in (u, v, idepth, hdi))
+        a2 = np.array(aff, dtype=np.float64)
+        self._ck(self.L.nalo_set_ref_sparse(self.h_, C.c_int(trk), C.c_int(ref_slot), C.c_int(u.size), _ptr(u), _ptr(v), _ptr(idepth), _ptr(hdi), _ptr(a2), C.c_float(exposure)))
+
+    def set_ref_dense(self, trk, ref_slot, idw0, wsum0, aff=(0.0, 0.0), exposure=1.0):
+        idw0 = np.ascontiguousarray(idw0, dtype=_f32).reshape(-1)
+        wsum0 = np.ascontiguousarray(wsum0, dtype=_f32).reshape(-1)
+        a2 = np.array(aff, dtype=np.float64)
+        self._ck(self.L.nalo_set_ref_dense(self.h_, C.c_int(trk), C.c_int(ref_slot), _ptr(idw0), _ptr(wsum0), _ptr(a2), C.c_float(exposure)))
+
+    def ref_count(self, trk, lvl):
+        n = C.c_int(0)
+        self._ck(self.L.nalo_get_ref_count(self.h_, C.c_int(trk), C.c_int(lvl), C.byref(n)))
+        return n.value
+
+    def ref_points(self, trk, lvl):
+        n = self.ref_count(trk, lvl)
+        arrs = [np.zeros(max(n, 1), dtype=_f32) for _ in range(4)]
+        self._ck(self.L.nalo_get_ref_points(self.h_, C.c_int(trk), C.c_int(lvl), *[_ptr(a) for a in arrs]))
+        return [a[:n] for a in arrs]
+
+    def ref_depth_maps(self, trk, lvl):
+        w, h = self.sizes[lvl]
+        a = np.zeros(w * h, dtype=_f32)
+        b = np.zeros(w * h, dtype=_f32)
+        self._ck(self.L.nalo_get_ref_depth_maps(self.h_, C.c_int(trk), C.c_int(lvl), _ptr(a), _ptr(b)))
+        return a, b
+
+    # ---- a6/a7 hooks
+    def set_new_frame(self, trk, slot, exposure=1.0):
+        self._ck(self.L.nalo_set_new_frame(self.h_, C.c_int(trk), C.c_int(slot), C.c_float(exposure)))
+
+    def calc_res(self, trk, lvl, pose7, aff2, cutoffTH, want_mask=True):
+        pose7 = np.ascontiguousarray(pose7, dtype=np.float64)
+        aff2 = np.ascontiguousarray(aff2, dtype=np.float64)
+        out = np.zeros(6)
+        n = self.ref_count(trk, lvl)
+        mask = np.zeros(max(n, 1), dtype=np.uint8) if want_mask else None
+        self._ck(self.L.nalo_calc_res(self.h_, C.c_int(trk), C.c_int(lvl), _ptr(pose7), _ptr(aff2), C.c_float(cutoffTH), _ptr(out), _ptr(mask)))
+        return out, (mask[:n] if want_mask else None)
+
+    def calc_gs(self, trk, lvl, pose7, aff2):
+        pose7 = np.ascontiguousarray(pose7, dtype=np.float64)
+        aff2 = np.ascontiguousarray(aff2, dtype=np.float64)
+        H = np.zeros((8, 8))
+        b = np.zeros(8)
+        self._ck(self.L.nalo_calc_gs(self.h_, C.c_int(trk), C.c_int(lvl), _ptr(pose7), _ptr(aff2), _ptr(H), _ptr(b)))
+        return H, b
+
+    # ---- a8
+    def track(self, trk, new_slot, pose7, aff2, coarsestLvl=None, minRes=None, exposure=1.0):
+        pose = np.array(pose7, dtype=np.float64)
+        aff = np.array(aff2, dtype=np.float64)
+        if coarsestLvl is None:
+            coarsestLvl = min(self.levels, 5) - 1
+        mr = np.full(5, np.nan) if minRes is None else np.ascontiguousarray(minRes, dtype=np.float64)
+        lr = np.zeros(5)
+        fl = np.zeros(3)
+        ok = C.c_int(0)
+        st = NaloTrackStats()
+        self._ck(self.L.nalo_track(self.h_, C.c_int(trk), C.c_int(new_slot), C.c_float(exposure), _ptr(pose), _ptr(aff), C.c_int(coarsestLvl), _ptr(mr), _ptr(lr), _ptr(fl), C.byref(ok), C.byref(st)))
+        return bool(ok.value), pose, aff, lr, fl, dict(residuals=st.residuals, evals=st.evals, iters=st.iters, launches=st.launches)
+
+    # ---- a11
+    def track_multi(self, trk, new_slot, poses7, affs2, coarsestLvl=None, exposure=1.0):
+        poses = np.ascontiguousarray(poses7, dtype=np.float64).copy()
+        n = poses.shape[0]
+        affs = np.ascontiguousarray(affs2, dtype=np.float64).copy()
+        if coarsestLvl is None:
+            coarsestLvl = min(self.levels, 5) - 1
+        ok = np.zeros(n, dtype=np.int32)
+        lr = np.zeros((n, 5))
+        fl = np.zeros((n, 3))
+        pl = np.zeros((n, 6), dtype=np.int32)
+        pr = np.zeros((n, 6))
+        st = NaloTrackStats()
+        self._ck(self.L.nalo_track_multi(self.h_, C.c_int(trk), C.c_int(new_slot), C.c_float(exposure), C.c_int(n), _ptr(poses), _ptr(affs), C.c_int(coarsestLvl), _ptr(ok), _ptr(lr), _ptr(fl), _ptr(pl), _ptr(pr), C.byref(st)))
+        return dict(ok=ok, poses=poses, affs=affs, lastRes=lr, flow=fl, pass_lvl=pl, pass_res=pr,
+                    stats=dict(residuals=st.residuals, evals=st.evals, iters=st.iters, launches=st.launches))
+
+
+def motion_candidates(sprelast_c2w, slast_c2w, lastF_c2w, poses_valid=True):
+    L = load()
+    out = np.zeros((31, 7))
+    a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (sprelast_c2w, slast_c2w, lastF_c2w))
+    n = C.c_int(0)
+    rc = L.nalo_motion_candidates(_ptr(a), _ptr(b), _ptr(c), C.c_int(1 if poses_valid else 0), _ptr(out), C.byref(n))
+    if rc != NALO_OK:
+        raise NaloError(rc, "nalo_motion_candidates")
+    return out[: n.value].copy()
+
+
+def winner_rule(res, aff_last, lastCoarseRMSE, reTrackThreshold=1.5, first_try=None):
+    """Replay FullSystem::trackNewCoarse's sequential winner rule over the results of Context.track_multi."""
+    L = load()
+    n = res["poses"].shape[0]
+    rmse = np.array(lastCoarseRMSE, dtype=np.float64)
+    aff_last = np.ascontiguousarray(aff_last, dtype=np.float64)
+    ft = np.ascontiguousarray(first_try if first_try is not None else res["poses"][0], dtype=np.float64)
+    pose = np.zeros(7)
+    aff = np.zeros(2)
+    flow = np.zeros(3)
+    ach = np.zeros(5)
+    used = C.c_int(0)
+    good = C.c_int(0)
+    rc = L.nalo_winner_rule(
+        C.c_int(n), _ptr(res["poses"]), _ptr(res["affs"]), _ptr(res["ok"]), _ptr(res["flow"]), _ptr(res["pass_lvl"]), _ptr(res["pass_res"]),
+        _ptr(aff_last), _ptr(ft), _ptr(rmse), C.c_float(reTrackThreshold), _ptr(pose), _ptr(aff), _ptr(flow), _ptr(ach), C.byref(used), C.byref(good),
+    )
+    if rc != NALO_OK:
+        raise NaloError(rc, "nalo_winner_rule")
+    return dict(good=bool(good.value), pose=pose, aff=aff, flow=flow, achievedRes=ach, lastCoarseRMSE=rmse, tries=used.value)

@@ -1,0 +1,154 @@
+// nalo_common.cuh — shared declarations of libnalo_gpu.so (sm_100a only; no CPU fallback).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nalo_gpu.h"
+
+#define NALO_NPART 52        // words of one block partial: 45 H/b/rr + E + flowT + flowRT + 4 ints
+#define NALO_TRACK_THREADS 512
+#define NALO_PIX_ALIGN 32    // level offsets (in pixels) are multiples of this => 512-byte aligned float4 rows
+
+struct NaloLevelGeom {
+  int w, h;
+  int off;      // pixel offset of the level inside a frame buffer
+  float fx, fy, cx, cy;
+  float Ki[9];  // row-major inverse intrinsics
+};
+
+// Device image pyramid of one frame: float4 per pixel {I, dx, dy, absSquaredGrad}.
+struct NaloFrame {
+  float4* pix = nullptr;
+  bool valid = false;
+};
+
+struct NaloTrackerState {
+  bool haveK = false, haveRef = false;
+  NaloLevelGeom geom[NALO_MAX_LEVELS];
+  float4* pts[NALO_MAX_LEVELS] = {};   // ref point cloud {u,v,idepth,color}, capacity w_l*h_l
+  int pc_n[NALO_MAX_LEVELS] = {};
+  float* idepth[NALO_MAX_LEVELS] = {};      // makeCoarseDepthL0 grids
+  float* weightSums[NALO_MAX_LEVELS] = {};
+  double refAff[2] = {0, 0};
+  float refExposure = 1.f;
+  int refSlot = -1;
+  int newSlot = -1;
+  float newExposure = 1.f;
+  float lastCutoff = 20.f;
+};
+
+// One alignment problem as the tracking kernel sees it.
+struct NaloTrackProblem {
+  const float4* pts[NALO_TRACK_LEVELS];
+  int n[NALO_TRACK_LEVELS];
+  const float4* img;  // new-frame pyramid
+  NaloLevelGeom geom[NALO_TRACK_LEVELS];
+  double pose[7];
+  double aff[2];
+  double minRes[NALO_TRACK_LEVELS];
+  double refAff[2];
+  float refExposure, newExposure;
+  int coarsestLvl;
+  int useAbort;  // 0: never abort on minRes (multi-hypothesis / batch mode)
+};
+
+struct NaloTrackResult {
+  int ok;
+  int nPass;
+  double pose[7];
+  double aff[2];
+  double lastRes[NALO_TRACK_LEVELS];
+  double flow[3];
+  int passLvl[6];
+  double passRes[6];
+  long long residuals;
+  int evals;
+  int iters;
+};
+
+struct NaloSettingsDev {
+  float huberTH, coarseCutoffTH, affineOptModeA, affineOptModeB;
+};
+
+struct nalo_ctx {
+  int device = 0;
+  int w0 = 0, h0 = 0, levels = 0, maxFrames = 0;
+  int lw[NALO_MAX_LEVELS], lh[NALO_MAX_LEVELS], loff[NALO_MAX_LEVELS];
+  int totPix = 0;     // padded pixel count of one pyramid
+  int totPixDense = 0;  // unpadded (reference concatenation)
+  int denseOff[NALO_MAX_LEVELS];
+  int numSMs = 0;
+  cudaStream_t stream = nullptr;
+  NaloParams params;
+  std::vector<NaloFrame> frames;
+  NaloTrackerState trk[NALO_MAX_TRACKERS];
+  // scratch
+  float* d_color = nullptr;        // w0*h0 staging of the input image
+  float* d_B = nullptr;            // 256 floats
+  float* d_stage = nullptr;        // 4 floats per dense pixel: host-layout staging (dIp AoS + absgrad)
+  void* d_flush = nullptr;         // L2 flush buffer
+  size_t flushBytes = 0;
+  // tracking workspace
+  NaloTrackProblem* d_problems = nullptr;
+  NaloTrackResult* d_results = nullptr;
+  NaloTrackProblem* h_problems = nullptr;  // pinned
+  NaloTrackResult* h_results = nullptr;    // pinned
+  float* d_partials = nullptr;
+  unsigned long long* d_barriers = nullptr;
+  int maxGroups = 0;
+  int trackBlocksPerSM = 1;
+  uint8_t* d_mask = nullptr;      // w0*h0 bytes
+  uint8_t* d_mask_all = nullptr;  // totPixDense bytes (per-pixel validity flags of every level)
+  float* d_ptlist = nullptr;      // 4*w0*h0 floats: sparse reference list staging
+  int* d_owner = nullptr;         // w0*h0 ints
+  int* d_scan = nullptr;      // compaction scratch
+  int* d_counts = nullptr;    // small int scratch (device)
+  int* h_counts = nullptr;    // pinned
+  // selector state
+  uint8_t* d_randomPattern = nullptr;
+  float* d_ths = nullptr;
+  float* d_thsSmoothed = nullptr;
+  int thsCap = 0;
+  int histFrameSlot = -1;
+  float* d_map = nullptr;
+  int* d_selScratch = nullptr;
+  size_t selScratchInts = 0;
+  long long launches = 0;
+  std::string err;
+};
+
+extern std::string g_nalo_create_error;
+
+int nalo_fail(nalo_ctx* ctx, int code, const char* fmt, ...);
+
+#define NALO_CUDA(ctx, call)                                                                           \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess) return nalo_fail(ctx, NALO_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                                             cudaGetErrorString(e__));                                 \
+  } while (0)
+
+#define NALO_CHECK_LAUNCH(ctx)                                                                     \
+  do {                                                                                             \
+    (ctx)->launches++;                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess) return nalo_fail(ctx, NALO_E_CUDA, "%s:%d launch: %s", __FILE__, __LINE__, \
+                                             cudaGetErrorString(e__));                             \
+  } while (0)
+
+// internal cross-file entry points
+int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float* B256_host);
+int nalo_images_to_host(nalo_ctx* ctx, int slot, float* dIp_host, float* absgrad_host);
+int nalo_depth_finish(nalo_ctx* ctx, int trk, int ref_slot);
+int nalo_track_init(nalo_ctx* ctx);
+void nalo_track_free(nalo_ctx* ctx);
+int nalo_select_init(nalo_ctx* ctx);
+void nalo_select_free(nalo_ctx* ctx);
+void nalo_fill_problem(nalo_ctx* ctx, int trk, NaloTrackProblem* P);
+int nalo_track_launch(nalo_ctx* ctx, int nProblems, int blocksPerProblem, const NaloTrackProblem* d_problems, NaloTrackResult* d_results);

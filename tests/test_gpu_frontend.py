@@ -1,0 +1,98 @@
+"""GPU parity: a1 makeImages and a5 makeCoarseDepthL0 through the C ABI vs the CPU oracle (bit-exact)."""
+import numpy as np
+import pytest
+
+from conftest import make_oracle_tracker
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.mark.parametrize("which", ["small", "kitti"])
+def test_make_images_bit_exact(which, request, oracle):
+    P = request.getfixturevalue(f"{which}_pair")
+    ctx = request.getfixturevalue(f"gpu_ctx_{which}")
+    dIp, ag = ctx.make_images(0, P["ref"], want_host=True)
+    assert np.array_equal(_bits(dIp), _bits(P["dref"]))
+    assert np.array_equal(_bits(ag), _bits(P["agref"]))
+
+
+def test_make_images_gamma_weights(small_pair, gpu_ctx_small, oracle):
+    P = small_pair
+    B = (np.arange(256, dtype=np.float32) ** 1.1).astype(np.float32)
+    dIp, ag = gpu_ctx_small.make_images(2, P["new"], B256=B, want_host=True)
+    o_d, o_ag = oracle.make_images(P["new"], P["w"], P["h"], P["L"], B256=B)
+    assert np.array_equal(_bits(dIp), _bits(o_d))
+    assert np.array_equal(_bits(ag), _bits(o_ag))
+
+
+def test_make_images_nonfinite(small_pair, gpu_ctx_small, oracle):
+    P = small_pair
+    img = P["ref"].copy()
+    img[50, 60] = np.nan
+    img[100, 200] = np.inf
+    dIp, ag = gpu_ctx_small.make_images(2, img, want_host=True)
+    o_d, o_ag = oracle.make_images(img, P["w"], P["h"], P["L"])
+    assert np.array_equal(_bits(dIp), _bits(o_d))
+    assert np.array_equal(_bits(ag), _bits(o_ag))
+
+
+@pytest.mark.parametrize("which", ["small", "kitti"])
+def test_dense_reference_cloud(which, request, oracle):
+    P = request.getfixturevalue(f"{which}_pair")
+    ctx = request.getfixturevalue(f"gpu_ctx_{which}")
+    T, idw, ws = make_oracle_tracker(oracle, P)
+    ctx.make_images(0, P["ref"])
+    ctx.make_k(0, *P["scene"].K)
+    assert np.array_equal(_bits(ctx.get_k(0)), _bits(T.get_K()))
+    ctx.set_ref_dense(0, 0, idw, ws)
+    for l in range(P["L"]):
+        assert ctx.ref_count(0, l) == T.pc_n(l)
+        for a, b in zip(ctx.ref_points(0, l), T.get_pc(l)):
+            assert np.array_equal(_bits(a), _bits(b))
+        gi, gw = ctx.ref_depth_maps(0, l)
+        oi, ow = T.get_depth_maps(l)
+        assert np.array_equal(_bits(gi), _bits(oi))
+        assert np.array_equal(_bits(gw), _bits(ow))
+
+
+def test_sparse_reference_cloud_with_collisions(small_pair, gpu_ctx_small, oracle):
+    from nalo_slam_b200 import synth
+
+    P = small_pair
+    rng = np.random.default_rng(5)
+    n = 3000
+    u = rng.uniform(3, P["w"] - 4, n).astype(np.float32)
+    v = rng.uniform(3, P["h"] - 4, n).astype(np.float32)
+    # force collisions: many points onto the same pixels, in scrambled order
+    u[:600] = u[600:1200]
+    v[:600] = v[600:1200]
+    u[1200:1300] = 17.2
+    v[1200:1300] = 23.4
+    idp = P["scene"].idepth(u, v).astype(np.float32) * rng.uniform(0.9, 1.1, n).astype(np.float32)
+    hdi = rng.uniform(1e-5, 1e-1, n).astype(np.float32)
+    T = oracle.Tracker(P["w"], P["h"], P["L"])
+    T.makeK(*P["scene"].K)
+    T.set_ref_frame(P["dref"])
+    T.make_depth_sparse(u, v, idp, hdi)
+    ctx = gpu_ctx_small
+    ctx.make_images(0, P["ref"])
+    ctx.make_k(0, *P["scene"].K)
+    ctx.set_ref_sparse(0, 0, u, v, idp, hdi)
+    for l in range(P["L"]):
+        assert ctx.ref_count(0, l) == T.pc_n(l)
+        for a, b in zip(ctx.ref_points(0, l), T.get_pc(l)):
+            assert np.array_equal(_bits(a), _bits(b))
+
+
+def test_empty_reference(small_pair, gpu_ctx_small):
+    P = small_pair
+    ctx = gpu_ctx_small
+    ctx.make_images(0, P["ref"])
+    ctx.make_k(0, *P["scene"].K)
+    z = np.zeros(0, dtype=np.float32)
+    ctx.set_ref_sparse(0, 0, z, z, z, z)
+    assert all(ctx.ref_count(0, l) == 0 for l in range(P["L"]))
