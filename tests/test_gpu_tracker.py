@@ -24,13 +24,32 @@ def _setup(ctx, P, oracle, keep=0.43):
     return T
 
 
-def _check_system(Hg, bg, Ho, bo):
+def _check_system(Hg, bg, Ho, bo, rr_bound):
+    """|dH_ij| <= 1e-4 sqrt(H_ii H_jj) and |db_i| <= 1e-4 sqrt(H_ii * sum(w r^2)/n): relative to the Cauchy-Schwarz
+    bound of each entry, i.e. to the magnitude of the terms that were summed (entries that are small only through
+    cancellation cannot be required to agree to 1e-4 of their own value in fp32)."""
     d = np.sqrt(np.abs(np.diag(Ho)))
     scale = np.outer(d, d)
     assert np.all(np.abs(Hg - Ho) <= H_TOL * scale + 1e-300), np.max(np.abs(Hg - Ho) / scale)
     assert np.allclose(Hg, Hg.T)
-    big = np.abs(bo) > 1e-3 * np.max(np.abs(bo))
-    assert np.all(np.abs(bg - bo)[big] <= H_TOL * np.abs(bo)[big] * 10 + 0) or np.all(np.abs(bg - bo) <= H_TOL * d * np.sqrt(np.abs(Ho).max()))
+    assert np.all(np.abs(bg - bo) <= H_TOL * d * np.sqrt(rr_bound) + 1e-300), np.max(np.abs(bg - bo) / (d * np.sqrt(rr_bound)))
+    # entries that are not cancellation-dominated also agree to 1e-4 of their own value
+    bigH = np.abs(Ho) > 0.1 * scale
+    assert np.all(np.abs(Hg - Ho)[bigH] <= H_TOL * np.abs(Ho)[bigH])
+
+
+def _exact_energy(T, rs_o, cutoff, huber=9.0):
+    """float64 sum of the reference's float32 energy terms (CoarseTracker.cpp:995,1003). The reference adds them
+    sequentially in float32, which at 3.5e5 terms carries up to ~1e-3 relative error; the GPU's tree sum is
+    compared against this exact sum of the very same terms instead."""
+    wb = T.warped()
+    r, hw = wb[5], wb[6]
+    nW = int(np.count_nonzero(hw)) if wb.shape[1] else 0
+    f = np.float32
+    terms = ((hw * r) * r) * (f(2) - hw)
+    n_sat = int(round(rs_o[5] * rs_o[1])) if rs_o[1] > 0 else 0
+    max_energy = f(f(f(2) * f(huber)) * f(cutoff)) - f(huber) * f(huber)
+    return float(np.sum(terms.astype(np.float64)) + float(max_energy) * n_sat), nW
 
 
 @pytest.mark.parametrize("which", ["small", "kitti"])
@@ -54,12 +73,15 @@ def test_calc_res_and_gs_all_levels(which, request, oracle):
                 assert np.array_equal(m_g, m_o), f"mask mismatch lvl {lvl}: {np.count_nonzero(m_g != m_o)}"
                 assert rs_g[1] == rs_o[1]
                 assert rs_g[5] == rs_o[5] or (np.isnan(rs_g[5]) and np.isnan(rs_o[5]))
-                assert abs(rs_g[0] - rs_o[0]) <= 1e-4 * abs(rs_o[0]) + 1e-6
+                E_exact, nW = _exact_energy(T, rs_o, cutoff)
+                assert abs(rs_g[0] - E_exact) <= 2e-6 * abs(E_exact) + 1e-6, (rs_g[0], E_exact, rs_o[0])
+                # the reference's own sequential fp32 sum stays within its n*eps/2 worst-case bound of the same value
+                assert abs(rs_o[0] - E_exact) <= max(rs_o[1], 1) * 6e-8 * abs(E_exact) + 1e-6
                 for k in (2, 4):
                     assert abs(rs_g[k] - rs_o[k]) <= 1e-4 * abs(rs_o[k]) + 1e-9
                 Ho, bo = T.calc_gs(lvl, pose, aff)
                 Hg, bg = ctx.calc_gs(0, lvl, pose, aff)
-                _check_system(Hg, bg, Ho, bo)
+                _check_system(Hg, bg, Ho, bo, rr_bound=E_exact / max(T.warped().shape[1], 1))
 
 
 def test_identity_warp_zero_residual(small_pair, gpu_ctx_small, oracle):
@@ -72,10 +94,14 @@ def test_identity_warp_zero_residual(small_pair, gpu_ctx_small, oracle):
     ctx.make_k(0, *P["scene"].K)
     ctx.set_ref_dense(0, 0, idw, ws)
     ctx.set_new_frame(0, 1)
+    T.set_new_frame(P["dref"])
     rs, mask = ctx.calc_res(0, 0, synth.pose_identity(), [0, 0], 20.0)
-    assert rs[0] == 0.0 and rs[1] > 0 and rs[5] == 0.0
+    rs_o, mask_o = T.calc_res(0, synth.pose_identity(), [0, 0], 20.0)
+    assert np.array_equal(mask, mask_o)
+    # K*Ki*(x,y,1) is only integer up to fp32 rounding, so the interpolated residual is ~1e-5 grey levels, not 0
+    assert rs[1] > 0 and rs[5] == 0.0 and rs[0] / rs[1] < 1e-6 and rs_o[0] / rs_o[1] < 1e-6
     H, b = ctx.calc_gs(0, 0, synth.pose_identity(), [0, 0])
-    assert np.all(b == 0.0)
+    assert np.all(np.abs(b) <= 1e-3 * np.sqrt(np.diag(H)))
     assert np.all(np.linalg.eigvalsh(H) > -1e-9 * np.abs(H).max())
 
 
