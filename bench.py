@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the photometric-alignment hot path (BASELINE.json configs[1]).
+
+A "step" is one pass of the per-frame hot path over one synthetic KITTI-shaped frame:
+    FrameHessian::makeImages(new 1241x376 image, 5 levels)  +  CoarseTracker::trackNewestCoarse (dense=1 cloud,
+    1 hypothesis, initial pose = identity), reference already set (one dense keyframe).
+Metric: residuals/s = reference points evaluated by calcRes (valid or not) per second, whole job; the line also
+carries ms_per_frame and gn_iters_per_s (the other two figures BASELINE.json's metric names).
+
+  value : inputs resident in HBM (device image), CUDA-event time on the library's stream, L2 flushed between steps.
+  e2e   : same step through the C ABI with the image in pinned HOST memory (H2D inside the timed region, pose
+          read back to the host), wall clock.
+  roofline : tracking kernel, algorithmic bytes sum_l evals_l*(16 N_l + 12 w_l h_l) / device time of the kernel.
+  cpu_baseline : the CPU oracle (restatement of the reference; the reference itself cannot be compiled here) on
+          1 host core, bounded sample, rank 0 at N=1 only.
+
+--impl reference : the CPU oracle on all host cores (one frame per core at a time), same metric/config.
+N>1 (torchrun): every rank runs the same per-GPU workload on its own GPU (independent frame-pair alignments,
+weak scaling) and one NCCL all_gather collects the per-frame results.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from nalo_slam_b200 import synth  # noqa: E402
+
+W, H, LEVELS = synth.KITTI_W, synth.KITTI_H, 5
+N_FRAMES = 8          # distinct new frames cycled through
+KEEP = 0.43           # fraction of level-0 pixels seeded (gradient-bearing), SURVEY.md §8(d) config 2
+METRIC = "dense-track residuals/s @1241x376 5-lvl"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons with NVML during the timed region."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            self.err = str(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_workload(seed=synth.DEFAULT_SEED, n_frames=N_FRAMES):
+    sc = synth.make_scene(W, H, seed=seed)
+    rng = np.random.default_rng(seed)
+    ref = synth.render_ref(sc)
+    news, gts = [], []
+    for _ in range(n_frames):
+        xi, aff = synth.random_motion(rng)
+        gt = synth.se3_exp(xi)
+        news.append(synth.render_new(sc, gt, aff))
+        gts.append(gt)
+    return sc, ref, news, gts
+
+
+def algorithmic_bytes(evals_per_level, pc_n):
+    """fused calcRes+calcGS moves 16*N_l (point cloud) + 12*w_l*h_l ({I,dx,dy} of the new frame)
+    per evaluation at level l."""
+    tot = 0
+    for l, e in enumerate(evals_per_level):
+        if l < LEVELS:
+            tot += e * (16 * pc_n[l] + 12 * (W >> l) * (H >> l))
+    return tot
+
+
+def cpu_arm(sc, ref, news, n_threads, budget_s, fast=True):
+    """Oracle timing: makeImages + track per frame. Returns dict(value, ms_per_frame, frames, ...)."""
+    from oracle import oracle_py as O
+
+    O.build()
+    dref, agref = O.make_images(ref, W, H, LEVELS, fast=fast)
+    idw, ws = synth.dense_reference_maps(sc, agref[: W * H], KEEP)
+    trackers = []
+    for _ in range(n_threads):
+        T = O.Tracker(W, H, LEVELS, fast=fast)
+        T.set_settings(affineOptModeA=0, affineOptModeB=0)
+        T.makeK(*sc.K)
+        T.set_ref_frame(dref)
+        T.make_depth_dense(idw.ravel(), ws.ravel())
+        trackers.append(T)
+    p0 = np.tile(synth.pose_identity(), (n_threads, 1))
+    a0 = np.zeros((n_threads, 2))
+    # one untimed round (page-in, caches), then timed rounds of n_threads frames until the budget is used
+    O.frames_batch(trackers, [news[i % len(news)] for i in range(n_threads)], p0, a0, LEVELS - 1)
+    t_tot, frames, res, iters = 0.0, 0, 0, 0
+    k = 0
+    while t_tot < budget_s:
+        cols = [news[(k + i) % len(news)] for i in range(n_threads)]
+        t0 = time.perf_counter()
+        ok, poses, affs, lr, st = O.frames_batch(trackers, cols, p0, a0, LEVELS - 1)
+        t_tot += time.perf_counter() - t0
+        frames += n_threads
+        res += st["residuals"]
+        iters += st["iters"]
+        k += n_threads
+    return dict(value=res / t_tot, ms_per_frame=1e3 * t_tot / frames * 1.0, frames=frames, seconds=t_tot,
+                gn_iters_per_s=iters / t_tot, residuals_per_frame=res / frames, pc_n=[trackers[0].pc_n(l) for l in range(LEVELS)])
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sc, ref, news, gts = make_workload()
+    cores = os.cpu_count() or 1
+    # bounded sample: each "step" is one round of `cores` frames; steps+warmup rounds sized to a few minutes at most
+    budget = min(60.0, max(2.0, 1.5 * (args.steps + args.warmup)))
+    r = cpu_arm(sc, ref, news, cores, budget, fast=True)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "residuals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "dense=1 coarse tracking, 1241x376, 5 levels, 1 hypothesis, makeImages+trackNewestCoarse per frame",
+                   "pc_n": r["pc_n"], "frames_timed": r["frames"]},
+        "ms_per_frame": r["ms_per_frame"], "gn_iters_per_s": r["gn_iters_per_s"],
+        "cpu_baseline": {"value": r["value"], "unit": "residuals/s", "cores": cores, "kind": "port",
+                         "sample": f"{r['frames']} frames ({r['seconds']:.1f} s), one frame per core at a time, oracle -O3 -march=x86-64-v3"},
+        "e2e": {"value": r["value"], "unit": "residuals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+
+    from nalo_slam_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    sc, ref, news, gts = make_workload(seed=synth.DEFAULT_SEED + rank)  # every rank aligns its own frame pairs
+    ctx = capi.Context(W, H, LEVELS, device=local_rank, max_frames=3)
+    ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)  # mode=1 of the reference preset (main_dso_pangolin.cpp:429-435)
+    _, agref = ctx.make_images(0, ref, want_host=True)
+    idw, ws = synth.dense_reference_maps(sc, agref[: W * H], KEEP)
+    ctx.make_k(0, *sc.K)
+    ctx.set_ref_dense(0, 0, idw, ws)
+    pc_n = [ctx.ref_count(0, l) for l in range(LEVELS)]
+    # inputs: device-resident copies (value arm) and pinned host copies (e2e arm)
+    dev_imgs = [torch.from_numpy(np.ascontiguousarray(n)).cuda() for n in news]
+    pin_imgs = []
+    for n in news:
+        a = capi.pinned_array((H, W), np.float32)
+        a[...] = n
+        pin_imgs.append(a)
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
+    p0 = synth.pose_identity()
+    K, Wu = args.steps, args.warmup
+    results = np.zeros((K, 16))
+
+    def step_dev(i):
+        ctx.make_images_dev(1, dev_imgs[i % N_FRAMES].data_ptr())
+        return ctx.track(0, 1, p0, [0.0, 0.0])
+
+    def step_host(i):
+        ctx.make_images(1, pin_imgs[i % N_FRAMES])
+        return ctx.track(0, 1, p0, [0.0, 0.0])
+
+    for i in range(Wu):
+        ctx.flush_l2()
+        step_dev(i)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.kernel_launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    tot_res = tot_iters = tot_evals = 0
+    kern_ms, alg_bytes = [], []
+    for i in range(K):
+        ctx.flush_l2()  # untimed: cold L2 for every step
+        with torch.cuda.stream(ext):
+            ev[i][0].record()
+        ok, pose, aff, lr, fl, st = step_dev(i)
+        with torch.cuda.stream(ext):
+            ev[i][1].record()
+        tot_res += st["residuals"]
+        tot_iters += st["iters"]
+        tot_evals += st["evals"]
+        kern_ms.append(st["kernel_ms"])
+        alg_bytes.append(algorithmic_bytes(st["evals_per_level"], pc_n))
+        results[i, 0] = ok
+        results[i, 1:8] = pose
+        results[i, 8:10] = aff
+        results[i, 10:15] = lr
+    launches = ctx.kernel_launches() - launches0
+    # single tiny gather of the per-frame results (inside the timed region)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res_dev = torch.from_numpy(results).cuda()
+    g0.record()
+    if dist:
+        gathered = [torch.empty_like(res_dev) for _ in range(world)]
+        dist.all_gather(gathered, res_dev)
+    g1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms)) + (g0.elapsed_time(g1) if dist else 0.0)
+    if dist:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        agg = torch.tensor([tot_res, tot_iters, launches], device="cuda", dtype=torch.float64)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        job_res, job_iters, job_launches = (float(x) for x in agg.tolist())
+    else:
+        job_res, job_iters, job_launches = float(tot_res), float(tot_iters), float(launches)
+
+    # ---- e2e arm: host image in, pose out, wall clock, through the C ABI
+    for i in range(min(Wu, 3)):
+        step_host(i)
+    if dist:
+        dist.barrier()
+    e2e_s, e2e_res = 0.0, 0
+    for i in range(K):
+        ctx.flush_l2()
+        ctx.sync()
+        t0 = time.perf_counter()
+        ok, pose, aff, lr, fl, st = step_host(i)
+        e2e_s += time.perf_counter() - t0
+        e2e_res += st["residuals"]
+    if dist:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        t = torch.tensor([float(e2e_res)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e_res = float(t.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        k_ms = float(np.mean(kern_ms))
+        achieved = float(np.mean(alg_bytes)) / (k_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("track_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": job_res / (total_ms * 1e-3), "unit": "residuals/s", "n_gpus": world, "steps": K, "warmup": Wu,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "dense=1 coarse tracking, 1241x376, 5 levels, 1 hypothesis, makeImages+trackNewestCoarse per frame",
+                       "pc_n": pc_n, "seeded_px": int(ws.sum()), "l2": "flushed between steps (256 MiB memset, untimed)",
+                       "frames_per_step_per_gpu": 1, "init_pose": "identity"},
+            "ms_per_frame": total_ms / K, "gn_iters_per_s": job_iters / (total_ms * 1e-3),
+            "residuals_per_frame": tot_res / K, "evals_per_frame": tot_evals / K,
+            "e2e": {"value": e2e_res / e2e_s, "unit": "residuals/s", "ms_per_frame": 1e3 * e2e_s / K,
+                    "h2d_bytes_per_step": int(W * H * 4 + 1200), "d2h_bytes_per_step": 256},
+            "gpu_launches": int(job_launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "track_kernel", "kernel_ms": k_ms,
+                         "alg_bytes_per_launch": float(np.mean(alg_bytes)),
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+        }
+        if world == 1 and not args.no_cpu:
+            r = cpu_arm(sc, ref, news, 1, args.cpu_budget, fast=True)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "residuals/s", "cores": 1, "kind": "port",
+                                    "ms_per_frame": r["ms_per_frame"],
+                                    "sample": f"{r['frames']} frames ({r['seconds']:.1f} s) of the same workload on 1 host core (the reference tracker is single-threaded), oracle -O3 -march=x86-64-v3"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

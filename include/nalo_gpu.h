@@ -63,6 +63,8 @@ typedef struct NaloTrackStats {
   int evals;            /* number of calcRes evaluations (fused with calcGS) */
   int iters;            /* LM iterations (CoarseTracker.cpp:1133 loop bodies) */
   int launches;         /* CUDA kernels launched by the call */
+  int evals_per_level[NALO_TRACK_LEVELS]; /* evaluations per pyramid level (for the roofline's algorithmic bytes) */
+  float kernel_ms;      /* device time of the tracking kernel (CUDA events on the context stream) */
 } NaloTrackStats;
 
 void nalo_default_params(NaloParams* p);

@@ -41,7 +41,12 @@ class NaloParams(C.Structure):
 
 
 class NaloTrackStats(C.Structure):
-    _fields_ = [("residuals", C.c_longlong), ("evals", C.c_int), ("iters", C.c_int), ("launches", C.c_int)]
+    _fields_ = [("residuals", C.c_longlong), ("evals", C.c_int), ("iters", C.c_int), ("launches", C.c_int),
+                ("evals_per_level", C.c_int * 5), ("kernel_ms", C.c_float)]
+
+    def as_dict(self):
+        return dict(residuals=self.residuals, evals=self.evals, iters=self.iters, launches=self.launches,
+                    evals_per_level=list(self.evals_per_level), kernel_ms=float(self.kernel_ms))
 
 
 class NaloBAProblem(C.Structure):
@@ -302,7 +307,7 @@ class Context:
         ok = C.c_int(0)
         st = NaloTrackStats()
         self._ck(self.L.nalo_track(self.h_, C.c_int(trk), C.c_int(new_slot), C.c_float(exposure), _ptr(pose), _ptr(aff), C.c_int(coarsestLvl), _ptr(mr), _ptr(lr), _ptr(fl), C.byref(ok), C.byref(st)))
-        return bool(ok.value), pose, aff, lr, fl, dict(residuals=st.residuals, evals=st.evals, iters=st.iters, launches=st.launches)
+        return bool(ok.value), pose, aff, lr, fl, st.as_dict()
 
     # ---- a11
     def track_multi(self, trk, new_slot, poses7, affs2, coarsestLvl=None, exposure=1.0):
@@ -319,7 +324,7 @@ class Context:
         st = NaloTrackStats()
         self._ck(self.L.nalo_track_multi(self.h_, C.c_int(trk), C.c_int(new_slot), C.c_float(exposure), C.c_int(n), _ptr(poses), _ptr(affs), C.c_int(coarsestLvl), _ptr(ok), _ptr(lr), _ptr(fl), _ptr(pl), _ptr(pr), C.byref(st)))
         return dict(ok=ok, poses=poses, affs=affs, lastRes=lr, flow=fl, pass_lvl=pl, pass_res=pr,
-                    stats=dict(residuals=st.residuals, evals=st.evals, iters=st.iters, launches=st.launches))
+                    stats=st.as_dict())
 
 
 def motion_candidates(sprelast_c2w, slast_c2w, lastF_c2w, poses_valid=True):

@@ -70,6 +70,7 @@ struct NaloTrackResult {
   long long residuals;
   int evals;
   int iters;
+  int evalsLvl[NALO_TRACK_LEVELS];
 };
 
 struct NaloSettingsDev {
@@ -120,6 +121,7 @@ struct nalo_ctx {
   int* d_selScratch = nullptr;
   size_t selScratchInts = 0;
   long long launches = 0;
+  cudaEvent_t evA = nullptr, evB = nullptr;
   std::string err;
 };
 

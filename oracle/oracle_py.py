@@ -285,6 +285,23 @@ def track_batch(trackers, new_frames, poses7, affs2, coarsestLvl):
     return ok, poses, affs, lr
 
 
+def frames_batch(trackers, colors, poses7, affs2, coarsestLvl):
+    """makeImages + trackNewestCoarse per colour image over len(trackers) std::threads (bench helper).
+    Returns (ok, poses, affs, lastRes, stats dict summed over threads)."""
+    L = trackers[0].L
+    nT, nJ = len(trackers), len(colors)
+    hs = (C.c_void_p * nT)(*[t.h_ for t in trackers])
+    cols = [np.ascontiguousarray(c, dtype=_f32).reshape(-1) for c in colors]
+    fp = (C.c_void_p * nJ)(*[c.ctypes.data for c in cols])
+    poses = np.ascontiguousarray(poses7, dtype=np.float64).copy()
+    affs = np.ascontiguousarray(affs2, dtype=np.float64).copy()
+    ok = np.zeros(nJ, dtype=np.int32)
+    lr = np.zeros((nJ, 5))
+    st = np.zeros(3, dtype=np.int64)
+    L.oracle_frames_batch(hs, C.c_int(nT), C.c_int(nJ), fp, _ptr(poses), _ptr(affs), C.c_int(coarsestLvl), _ptr(ok), _ptr(lr), _ptr(st))
+    return ok, poses, affs, lr, dict(residuals=int(st[0]), calc_res=int(st[1]), iters=int(st[2]))
+
+
 def se3_exp(xi):
     out = np.zeros(7)
     xi = np.ascontiguousarray(xi, dtype=np.float64)

@@ -836,4 +836,40 @@ void oracle_track_batch(void** trackers, int nThreads, int nJobs, const float** 
   for (auto& t : th) t.join();
 }
 
+// Bench helper (not in the reference): per job the full per-frame hot path = makeImages(new colour image) +
+// trackNewestCoarse from the given initial pose, jobs pulled by `nThreads` std::threads (one tracker each).
+void oracle_make_images(int w0, int h0, int levels, const float* color, const float* B256, float* dIp, float* absgrad);
+void oracle_frames_batch(void** trackers, int nThreads, int nJobs, const float** colors, double* poses7, double* affs2,
+                         int coarsestLvl, int* ok_out, double* lastRes5_out, long long* stats3_out) {
+  std::atomic<int> next(0);
+  std::vector<long long> st(3 * (size_t)nThreads, 0);
+  auto worker = [&](int tid) {
+    OTracker* T = (OTracker*)trackers[tid];
+    size_t tot = 0;
+    for (int l = 0; l < T->levels; l++) tot += (size_t)T->w[l] * T->h[l];
+    std::vector<float> dIp(3 * tot), ag(tot);
+    T->statResiduals = T->statCalcRes = T->statIters = 0;
+    for (;;) {
+      int j = next.fetch_add(1);
+      if (j >= nJobs) break;
+      oracle_make_images(T->w[0], T->h[0], T->levels, colors[j], nullptr, dIp.data(), ag.data());
+      set_frame_ptrs(T, dIp.data(), T->newdIp);
+      T->new_exposure = 1.f;
+      orc::SE3 s = orc::se3_from_array(poses7 + 7 * j);
+      double minRes[5] = {NAN, NAN, NAN, NAN, NAN};
+      bool ok = tracker_track(T, s, affs2 + 2 * j, coarsestLvl, minRes);
+      orc::se3_to_array(s, poses7 + 7 * j);
+      ok_out[j] = ok ? 1 : 0;
+      for (int k = 0; k < 5; k++) lastRes5_out[5 * j + k] = T->lastResiduals[k];
+    }
+    st[3 * tid + 0] = T->statResiduals; st[3 * tid + 1] = T->statCalcRes; st[3 * tid + 2] = T->statIters;
+  };
+  std::vector<std::thread> th;
+  for (int t = 0; t < nThreads; t++) th.emplace_back(worker, t);
+  for (auto& t : th) t.join();
+  stats3_out[0] = stats3_out[1] = stats3_out[2] = 0;
+  for (int t = 0; t < nThreads; t++)
+    for (int k = 0; k < 3; k++) stats3_out[k] += st[3 * t + k];
+}
+
 }  // extern "C"
