@@ -100,8 +100,8 @@ struct nalo_ctx {
   NaloTrackResult* d_results = nullptr;
   NaloTrackProblem* h_problems = nullptr;  // pinned
   NaloTrackResult* h_results = nullptr;    // pinned
-  float* d_partials = nullptr;
-  unsigned long long* d_barriers = nullptr;
+  unsigned long long* d_xchg = nullptr;  // flagged 64-bit exchange words of the tracking groups
+  size_t xchgBytes = 0;
   int maxGroups = 0;
   int trackBlocksPerSM = 1;
   uint8_t* d_mask = nullptr;      // w0*h0 bytes
