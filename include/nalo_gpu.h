@@ -98,6 +98,9 @@ int nalo_get_frame(nalo_ctx* ctx, int slot, float* dIp_host, float* absgrad_host
  * initial value 3). map_out: float[w*h] in {0,1,2,4}. Returns the count in *n_out. */
 int nalo_select_pixels(nalo_ctx* ctx, int slot, float density, int recursionsLeft, float thFactor, int* currentPotential_inout,
                        float* map_out_host, int* n_out);
+/* PixelSelector::randomPattern (:43-45): srand(3141592); rand() & 0xFF, glibc's generator restated so the
+ * product does not depend on the host libc. Host-only, needs no context or device. */
+void nalo_random_pattern(int n, unsigned char* out);
 /* parity hooks: makeHists (:78-143) and select (:564-707) */
 int nalo_selector_make_hists(nalo_ctx* ctx, int slot, float* ths_out, float* thsSmoothed_out, int* n_blocks_out);
 int nalo_selector_select(nalo_ctx* ctx, int slot, int pot, float thFactor, float* map_out_host, int n3_out[3]);

@@ -358,3 +358,118 @@ def winner_rule(res, aff_last, lastCoarseRMSE, reTrackThreshold=1.5, first_try=N
     if rc != NALO_OK:
         raise NaloError(rc, "nalo_winner_rule")
     return dict(good=bool(good.value), pose=pose, aff=aff, flow=flow, achievedRes=ach, lastCoarseRMSE=rmse, tries=used.value)
+
+
+def random_pattern(n):
+    """PixelSelector::randomPattern (glibc rand() restated inside the library; host-only call)."""
+    out = np.zeros(n, dtype=np.uint8)
+    load().nalo_random_pattern(C.c_int(n), _ptr(out))
+    return out
+
+
+def scene_param_block(scene):
+    """Flatten a synth.Scene for nalo_batch_synth_pair: [n, amp, fx, fy, phi, plane[3], nb, bumps[nb][4], K[4]]."""
+    return np.concatenate(
+        [[len(scene.amp)], scene.amp, scene.fxk, scene.fyk, scene.phi, scene.plane, [len(scene.bumps)], np.asarray(scene.bumps).ravel(), scene.K]
+    ).astype(np.float64)
+
+
+class Batch:
+    """nalo_batch: independent frame-pair alignments resident in HBM (BASELINE.json config 5)."""
+
+    def __init__(self, ctx: Context, capacity: int):
+        self.ctx, self.L, self.capacity = ctx, ctx.L, capacity
+        h_ = _P()
+        ctx._ck(self.L.nalo_batch_create(ctx.h_, C.c_int(capacity), C.byref(h_)))
+        self.h_ = h_
+
+    def close(self):
+        if getattr(self, "h_", None):
+            self.L.nalo_batch_destroy(self.h_)
+            self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_pair(self, i, ref, idw0, wsum0, new, K):
+        a = [np.ascontiguousarray(x, dtype=_f32).reshape(-1) for x in (ref, idw0, wsum0, new)]
+        self.ctx._ck(self.L.nalo_batch_set_pair(self.h_, C.c_int(i), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), *[C.c_float(k) for k in K]))
+
+    def synth_pair(self, i, scene_block, pose_gt, aff_gt, tau):
+        sb = np.ascontiguousarray(scene_block, dtype=np.float64)
+        pg = np.ascontiguousarray(pose_gt, dtype=np.float64)
+        ag = np.ascontiguousarray(aff_gt, dtype=np.float64)
+        self.ctx._ck(self.L.nalo_batch_synth_pair(self.h_, C.c_int(i), _ptr(sb), C.c_int(sb.size), _ptr(pg), _ptr(ag), C.c_float(tau)))
+
+    def track(self, first, count, poses7=None, affs2=None, coarsestLvl=None):
+        poses = np.tile(np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float64), (count, 1)) if poses7 is None else np.ascontiguousarray(poses7, dtype=np.float64).copy()
+        affs = np.zeros((count, 2)) if affs2 is None else np.ascontiguousarray(affs2, dtype=np.float64).copy()
+        if coarsestLvl is None:
+            coarsestLvl = min(self.ctx.levels, 5) - 1
+        ok = np.zeros(count, dtype=np.int32)
+        lr = np.zeros((count, 5))
+        st = NaloTrackStats()
+        self.ctx._ck(self.L.nalo_batch_track(self.h_, C.c_int(first), C.c_int(count), _ptr(poses), _ptr(affs), C.c_int(coarsestLvl), _ptr(ok), _ptr(lr), C.byref(st)))
+        return dict(ok=ok, poses=poses, affs=affs, lastRes=lr, stats=st.as_dict())
+
+    def results_dev_ptr(self) -> int:
+        return int(self.L.nalo_batch_results_dev(self.h_) or 0)
+
+
+class BA:
+    """nalo_ba: windowed-BA accumulators (AccumulatedTopHessianSSE / AccumulatedSCHessianSSE) on a flattened problem."""
+
+    def __init__(self, ctx: Context, max_res: int, max_pts: int):
+        self.ctx, self.L = ctx, ctx.L
+        h_ = _P()
+        ctx._ck(self.L.nalo_ba_create(ctx.h_, C.c_int(max_res), C.c_int(max_pts), C.byref(h_)))
+        self.h_ = h_
+        self.prob = None
+
+    def close(self):
+        if getattr(self, "h_", None):
+            self.L.nalo_ba_destroy(self.h_)
+            self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, prob: dict):
+        self.prob = prob
+        P = NaloBAProblem()
+        P.nf, P.n_pts, P.n_res = prob["nf"], prob["n_pts"], prob["n_res"]
+        for k in ("rec", "res_toZero", "bucket_begin", "pt_begin", "pt_res", "deltaF", "priorF", "adHTdeltaF", "cDeltaF"):
+            a = prob.get(k)
+            setattr(P, k, None if a is None else a.ctypes.data)
+        self._keep = P
+        self.ctx._ck(self.L.nalo_ba_upload(self.h_, C.byref(P)))
+
+    def accumulate_top(self, mode=0):
+        nf, nP = self.prob["nf"], self.prob["n_pts"]
+        H = np.zeros((nf * nf, 13, 13))
+        pp = np.zeros((max(nP, 1), 6), dtype=_f32)
+        n = C.c_int(0)
+        self.ctx._ck(self.L.nalo_ba_accumulate_top(self.h_, C.c_int(mode), _ptr(H), _ptr(pp), C.byref(n)))
+        return H, pp[:nP], n.value
+
+    def take_data(self):
+        out = np.zeros((max(self.prob["n_res"], 1), 8), dtype=_f32)
+        self.ctx._ck(self.L.nalo_ba_take_data(self.h_, _ptr(out)))
+        return out[: self.prob["n_res"]]
+
+    def accumulate_sc(self, shiftPriorToZero=True, useL=False):
+        nf, nP = self.prob["nf"], self.prob["n_pts"]
+        accD = np.zeros((nf**3, 8, 8))
+        accE = np.zeros((nf**2, 8, 4))
+        accEB = np.zeros((nf**2, 8))
+        accHcc = np.zeros((4, 4))
+        accbc = np.zeros(4)
+        pp = np.zeros((max(nP, 1), 3), dtype=_f32)
+        self.ctx._ck(self.L.nalo_ba_accumulate_sc(self.h_, C.c_int(1 if shiftPriorToZero else 0), C.c_int(1 if useL else 0), _ptr(accD), _ptr(accE), _ptr(accEB), _ptr(accHcc), _ptr(accbc), _ptr(pp)))
+        return dict(accD=accD, accE=accE, accEB=accEB, accHcc=accHcc, accbc=accbc, perPoint=pp[:nP])

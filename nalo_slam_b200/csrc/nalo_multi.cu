@@ -1,0 +1,256 @@
+// nalo_multi.cu — a11: FullSystem::trackNewCoarse (src/FullSystem/FullSystem.cpp:502-699).
+//
+//   nalo_motion_candidates : the 31 SE3 initialisations (:516-580), host fp64.
+//   nalo_track_multi       : all candidates tracked concurrently by ONE launch of the persistent tracking kernel
+//                            (nalo_track.cu), a group of CTAs per candidate, no abort thresholds. Per candidate the
+//                            residual after every level pass is recorded.
+//   nalo_winner_rule       : the sequential winner rule (:583-666) replayed in index order on those records. A try
+//                            "would have been aborted" (CoarseTracker.cpp:1227) iff after some pass its residual
+//                            exceeds 1.5x the thresholds it would have been handed; levels after that stay NaN.
+//                            Levels are tracked identically with or without thresholds, so the replay reproduces
+//                            the sequential loop exactly — including its early break.
+// On several GPUs the candidates are partitioned across ranks, every rank calls nalo_track_multi on its share,
+// the small per-candidate records are gathered (NCCL, see bench.py / INTEGRATION.md) and rank 0 replays the rule.
+#include "nalo_common.cuh"
+
+namespace {
+
+struct SE3d {
+  double q[4];  // x,y,z,w
+  double t[3];
+};
+SE3d from7(const double* p) { SE3d s; for (int i = 0; i < 4; i++) s.q[i] = p[i]; for (int i = 0; i < 3; i++) s.t[i] = p[4 + i]; return s; }
+void to7(const SE3d& s, double* p) { for (int i = 0; i < 4; i++) p[i] = s.q[i]; for (int i = 0; i < 3; i++) p[4 + i] = s.t[i]; }
+SE3d identity() { SE3d s; s.q[0] = s.q[1] = s.q[2] = 0; s.q[3] = 1; s.t[0] = s.t[1] = s.t[2] = 0; return s; }
+void qmul(const double* a, const double* b, double* r) {
+  r[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  r[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  r[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+  r[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+}
+void qnorm(double* q) {
+  const double l = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; i++) q[i] /= l;
+}
+void qrot(const double* q, const double* v, double* o) {  // Eigen _transformVector
+  double uv[3] = {q[1] * v[2] - q[2] * v[1], q[2] * v[0] - q[0] * v[2], q[0] * v[1] - q[1] * v[0]};
+  for (int i = 0; i < 3; i++) uv[i] += uv[i];
+  const double c[3] = {q[1] * uv[2] - q[2] * uv[1], q[2] * uv[0] - q[0] * uv[2], q[0] * uv[1] - q[1] * uv[0]};
+  for (int i = 0; i < 3; i++) o[i] = v[i] + q[3] * uv[i] + c[i];
+}
+SE3d mul(const SE3d& a, const SE3d& b) {  // se3.hpp:239-272
+  SE3d r;
+  double rt[3];
+  qrot(a.q, b.t, rt);
+  for (int i = 0; i < 3; i++) r.t[i] = a.t[i] + rt[i];
+  qmul(a.q, b.q, r.q);
+  qnorm(r.q);
+  return r;
+}
+SE3d inv(const SE3d& a) {  // se3.hpp:169-173
+  SE3d r;
+  r.q[0] = -a.q[0]; r.q[1] = -a.q[1]; r.q[2] = -a.q[2]; r.q[3] = a.q[3];
+  const double nt[3] = {-a.t[0], -a.t[1], -a.t[2]};
+  qrot(r.q, nt, r.t);
+  return r;
+}
+void cross(const double* a, const double* b, double* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+void se3_log(const SE3d& s, double* out) {  // so3.hpp:486-524, se3.hpp:560-587
+  const double sq = s.q[0] * s.q[0] + s.q[1] * s.q[1] + s.q[2] * s.q[2];
+  const double n = std::sqrt(sq), w = s.q[3];
+  double f;
+  if (n < 1e-10) f = 2.0 / w - 2.0 * sq / (w * w * w);
+  else if (std::fabs(w) < 1e-10) f = (w > 0 ? M_PI : -M_PI) / n;
+  else f = 2.0 * std::atan(n / w) / n;
+  const double theta = f * n;
+  const double om[3] = {f * s.q[0], f * s.q[1], f * s.q[2]};
+  // V^-1 t = t - 0.5 om x t + c om x (om x t)
+  double ot[3], oot[3];
+  cross(om, s.t, ot);
+  cross(om, ot, oot);
+  const double c = (std::fabs(theta) < 1e-10) ? (1. / 12.) : (1.0 - theta / (2.0 * std::tan(theta / 2.0))) / (theta * theta);
+  for (int i = 0; i < 3; i++) out[i] = s.t[i] - 0.5 * ot[i] + c * oot[i];
+  out[3] = om[0]; out[4] = om[1]; out[5] = om[2];
+}
+SE3d se3_exp(const double* a) {  // so3.hpp:343-369, se3.hpp:407-428
+  SE3d r;
+  const double* om = a + 3;
+  const double tsq = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+  const double th = std::sqrt(tsq);
+  double imag, real;
+  if (th < 1e-10) {
+    imag = 0.5 - tsq / 48.0 + tsq * tsq / 3840.0;
+    real = 1.0 - 0.5 * tsq + tsq * tsq / 384.0;
+  } else {
+    imag = std::sin(0.5 * th) / th;
+    real = std::cos(0.5 * th);
+  }
+  r.q[0] = imag * om[0]; r.q[1] = imag * om[1]; r.q[2] = imag * om[2]; r.q[3] = real;
+  qnorm(r.q);
+  if (th < 1e-10) {
+    qrot(r.q, a, r.t);
+  } else {
+    double ov[3], oov[3];
+    cross(om, a, ov);
+    cross(om, ov, oov);
+    const double c1 = (1.0 - std::cos(th)) / tsq, c2 = (th - std::sin(th)) / (tsq * th);
+    for (int i = 0; i < 3; i++) r.t[i] = a[i] + c1 * ov[i] + c2 * oov[i];
+  }
+  return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nalo_motion_candidates(const double sprelast_c2w[7], const double slast_c2w[7], const double lastF_c2w[7], int posesValid,
+                           double* tries_out, int* n_out) {
+  if (!sprelast_c2w || !slast_c2w || !lastF_c2w || !tries_out || !n_out) return NALO_E_ARG;
+  if (!posesValid) {  // FullSystem.cpp:575-579
+    to7(identity(), tries_out);
+    *n_out = 1;
+    return NALO_OK;
+  }
+  const SE3d sprelast = from7(sprelast_c2w), slast = from7(slast_c2w), lastF = from7(lastF_c2w);
+  const SE3d slast_2_sprelast = mul(inv(sprelast), slast);
+  const SE3d lastF_2_slast = mul(inv(slast), lastF);
+  const SE3d fh_2_slast = slast_2_sprelast;  // constant-motion assumption
+  const SE3d fhi = inv(fh_2_slast);
+  int n = 0;
+  const SE3d M = mul(fhi, lastF_2_slast);
+  to7(M, tries_out + 7 * n++);                                    // constant motion
+  to7(mul(mul(fhi, fhi), lastF_2_slast), tries_out + 7 * n++);    // double motion (frame skipped)
+  {
+    double lg[6];
+    se3_log(fh_2_slast, lg);
+    for (int i = 0; i < 6; i++) lg[i] *= 0.5;
+    to7(mul(inv(se3_exp(lg)), lastF_2_slast), tries_out + 7 * n++);  // half motion
+  }
+  to7(lastF_2_slast, tries_out + 7 * n++);  // zero motion
+  to7(identity(), tries_out + 7 * n++);     // zero motion from the keyframe
+  const double d = (double)0.02f;           // `float rotDelta = 0.02`, promoted in Quaterniond(1, ...)
+  static const signed char pat[26][3] = {{1, 0, 0},   {0, 1, 0},   {0, 0, 1},    {-1, 0, 0},  {0, -1, 0},   {0, 0, -1},  {1, 1, 0},
+                                         {0, 1, 1},   {1, 0, 1},   {-1, 1, 0},   {0, -1, 1},  {-1, 0, 1},   {1, -1, 0},  {0, 1, -1},
+                                         {1, 0, -1},  {-1, -1, 0}, {0, -1, -1},  {-1, 0, -1}, {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1},
+                                         {-1, 1, 1},  {1, -1, -1}, {1, -1, 1},   {1, 1, -1},  {1, 1, 1}};
+  for (int k = 0; k < 26; k++) {
+    SE3d q = identity();
+    q.q[0] = pat[k][0] * d; q.q[1] = pat[k][1] * d; q.q[2] = pat[k][2] * d; q.q[3] = 1.0;
+    qnorm(q.q);
+    to7(mul(M, q), tries_out + 7 * n++);
+  }
+  *n_out = n;
+  return NALO_OK;
+}
+
+int nalo_track_multi(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, int nHyp, double* poses7, double* affs2,
+                     int coarsestLvl, int* ok_out, double* lastRes5_out, double* flow3_out, int* pass_lvl_out, double* pass_res_out,
+                     NaloTrackStats* stats) {
+  if (!ctx || trk < 0 || trk >= NALO_MAX_TRACKERS || !poses7 || !affs2) return NALO_E_ARG;
+  if (nHyp < 1 || nHyp > NALO_MAX_HYPOTHESES) return nalo_fail(ctx, NALO_E_ARG, "nHyp %d out of [1,%d]", nHyp, NALO_MAX_HYPOTHESES);
+  if (coarsestLvl < 0 || coarsestLvl >= NALO_TRACK_LEVELS || coarsestLvl >= ctx->levels) return NALO_E_ARG;
+  int rc = nalo_set_new_frame(ctx, trk, new_slot, exposure_new);
+  if (rc != NALO_OK) return rc;
+  NaloTrackerState& T = ctx->trk[trk];
+  if (!T.haveK || !T.haveRef) return nalo_fail(ctx, NALO_E_STATE, "tracker %d has no reference", trk);
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long long l0 = ctx->launches;
+  for (int i = 0; i < nHyp; i++) {
+    NaloTrackProblem* P = ctx->h_problems + i;
+    nalo_fill_problem(ctx, trk, P);
+    for (int k = 0; k < 7; k++) P->pose[k] = poses7[7 * i + k];
+    P->aff[0] = affs2[2 * i];
+    P->aff[1] = affs2[2 * i + 1];
+    P->coarsestLvl = coarsestLvl;
+    P->useAbort = 0;
+  }
+  NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_problems, ctx->h_problems, sizeof(NaloTrackProblem) * nHyp, cudaMemcpyHostToDevice, ctx->stream));
+  if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evA, ctx->stream));
+  rc = nalo_track_launch(ctx, nHyp, ctx->maxGroups / nHyp, ctx->d_problems, ctx->d_results);
+  if (rc != NALO_OK) return rc;
+  if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));
+  NALO_CUDA(ctx, cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(NaloTrackResult) * nHyp, cudaMemcpyDeviceToHost, ctx->stream));
+  NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stats) { memset(stats, 0, sizeof(*stats)); }
+  for (int i = 0; i < nHyp; i++) {
+    const NaloTrackResult& R = ctx->h_results[i];
+    for (int k = 0; k < 7; k++) poses7[7 * i + k] = R.pose[k];
+    affs2[2 * i] = R.aff[0];
+    affs2[2 * i + 1] = R.aff[1];
+    if (ok_out) ok_out[i] = R.ok;
+    if (lastRes5_out) for (int k = 0; k < 5; k++) lastRes5_out[5 * i + k] = R.lastRes[k];
+    if (flow3_out) for (int k = 0; k < 3; k++) flow3_out[3 * i + k] = R.flow[k];
+    if (pass_lvl_out) for (int k = 0; k < 6; k++) pass_lvl_out[6 * i + k] = R.passLvl[k];
+    if (pass_res_out) for (int k = 0; k < 6; k++) pass_res_out[6 * i + k] = R.passRes[k];
+    if (stats) {
+      stats->residuals += R.residuals;
+      stats->evals += R.evals;
+      stats->iters += R.iters;
+      for (int k = 0; k < NALO_TRACK_LEVELS; k++) stats->evals_per_level[k] += R.evalsLvl[k];
+    }
+  }
+  if (stats) {
+    stats->launches = (int)(ctx->launches - l0);
+    NALO_CUDA(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->evA, ctx->evB));
+  }
+  return NALO_OK;
+}
+
+int nalo_winner_rule(int nHyp, const double* poses7, const double* affs2, const int* ok, const double* flow3, const int* pass_lvl,
+                     const double* pass_res, const double aff_last[2], const double first_try_pose7[7], double lastCoarseRMSE5[5],
+                     float reTrackThreshold, double pose_out7[7], double aff_out2[2], double flow_out3[3], double achievedRes5[5],
+                     int* tries_used, int* haveOneGood_out) {
+  if (nHyp < 0 || (nHyp > 0 && (!poses7 || !affs2 || !ok || !flow3 || !pass_lvl || !pass_res)) || !aff_last || !lastCoarseRMSE5 || !pose_out7 ||
+      !aff_out2 || !flow_out3 || !achievedRes5)
+    return NALO_E_ARG;
+  double flowVecs[3] = {100, 100, 100};
+  double bestPose[7] = {0, 0, 0, 1, 0, 0, 0};
+  double bestAff[2] = {0, 0};
+  double achieved[5] = {NAN, NAN, NAN, NAN, NAN};
+  bool haveOneGood = false;
+  int tries = 0;
+  for (int i = 0; i < nHyp; i++) {
+    // replay of trackNewestCoarse(…, minResForAbort = achieved) on the recorded passes
+    double lastRes[5] = {NAN, NAN, NAN, NAN, NAN};
+    bool aborted = false;
+    for (int p = 0; p < 6; p++) {
+      const int lvl = pass_lvl[6 * i + p];
+      if (lvl < 0) break;
+      lastRes[lvl] = pass_res[6 * i + p];
+      if (lastRes[lvl] > 1.5 * achieved[lvl]) { aborted = true; break; }  // CoarseTracker.cpp:1227
+    }
+    const bool trackingIsGood = !aborted && ok[i] != 0;
+    tries++;
+    if (trackingIsGood && std::isfinite((float)lastRes[0]) && !(lastRes[0] >= achieved[0])) {
+      for (int k = 0; k < 3; k++) flowVecs[k] = flow3[3 * i + k];
+      bestAff[0] = affs2[2 * i];
+      bestAff[1] = affs2[2 * i + 1];
+      for (int k = 0; k < 7; k++) bestPose[k] = poses7[7 * i + k];
+      haveOneGood = true;
+    }
+    if (haveOneGood) {
+      for (int k = 0; k < 5; k++)
+        if (!std::isfinite((float)achieved[k]) || achieved[k] > lastRes[k]) achieved[k] = lastRes[k];
+    }
+    if (haveOneGood && achieved[0] < lastCoarseRMSE5[0] * reTrackThreshold) break;
+  }
+  if (!haveOneGood) {  // FullSystem.cpp:658-664
+    flowVecs[0] = flowVecs[1] = flowVecs[2] = 0;
+    bestAff[0] = aff_last[0];
+    bestAff[1] = aff_last[1];
+    if (first_try_pose7) for (int k = 0; k < 7; k++) bestPose[k] = first_try_pose7[k];
+  }
+  for (int k = 0; k < 5; k++) lastCoarseRMSE5[k] = achieved[k];
+  for (int k = 0; k < 7; k++) pose_out7[k] = bestPose[k];
+  aff_out2[0] = bestAff[0];
+  aff_out2[1] = bestAff[1];
+  for (int k = 0; k < 3; k++) flow_out3[k] = flowVecs[k];
+  for (int k = 0; k < 5; k++) achievedRes5[k] = achieved[k];
+  if (tries_used) *tries_used = tries;
+  if (haveOneGood_out) *haveOneGood_out = haveOneGood ? 1 : 0;
+  return NALO_OK;
+}
+
+}  // extern "C"

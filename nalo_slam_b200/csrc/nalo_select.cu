@@ -1,0 +1,555 @@
+// nalo_select.cu — a2-a4: PixelSelector (src/FullSystem/PixelSelector2.cpp) on sm_100a.
+//
+//   makeHists (:78-143)  hist_kernel   : one CTA per 32x32 block, shared-memory 50-bin histogram of
+//                                        (int)sqrtf(absSquaredGrad0), median + minGradHistAdd.
+//                        smooth_kernel : 3x3 box mean (same summation order), squared.
+//   select (:564-707)    The reference walks the image in nested 4pot/2pot/pot blocks and picks, per block, the
+//       pixel with the largest |grad . dir| where dir = directions[randomPattern[n2] & 15] and n2 is the number
+//       of label-1 selections made SO FAR — a serial dependency over ~50k blocks. It is broken
+//       up exactly, not approximately:
+//         block_mask_kernel : per pot-block, for all 16 directions at once, "would this block select anything"
+//                             (bit d set iff some pixel above threshold has |grad.dir_d| > 0). Almost every block
+//                             is all-ones or zero, i.e. independent of the direction.
+//         exclusive scan    : n2 at the start of every pot-block, assuming direction-independent blocks.
+//         resolve_kernel    : the rare direction-dependent blocks are replayed sequentially (one thread, in
+//                             order, a handful of entries), then the scan is redone with their true outcome.
+//         select_kernel     : one thread per 4pot block replays the reference's inner loops verbatim (same
+//                             sentinels, same tie-breaking) with the now-known n2 of each of its pot-blocks.
+//   makeMaps (:144-291)  host logic (potential adaptation, one recursion) + subsample_kernel for the
+//       random drop, whose running index `rn` is again an exclusive scan.
+// Arithmetic that feeds a comparison is un-contracted fp32 in the reference's order, so the selection map is
+// bit-identical to the CPU oracle. randomPattern is glibc's rand() restated (TYPE_3 additive feedback), so the
+// product does not depend on the host libc.
+#include "nalo_common.cuh"
+
+namespace {
+
+__constant__ float kDir[16][2] = {{0.f, 1.0000f},      {0.3827f, 0.9239f},  {0.1951f, 0.9808f},  {0.9239f, 0.3827f},
+                                  {0.7071f, 0.7071f},  {0.3827f, -0.9239f}, {0.8315f, 0.5556f},  {0.8315f, -0.5556f},
+                                  {0.5556f, -0.8315f}, {0.9808f, 0.1951f},  {0.9239f, -0.3827f}, {0.7071f, -0.7071f},
+                                  {0.5556f, 0.8315f},  {0.9808f, -0.1951f}, {1.0000f, 0.0000f},  {0.1951f, -0.9808f}};
+
+// ---------------------------------------------------------------------------------------------- generic int scan
+__global__ void __launch_bounds__(1024) scan_block_kernel(const int* __restrict__ in, int* __restrict__ out, int* __restrict__ blockSums, int n) {
+  __shared__ int warpSums[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const int v = (i < n) ? in[i] : 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warpSums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = warpSums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    warpSums[lane] = w;
+  }
+  __syncthreads();
+  const int base = (wid > 0) ? warpSums[wid - 1] : 0;
+  if (i < n) out[i] = base + incl - v;
+  if (threadIdx.x == 1023) blockSums[blockIdx.x] = base + incl;
+}
+__global__ void __launch_bounds__(1024) scan_sums_kernel(int* __restrict__ blockSums, int nb, int* __restrict__ total) {
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = (i < nb) ? blockSums[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    const int incl = sh[threadIdx.x];
+    if (i < nb) blockSums[i] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+__global__ void __launch_bounds__(1024) scan_add_kernel(int* __restrict__ out, const int* __restrict__ blockSums, int n) {
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  if (i < n) out[i] += blockSums[blockIdx.x];
+}
+
+int exclusive_scan(nalo_ctx* ctx, const int* in, int* out, int n, int* blockSums, int* total) {
+  const int nb = (n + 1023) / 1024;
+  scan_block_kernel<<<nb, 1024, 0, ctx->stream>>>(in, out, blockSums, n);
+  NALO_CHECK_LAUNCH(ctx);
+  scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(blockSums, nb, total);
+  NALO_CHECK_LAUNCH(ctx);
+  scan_add_kernel<<<nb, 1024, 0, ctx->stream>>>(out, blockSums, n);
+  NALO_CHECK_LAUNCH(ctx);
+  return NALO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- makeHists
+__global__ void __launch_bounds__(256) hist_kernel(const float4* __restrict__ pix0, int w, int h, int w32, float cut, float add,
+                                                   float* __restrict__ ths) {
+  __shared__ int hist[52];
+  const int bx = blockIdx.x % w32, by = blockIdx.x / w32;
+  if (threadIdx.x < 52) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int k = threadIdx.x; k < 1024; k += 256) {
+    const int i = k & 31, j = k >> 5;
+    const int it = i + 32 * bx, jt = j + 32 * by;
+    if (it > w - 2 || jt > h - 2 || it < 1 || jt < 1) continue;
+    int g = (int)__fsqrt_rn(pix0[it + jt * w].w);
+    if (g > 48) g = 48;
+    atomicAdd(&hist[g + 1], 1);
+    atomicAdd(&hist[0], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // computeHistQuantil (:66-75); bins 50..90 are zero
+    int th = (int)__fadd_rn(__fmul_rn((float)hist[0], cut), 0.5f);
+    int q = 90;
+    for (int i = 0; i < 90; i++) {
+      th -= (i + 1 < 50) ? hist[i + 1] : 0;
+      if (th < 0) { q = i; break; }
+    }
+    ths[bx + by * w32] = __fadd_rn((float)q, add);
+  }
+}
+__global__ void smooth_kernel(const float* __restrict__ ths, float* __restrict__ thsSmoothed, int w32, int h32) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w32 * h32) return;
+  const int x = i % w32, y = i / w32;
+  float sum = 0.f, num = 0.f;
+#define ADD_(xx, yy) { num = __fadd_rn(num, 1.f); sum = __fadd_rn(sum, ths[(xx) + (yy) * w32]); }
+  if (x > 0) {
+    if (y > 0) ADD_(x - 1, y - 1);
+    if (y < h32 - 1) ADD_(x - 1, y + 1);
+    ADD_(x - 1, y);
+  }
+  if (x < w32 - 1) {
+    if (y > 0) ADD_(x + 1, y - 1);
+    if (y < h32 - 1) ADD_(x + 1, y + 1);
+    ADD_(x + 1, y);
+  }
+  if (y > 0) ADD_(x, y - 1);
+  if (y < h32 - 1) ADD_(x, y + 1);
+  ADD_(x, y);
+#undef ADD_
+  const float m = __fdiv_rn(sum, num);
+  thsSmoothed[i] = __fmul_rn(m, m);
+}
+
+// ---------------------------------------------------------------------------------------------- select
+struct SelGeom {
+  int w, h, w1, w2, pot;
+  int nX4, nY4;  // number of 4pot blocks
+  int thsStep;
+  int off1, off2;  // pixel offsets of levels 1,2 in the frame buffer
+  float thFactor, dw1, dw2;
+  int dirDist;
+};
+
+__device__ __forceinline__ bool border_skip(const SelGeom& g, int xf, int yf) { return xf < 4 || xf >= g.w - 5 || yf < 4 || yf > g.h - 4; }
+
+// slot = b4*16 + ((y3i*2 + x3i)*2 + y2i)*2 + x2i ; returns false when the sub-block does not exist (image edge)
+__device__ __forceinline__ bool slot_rect(const SelGeom& g, int slot, int& x0, int& y0, int& mx1, int& my1) {
+  const int b4 = slot >> 4, loc = slot & 15;
+  const int x2i = loc & 1, y2i = (loc >> 1) & 1, x3i = (loc >> 2) & 1, y3i = (loc >> 3) & 1;
+  const int x4 = (b4 % g.nX4) * 4 * g.pot, y4 = (b4 / g.nX4) * 4 * g.pot;
+  const int x34 = x4 + x3i * 2 * g.pot, y34 = y4 + y3i * 2 * g.pot;
+  if (x34 >= g.w || y34 >= g.h) return false;
+  x0 = x34 + x2i * g.pot;
+  y0 = y34 + y2i * g.pot;
+  if (x0 >= g.w || y0 >= g.h) return false;
+  mx1 = min(g.pot, g.w - x0);
+  my1 = min(g.pot, g.h - y0);
+  return true;
+}
+
+// per pot-block: bit d set iff the block would make a label-1 selection under direction d
+__global__ void __launch_bounds__(256) block_mask_kernel(const float4* __restrict__ pix, const float* __restrict__ thsSmoothed, SelGeom g,
+                                                         int nSlots, int* __restrict__ selUnamb, int* __restrict__ amb,
+                                                         unsigned short* __restrict__ masks) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= nSlots) return;
+  int x0, y0, mx1, my1;
+  unsigned m = 0;
+  if (slot_rect(g, slot, x0, y0, mx1, my1)) {
+    for (int y1 = 0; y1 < my1; y1++)
+      for (int x1 = 0; x1 < mx1; x1++) {
+        const int xf = x0 + x1, yf = y0 + y1;
+        if (border_skip(g, xf, yf)) continue;
+        const float th0 = thsSmoothed[(xf >> 5) + (yf >> 5) * g.thsStep];
+        const float4 p = pix[xf + g.w * yf];
+        if (p.w > __fmul_rn(th0, g.thFactor)) {
+          if (!g.dirDist) {
+            if (p.w > 0.f) m = 0xFFFFu;
+          } else {
+#pragma unroll
+            for (int d = 0; d < 16; d++) {
+              const float dn = fabsf(__fadd_rn(__fmul_rn(p.y, kDir[d][0]), __fmul_rn(p.z, kDir[d][1])));
+              if (dn > 0.f) m |= 1u << d;
+            }
+          }
+        }
+      }
+  }
+  masks[slot] = (unsigned short)m;
+  selUnamb[slot] = (m == 0xFFFFu) ? 1 : 0;
+  amb[slot] = (m != 0 && m != 0xFFFFu) ? 1 : 0;
+}
+
+// compact the ambiguous slots in order (ambPos = exclusive scan of amb)
+__global__ void amb_compact_kernel(const int* __restrict__ amb, const int* __restrict__ ambPos, int nSlots, int* __restrict__ ambList) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot < nSlots && amb[slot]) ambList[ambPos[slot]] = slot;
+}
+// one thread: replay the direction-dependent blocks in order; selFinal[slot] gets their true outcome
+__global__ void resolve_kernel(const int* __restrict__ ambList, const int* __restrict__ nAmb, const int* __restrict__ prefixUnamb,
+                               const unsigned short* __restrict__ masks, const unsigned char* __restrict__ randomPattern,
+                               int* __restrict__ selFinal) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int offset = 0;
+  const int n = *nAmb;
+  for (int k = 0; k < n; k++) {
+    const int slot = ambList[k];
+    const int n2 = prefixUnamb[slot] + offset;
+    const int d = randomPattern[n2] & 0xF;
+    const int sel = (masks[slot] >> d) & 1;
+    selFinal[slot] = sel;
+    offset += sel;
+  }
+}
+
+// one thread per 4pot block: the reference's nested loops (:608-703) with n2 taken from the scan
+__global__ void __launch_bounds__(128) select_kernel(const float4* __restrict__ pix, const float* __restrict__ thsSmoothed, SelGeom g,
+                                                     const int* __restrict__ n2Prefix, const unsigned char* __restrict__ randomPattern,
+                                                     float* __restrict__ map_out, int* __restrict__ counts) {
+  const int b4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b4 >= g.nX4 * g.nY4) return;
+  const int pot = g.pot, w = g.w, h = g.h;
+  const int x4 = (b4 % g.nX4) * 4 * pot, y4 = (b4 / g.nX4) * 4 * pot;
+  const float4* pix1 = pix + g.off1;
+  const float4* pix2 = pix + g.off2;
+  int c2 = 0, c3 = 0, c4 = 0;
+  const int my3 = min(4 * pot, h - y4), mx3 = min(4 * pot, w - x4);
+  int bestIdx4 = -1;
+  float bestVal4 = 0.f;
+  const int d4 = randomPattern[n2Prefix[b4 * 16]] & 0xF;
+  const float dir4x = kDir[d4][0], dir4y = kDir[d4][1];
+  for (int y3 = 0, y3i = 0; y3 < my3; y3 += 2 * pot, y3i++)
+    for (int x3 = 0, x3i = 0; x3 < mx3; x3 += 2 * pot, x3i++) {
+      const int x34 = x3 + x4, y34 = y3 + y4;
+      const int my2 = min(2 * pot, h - y34), mx2 = min(2 * pot, w - x34);
+      int bestIdx3 = -1;
+      float bestVal3 = 0.f;
+      const int d3 = randomPattern[n2Prefix[b4 * 16 + (y3i * 2 + x3i) * 4]] & 0xF;
+      const float dir3x = kDir[d3][0], dir3y = kDir[d3][1];
+      for (int y2 = 0, y2i = 0; y2 < my2; y2 += pot, y2i++)
+        for (int x2 = 0, x2i = 0; x2 < mx2; x2 += pot, x2i++) {
+          const int x234 = x2 + x34, y234 = y2 + y34;
+          const int my1 = min(pot, h - y234), mx1 = min(pot, w - x234);
+          int bestIdx2 = -1;
+          float bestVal2 = 0.f;
+          const int slot = b4 * 16 + ((y3i * 2 + x3i) * 2 + y2i) * 2 + x2i;
+          const int d2 = randomPattern[n2Prefix[slot]] & 0xF;
+          const float dir2x = kDir[d2][0], dir2y = kDir[d2][1];
+          for (int y1 = 0; y1 < my1; y1++)
+            for (int x1 = 0; x1 < mx1; x1++) {
+              const int xf = x1 + x234, yf = y1 + y234;
+              const int idx = xf + w * yf;
+              if (border_skip(g, xf, yf)) continue;
+              const float pixelTH0 = thsSmoothed[(xf >> 5) + (yf >> 5) * g.thsStep];
+              const float pixelTH1 = __fmul_rn(pixelTH0, g.dw1);
+              const float pixelTH2 = __fmul_rn(pixelTH1, g.dw2);
+              const float4 p = pix[idx];
+              const float ag0 = p.w;
+              if (ag0 > __fmul_rn(pixelTH0, g.thFactor)) {
+                float dirNorm = fabsf(__fadd_rn(__fmul_rn(p.y, dir2x), __fmul_rn(p.z, dir2y)));
+                if (!g.dirDist) dirNorm = ag0;
+                if (dirNorm > bestVal2) { bestVal2 = dirNorm; bestIdx2 = idx; bestIdx3 = -2; bestIdx4 = -2; }
+              }
+              if (bestIdx3 == -2) continue;
+              const float ag1 = pix1[(int)(xf * 0.5f + 0.25f) + (int)(yf * 0.5f + 0.25f) * g.w1].w;
+              if (ag1 > __fmul_rn(pixelTH1, g.thFactor)) {
+                float dirNorm = fabsf(__fadd_rn(__fmul_rn(p.y, dir3x), __fmul_rn(p.z, dir3y)));
+                if (!g.dirDist) dirNorm = ag1;
+                if (dirNorm > bestVal3) { bestVal3 = dirNorm; bestIdx3 = idx; bestIdx4 = -2; }
+              }
+              if (bestIdx4 == -2) continue;
+              const float ag2 = pix2[(int)(xf * 0.25f + 0.125f) + (int)(yf * 0.25f + 0.125f) * g.w2].w;
+              if (ag2 > __fmul_rn(pixelTH2, g.thFactor)) {
+                float dirNorm = fabsf(__fadd_rn(__fmul_rn(p.y, dir4x), __fmul_rn(p.z, dir4y)));
+                if (!g.dirDist) dirNorm = ag2;
+                if (dirNorm > bestVal4) { bestVal4 = dirNorm; bestIdx4 = idx; }
+              }
+            }
+          if (bestIdx2 > 0) { map_out[bestIdx2] = 1.f; bestVal3 = 1e10f; c2++; }
+        }
+      if (bestIdx3 > 0) { map_out[bestIdx3] = 2.f; bestVal4 = 1e10f; c3++; }
+    }
+  if (bestIdx4 > 0) { map_out[bestIdx4] = 4.f; c4++; }
+  if (c2) atomicAdd(&counts[0], c2);
+  if (c3) atomicAdd(&counts[1], c3);
+  if (c4) atomicAdd(&counts[2], c4);
+}
+
+// makeMaps random drop (:231-249): rn = exclusive scan of (map != 0)
+__global__ void nonzero_kernel(const float* __restrict__ map, int n, int* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = (map[i] != 0.f) ? 1 : 0;
+}
+__global__ void subsample_kernel(float* __restrict__ map, const int* __restrict__ rn, int n, const unsigned char* __restrict__ randomPattern,
+                                 int charTH, int* __restrict__ dropped) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (map[i] != 0.f && (int)randomPattern[rn[i]] > charTH) {
+    map[i] = 0.f;
+    atomicAdd(dropped, 1);
+  }
+}
+
+// glibc rand(): TYPE_3 additive feedback generator (r[i] = r[i-3] + r[i-31], 310 outputs discarded, result >> 1)
+void glibc_rand_bytes(unsigned seed, int n, unsigned char* out) {
+  std::vector<int32_t> r(344 + (size_t)n);
+  r[0] = (int32_t)seed;
+  for (int i = 1; i < 31; i++) {
+    long long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+    long long word = 16807 * lo - 2836 * hi;
+    if (word < 0) word += 2147483647;
+    r[i] = (int32_t)word;
+  }
+  for (int i = 31; i < 34; i++) r[i] = r[i - 31];
+  for (size_t i = 34; i < 344 + (size_t)n; i++) r[i] = (int32_t)((uint32_t)r[i - 31] + (uint32_t)r[i - 3]);
+  for (int k = 0; k < n; k++) out[k] = (unsigned char)((((uint32_t)r[344 + k]) >> 1) & 0xFF);
+}
+
+struct SelBuffers {
+  int nSlots;
+  int *selUnamb, *amb, *prefix, *ambPos, *ambList, *blockSums, *flags;
+  unsigned short* masks;
+};
+
+SelGeom make_geom(const nalo_ctx* ctx, int pot, float thFactor) {
+  SelGeom g;
+  g.w = ctx->w0; g.h = ctx->h0;
+  g.w1 = ctx->lw[1]; g.w2 = ctx->lw[2];
+  g.pot = pot;
+  g.nX4 = (g.w + 4 * pot - 1) / (4 * pot);
+  g.nY4 = (g.h + 4 * pot - 1) / (4 * pot);
+  g.thsStep = ctx->w0 / 32;
+  g.off1 = ctx->loff[1]; g.off2 = ctx->loff[2];
+  g.thFactor = thFactor;
+  g.dw1 = ctx->params.gradDownweightPerLevel;
+  g.dw2 = g.dw1 * g.dw1;
+  g.dirDist = ctx->params.selectDirectionDistribution ? 1 : 0;
+  return g;
+}
+
+int run_make_hists(nalo_ctx* ctx, int slot) {
+  const int w32 = ctx->w0 / 32, h32 = ctx->h0 / 32;
+  if (w32 * h32 > 0) {
+    hist_kernel<<<w32 * h32, 256, 0, ctx->stream>>>(ctx->frames[slot].pix, ctx->w0, ctx->h0, w32, ctx->params.minGradHistCut,
+                                                    ctx->params.minGradHistAdd, ctx->d_ths);
+    NALO_CHECK_LAUNCH(ctx);
+    smooth_kernel<<<(w32 * h32 + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_ths, ctx->d_thsSmoothed, w32, h32);
+    NALO_CHECK_LAUNCH(ctx);
+  }
+  ctx->histFrameSlot = slot;
+  return NALO_OK;
+}
+
+// select() into ctx->d_map; n3 = (n2,n3,n4) returned through pinned h_counts[32..34]
+int run_select(nalo_ctx* ctx, int slot, int pot, float thFactor, int n3[3]) {
+  if (pot < 1) pot = 1;
+  SelGeom g = make_geom(ctx, pot, thFactor);
+  const int nB4 = g.nX4 * g.nY4;
+  const int nSlots = nB4 * 16;
+  const size_t need = (size_t)nSlots * 6 + 4096;
+  if (need > ctx->selScratchInts) return nalo_fail(ctx, NALO_E_ARG, "selector scratch too small for pot %d", pot);
+  int* base = ctx->d_selScratch;
+  int* selUnamb = base;
+  int* amb = base + nSlots;
+  int* prefix = base + 2 * (size_t)nSlots;
+  int* ambPos = base + 3 * (size_t)nSlots;
+  int* ambList = base + 4 * (size_t)nSlots;
+  unsigned short* masks = reinterpret_cast<unsigned short*>(base + 5 * (size_t)nSlots);
+  int* blockSums = base + 6 * (size_t)nSlots;
+  int* counts = ctx->d_counts + 32;  // [0..2] n2,n3,n4 ; [3] nAmb ; [4] total
+  const float4* pix = ctx->frames[slot].pix;
+  const size_t n0 = (size_t)ctx->w0 * ctx->h0;
+  NALO_CUDA(ctx, cudaMemsetAsync(ctx->d_map, 0, sizeof(float) * n0, ctx->stream));
+  NALO_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(int) * 8, ctx->stream));
+  block_mask_kernel<<<(nSlots + 255) / 256, 256, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, nSlots, selUnamb, amb, masks);
+  NALO_CHECK_LAUNCH(ctx);
+  int rc = exclusive_scan(ctx, selUnamb, prefix, nSlots, blockSums, counts + 4);
+  if (rc != NALO_OK) return rc;
+  rc = exclusive_scan(ctx, amb, ambPos, nSlots, blockSums, counts + 3);
+  if (rc != NALO_OK) return rc;
+  NALO_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts + 32, counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int nAmb = ctx->h_counts[32 + 3];
+  if (nAmb > 0) {  // rare: direction-dependent blocks — replay them in order, then rescan with their true outcome
+    amb_compact_kernel<<<(nSlots + 255) / 256, 256, 0, ctx->stream>>>(amb, ambPos, nSlots, ambList);
+    NALO_CHECK_LAUNCH(ctx);
+    resolve_kernel<<<1, 32, 0, ctx->stream>>>(ambList, counts + 3, prefix, masks, ctx->d_randomPattern, selUnamb);
+    NALO_CHECK_LAUNCH(ctx);
+    rc = exclusive_scan(ctx, selUnamb, prefix, nSlots, blockSums, counts + 4);
+    if (rc != NALO_OK) return rc;
+  }
+  select_kernel<<<(nB4 + 127) / 128, 128, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, prefix, ctx->d_randomPattern, ctx->d_map, counts);
+  NALO_CHECK_LAUNCH(ctx);
+  NALO_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts + 32, counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 3; k++) n3[k] = ctx->h_counts[32 + k];
+  return NALO_OK;
+}
+
+int check_slot(nalo_ctx* ctx, int slot) {
+  if (!ctx) return NALO_E_ARG;
+  if (slot < 0 || slot >= ctx->maxFrames || !ctx->frames[slot].valid) return nalo_fail(ctx, NALO_E_STATE, "frame slot %d has no pyramid", slot);
+  if (ctx->levels < 3) return nalo_fail(ctx, NALO_E_STATE, "the pixel selector needs >= 3 pyramid levels");
+  return NALO_OK;
+}
+
+}  // namespace
+
+int nalo_select_init(nalo_ctx* ctx) {
+  const size_t n0 = (size_t)ctx->w0 * ctx->h0;
+  std::vector<unsigned char> rp(n0);
+  glibc_rand_bytes(3141592u, (int)n0, rp.data());  // srand(3141592); rand() & 0xFF  (PixelSelector2.cpp:43-45)
+  NALO_CUDA(ctx, cudaMalloc(&ctx->d_randomPattern, n0));
+  NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_randomPattern, rp.data(), n0, cudaMemcpyHostToDevice, ctx->stream));
+  NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int w32 = ctx->w0 / 32, h32 = ctx->h0 / 32;
+  // the reference allocates (w/32)*(h/32)+100 floats; select() can index up to ((w-1)>>5) + ((h-1)>>5)*w32
+  ctx->thsCap = std::max(w32 * h32 + 100, ((ctx->w0 - 1) >> 5) + ((ctx->h0 - 1) >> 5) * w32 + 1);
+  NALO_CUDA(ctx, cudaMalloc(&ctx->d_ths, sizeof(float) * ctx->thsCap));
+  NALO_CUDA(ctx, cudaMalloc(&ctx->d_thsSmoothed, sizeof(float) * ctx->thsCap));
+  NALO_CUDA(ctx, cudaMemsetAsync(ctx->d_ths, 0, sizeof(float) * ctx->thsCap, ctx->stream));
+  NALO_CUDA(ctx, cudaMemsetAsync(ctx->d_thsSmoothed, 0, sizeof(float) * ctx->thsCap, ctx->stream));
+  NALO_CUDA(ctx, cudaMalloc(&ctx->d_map, sizeof(float) * n0));
+  // scratch: pot = 1 is the worst case: ceil(w/4)*ceil(h/4)*16 slots
+  const size_t slotsMax = (size_t)((ctx->w0 + 3) / 4) * ((ctx->h0 + 3) / 4) * 16;
+  ctx->selScratchInts = std::max(slotsMax * 6 + 4096, 2 * n0 + 4096);
+  NALO_CUDA(ctx, cudaMalloc(&ctx->d_selScratch, sizeof(int) * ctx->selScratchInts));
+  return NALO_OK;
+}
+
+void nalo_select_free(nalo_ctx* ctx) {
+  cudaFree(ctx->d_randomPattern); cudaFree(ctx->d_ths); cudaFree(ctx->d_thsSmoothed); cudaFree(ctx->d_map); cudaFree(ctx->d_selScratch);
+}
+
+extern "C" {
+
+// glibc rand() & 0xFF stream used by PixelSelector (exported for the libc-independence KAT; host only)
+void nalo_random_pattern(int n, unsigned char* out) { glibc_rand_bytes(3141592u, n, out); }
+
+int nalo_selector_make_hists(nalo_ctx* ctx, int slot, float* ths_out, float* thsSmoothed_out, int* n_blocks_out) {
+  int rc = check_slot(ctx, slot);
+  if (rc != NALO_OK) return rc;
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  rc = run_make_hists(ctx, slot);
+  if (rc != NALO_OK) return rc;
+  const int nb = (ctx->w0 / 32) * (ctx->h0 / 32);
+  if (ths_out) NALO_CUDA(ctx, cudaMemcpyAsync(ths_out, ctx->d_ths, sizeof(float) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  if (thsSmoothed_out) NALO_CUDA(ctx, cudaMemcpyAsync(thsSmoothed_out, ctx->d_thsSmoothed, sizeof(float) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_blocks_out) *n_blocks_out = nb;
+  return NALO_OK;
+}
+
+int nalo_selector_select(nalo_ctx* ctx, int slot, int pot, float thFactor, float* map_out_host, int n3_out[3]) {
+  int rc = check_slot(ctx, slot);
+  if (rc != NALO_OK) return rc;
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->histFrameSlot != slot) {
+    rc = run_make_hists(ctx, slot);
+    if (rc != NALO_OK) return rc;
+  }
+  int n3[3];
+  rc = run_select(ctx, slot, pot, thFactor, n3);
+  if (rc != NALO_OK) return rc;
+  if (n3_out) for (int k = 0; k < 3; k++) n3_out[k] = n3[k];
+  if (map_out_host) {
+    NALO_CUDA(ctx, cudaMemcpyAsync(map_out_host, ctx->d_map, sizeof(float) * (size_t)ctx->w0 * ctx->h0, cudaMemcpyDeviceToHost, ctx->stream));
+    NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return NALO_OK;
+}
+
+// PixelSelector::makeMaps (:144-291)
+int nalo_select_pixels(nalo_ctx* ctx, int slot, float density, int recursionsLeft, float thFactor, int* currentPotential_inout,
+                       float* map_out_host, int* n_out) {
+  int rc = check_slot(ctx, slot);
+  if (rc != NALO_OK) return rc;
+  if (!currentPotential_inout) return NALO_E_ARG;
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  int currentPotential = *currentPotential_inout;
+  float numHave = 0, numWant = density, quotia = 0;
+  int idealPotential = currentPotential;
+  if (ctx->histFrameSlot != slot) {  // `if(fh != gradHistFrame) makeHists(fh)`
+    rc = run_make_hists(ctx, slot);
+    if (rc != NALO_OK) return rc;
+  }
+  for (;;) {
+    int n[3];
+    rc = run_select(ctx, slot, currentPotential, thFactor, n);
+    if (rc != NALO_OK) return rc;
+    numHave = (float)(n[0] + n[1] + n[2]);
+    quotia = numWant / numHave;
+    const float K = numHave * (currentPotential + 1) * (currentPotential + 1);
+    idealPotential = (int)(sqrtf(K / numWant) - 1);
+    if (idealPotential < 1) idealPotential = 1;
+    if (recursionsLeft > 0 && quotia > 1.25 && currentPotential > 1) {
+      if (idealPotential >= currentPotential) idealPotential = currentPotential - 1;
+      currentPotential = idealPotential;
+      recursionsLeft--;
+      continue;
+    } else if (recursionsLeft > 0 && quotia < 0.25) {
+      if (idealPotential <= currentPotential) idealPotential = currentPotential + 1;
+      currentPotential = idealPotential;
+      recursionsLeft--;
+      continue;
+    }
+    break;
+  }
+  int numHaveSub = (int)numHave;
+  const int n0 = ctx->w0 * ctx->h0;
+  if (quotia < 0.95) {
+    const unsigned char charTH = (unsigned char)(255 * quotia);
+    int* flags = ctx->d_selScratch;
+    int* rn = ctx->d_selScratch + n0;
+    int* blockSums = ctx->d_scan;
+    int* dropped = ctx->d_counts + 48;
+    NALO_CUDA(ctx, cudaMemsetAsync(dropped, 0, sizeof(int), ctx->stream));
+    nonzero_kernel<<<(n0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_map, n0, flags);
+    NALO_CHECK_LAUNCH(ctx);
+    rc = exclusive_scan(ctx, flags, rn, n0, blockSums, nullptr);
+    if (rc != NALO_OK) return rc;
+    subsample_kernel<<<(n0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_map, rn, n0, ctx->d_randomPattern, (int)charTH, dropped);
+    NALO_CHECK_LAUNCH(ctx);
+    NALO_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts + 48, dropped, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    numHaveSub -= ctx->h_counts[48];
+  }
+  *currentPotential_inout = idealPotential;
+  if (map_out_host) {
+    NALO_CUDA(ctx, cudaMemcpyAsync(map_out_host, ctx->d_map, sizeof(float) * (size_t)n0, cudaMemcpyDeviceToHost, ctx->stream));
+    NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (n_out) *n_out = numHaveSub;
+  return NALO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+"""GPU: a11 multi-hypothesis tracking + winner rule, and the batched frame-pair alignments (configs 3 and 5)."""
+import numpy as np
+import pytest
+
+from conftest import make_oracle_tracker
+from nalo_slam_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _history(P):
+    """A constant-velocity camera history whose prediction is close to the true refToNew."""
+    gt = P["gt"]
+    from oracle import oracle_py as O
+
+    lastF = synth.pose_identity()                       # reference keyframe at the origin
+    new_c2w = O.se3_inverse(gt)                          # camToWorld of the new frame
+    xi = O.se3_log(new_c2w)
+    slast = O.se3_exp(0.5 * xi)                          # previous frame half way
+    sprelast = synth.pose_identity()
+    return sprelast, slast, lastF
+
+
+def test_motion_candidates_match_oracle(small_pair, oracle):
+    sprelast, slast, lastF = _history(small_pair)
+    a = capi.motion_candidates(sprelast, slast, lastF)
+    b = oracle.motion_candidates(sprelast, slast, lastF)
+    assert a.shape == (31, 7) and b.shape == (31, 7)
+    assert np.allclose(a, b, atol=1e-14, rtol=0)
+    assert capi.motion_candidates(sprelast, slast, lastF, poses_valid=False).shape == (1, 7)
+
+
+def _setup(ctx, P, oracle):
+    T, idw, ws = make_oracle_tracker(oracle, P)
+    ctx.make_images(0, P["ref"])
+    ctx.make_images(1, P["new"])
+    ctx.make_k(0, *P["scene"].K)
+    ctx.set_ref_dense(0, 0, idw, ws)
+    return T
+
+
+@pytest.mark.parametrize("rmse0", [1e9, 0.0])
+def test_multi_hypothesis_winner_rule(rmse0, small_pair, gpu_ctx_small, oracle):
+    """All 31 candidates tracked concurrently + replayed winner rule == the oracle's sequential loop
+    (rmse0 = 1e9: early break after the first good try; rmse0 = 0: no early break, all 31 tries, with aborts)."""
+    P = small_pair
+    ctx = gpu_ctx_small
+    T = _setup(ctx, P, oracle)
+    tries = capi.motion_candidates(*_history(P))
+    aff_last = np.array([0.0, 0.0])
+    rmse = np.full(5, rmse0)
+    ref = T.track_new_coarse(tries, aff_last, rmse)
+    res = ctx.track_multi(0, 1, tries, np.tile(aff_last, (len(tries), 1)))
+    got = capi.winner_rule(res, aff_last, rmse)
+    assert got["good"] == ref["good"] and got["tries"] == ref["tries"]
+    dt, dr = synth.pose_distance(got["pose"], ref["pose"])
+    assert dt < 1e-5 and dr < 1e-5, (dt, dr)
+    assert np.allclose(got["achievedRes"], ref["achievedRes"], rtol=1e-3, equal_nan=True)
+    assert np.allclose(got["flow"], ref["flow"], rtol=1e-3, atol=1e-6)
+    assert res["stats"]["launches"] == 1
+    if rmse0 == 0.0:
+        assert got["tries"] == 31
+
+
+def test_multi_equals_single(small_pair, gpu_ctx_small, oracle):
+    """A candidate tracked inside a multi launch (small CTA group) gives the same pose as tracked alone (all SMs):
+    the group size changes the summation tree only."""
+    P = small_pair
+    ctx = gpu_ctx_small
+    _setup(ctx, P, oracle)
+    tries = capi.motion_candidates(*_history(P))[:5]
+    res = ctx.track_multi(0, 1, tries, np.zeros((5, 2)))
+    for i in range(5):
+        ok, pose, aff, lr, fl, st = ctx.track(0, 1, tries[i], [0, 0])
+        assert ok == bool(res["ok"][i])
+        dt, dr = synth.pose_distance(pose, res["poses"][i])
+        assert dt < 1e-6 and dr < 1e-6
+
+
+def test_batch_pairs(small_pair, gpu_ctx_small, oracle):
+    """Independent pairs in one launch: each result equals the single-pair track and recovers its own ground truth."""
+    P = small_pair
+    w, h, L = P["w"], P["h"], P["L"]
+    ctx = gpu_ctx_small
+    ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)
+    B = capi.Batch(ctx, 6)
+    rng = np.random.default_rng(21)
+    gts, singles = [], []
+    for i in range(6):
+        sc = synth.make_scene(w, h, seed=100 + i)
+        xi, aff = synth.random_motion(rng, 0.5)
+        gt = synth.se3_exp(xi)
+        ref = synth.render_ref(sc)
+        new = synth.render_new(sc, gt, aff)
+        _, ag = oracle.make_images(ref, w, h, L)
+        idw, ws = synth.dense_reference_maps(sc, ag[: w * h])
+        B.set_pair(i, ref, idw, ws, new, sc.K)
+        gts.append(gt)
+        # the same pair through the single-frame path
+        ctx.make_images(0, ref)
+        ctx.make_images(1, new)
+        ctx.make_k(0, *sc.K)
+        ctx.set_ref_dense(0, 0, idw, ws)
+        singles.append(ctx.track(0, 1, synth.pose_identity(), [0, 0]))
+    out = B.track(0, 6)
+    assert out["stats"]["launches"] == 2  # tracking kernel + result packing
+    for i in range(6):
+        assert out["ok"][i] == 1 and singles[i][0]
+        dt, dr = synth.pose_distance(out["poses"][i], singles[i][1])
+        assert dt < 1e-6 and dr < 1e-6, (i, dt, dr)
+        dt, dr = synth.pose_distance(out["poses"][i], gts[i])
+        assert dt < 3e-3 and dr < 3e-4
+    # a sub-range gives the same answers
+    # a sub-range gives the same answers (a different CTA-group size only changes the fp32 summation tree)
+    out2 = B.track(2, 3)
+    for k in range(3):
+        dt, dr = synth.pose_distance(out2["poses"][k], out["poses"][2 + k])
+        assert dt < 1e-6 and dr < 1e-6
+    B.close()
+
+
+def test_batch_synth_pair_on_device(small_pair, gpu_ctx_small, oracle):
+    """Device-side synthetic pair generation (bench utility) agrees with the numpy renderer and tracks to ground truth."""
+    P = small_pair
+    w, h, L = P["w"], P["h"], P["L"]
+    ctx = gpu_ctx_small
+    sc = synth.make_scene(w, h, seed=5)
+    rng = np.random.default_rng(5)
+    xi, aff = synth.random_motion(rng, 0.5)
+    gt = synth.se3_exp(xi)
+    _, ag = oracle.make_images(synth.render_ref(sc), w, h, L)
+    tau = float(np.quantile(ag[: w * h], 1 - 0.43))
+    B = capi.Batch(ctx, 2)
+    B.synth_pair(0, capi.scene_param_block(sc), gt, aff, tau)
+    dI, _ = ctx.get_frame(1)  # new frame pyramid left in slot 1
+    new = synth.render_new(sc, gt, aff)
+    assert np.max(np.abs(dI[: w * h, 0] - new.ravel())) < 2e-3
+    out = B.track(0, 1)
+    dt, dr = synth.pose_distance(out["poses"][0], gt)
+    assert out["ok"][0] == 1 and dt < 3e-3 and dr < 3e-4
+    B.close()
