@@ -1,0 +1,85 @@
+"""CPU: the oracle reproduces the committed golden vectors (tests/golden/oracle_small.npz, made by make_golden.py).
+GPU: the CUDA path through the C ABI reproduces the same goldens (bit-exact for masks/maps/indices, 1e-4 / 1e-5 bars)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "oracle_small.npz")
+
+
+def _load_generator():
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_oracle_matches_golden(oracle):
+    g = np.load(GOLD)
+    cur = _load_generator().compute(g["input_ref"], g["input_new"])
+    for k in cur:
+        a, b = cur[k], g[k]
+        if a.dtype.kind in "US" or a.dtype.kind in "iub":
+            assert np.array_equal(a, b), k
+        else:
+            assert np.allclose(a, b, rtol=1e-6, atol=1e-9 * (1 + np.abs(b).max()), equal_nan=True), k
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden():
+    from nalo_slam_b200 import capi, synth
+
+    mg = _load_generator()
+    g = np.load(GOLD)
+    w, h, L, sc, gt, aff = mg.scene_and_motion()
+    ref, new = g["input_ref"], g["input_new"]
+    ctx = capi.Context(w, h, L, device=0, max_frames=2)
+    ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)
+    dI, ag = ctx.make_images(0, ref, want_host=True)
+    assert mg.sha(dI) == g["a1_sha"][0] and mg.sha(ag) == g["a1_sha"][1]
+    ctx.make_images(1, new)
+    _, thsS = ctx.selector_make_hists(0)
+    assert np.array_equal(thsS, g["a2_thsSmoothed"])
+    for i, pot in enumerate((1, 2, 3, 5)):
+        m, n = ctx.selector_select(0, pot)
+        assert np.array_equal(n, g["a3_counts"][i]) and mg.sha(m) == g["a3_sha"][i]
+    n_sub, m, pot = ctx.select_pixels(0, 1500, 3)
+    assert (n_sub, pot) == tuple(g["a4"]) and mg.sha(m) == g["a4_sha"][0]
+    idw, ws = synth.dense_reference_maps(sc, ag[: w * h])
+    ctx.make_k(0, *sc.K)
+    ctx.set_ref_dense(0, 0, idw, ws)
+    assert [ctx.ref_count(0, l) for l in range(L)] == g["a5_pc_n"].tolist()
+    for l in range(L):
+        assert mg.sha(np.stack(ctx.ref_points(0, l))) == g["a5_sha"][l]
+    ctx.set_new_frame(0, 1)
+    p0 = synth.pose_identity()
+    rs, mask = ctx.calc_res(0, 0, p0, [0, 0], 20.0)
+    assert mg.sha(mask) == g["a6_mask_sha"][0] and rs[1] == g["a6_rs"][1] and rs[5] == g["a6_rs"][5]
+    assert abs(rs[0] - g["a6_rs"][0]) <= 1e-4 * g["a6_rs"][0]
+    H, b = ctx.calc_gs(0, 0, p0, [0, 0])
+    d = np.sqrt(np.diag(g["a7_H"]))
+    assert np.all(np.abs(H - g["a7_H"]) <= 1e-4 * np.outer(d, d))
+    ok, pose, a2, lr, fl, _ = ctx.track(0, 1, p0, [0, 0])
+    assert ok == bool(g["a8_ok"][0])
+    assert max(synth.pose_distance(pose, g["a8_pose"])) < 1e-5
+    assert np.allclose(lr, g["a8_lastRes"], rtol=1e-3, equal_nan=True)
+    tries = capi.motion_candidates(synth.pose_identity(), mg.O.se3_exp(0.5 * mg.O.se3_log(mg.O.se3_inverse(gt))), synth.pose_identity())
+    assert np.allclose(tries, g["a11_tries"], atol=1e-13)
+    res = ctx.track_multi(0, 1, tries, np.zeros((31, 2)))
+    out = capi.winner_rule(res, [0, 0], np.zeros(5))
+    assert out["tries"] == int(g["a11_tries_used"][0]) and max(synth.pose_distance(out["pose"], g["a11_pose"])) < 1e-5
+    prob = synth.make_ba_problem(nf=4, pts_per_frame=30, seed=8, lin_fraction=0.25)
+    ba = capi.BA(ctx, 1024, 256)
+    ba.upload(prob)
+    for mode in (0, 1, 2):
+        Hb, pp, n = ba.accumulate_top(mode)
+        Ho = g[f"a9_H_mode{mode}"]
+        assert n == int(g[f"a9_n_mode{mode}"][0])
+        for k in range(Ho.shape[0]):
+            dd = np.sqrt(np.abs(np.diag(Ho[k])))
+            assert np.all(np.abs(Hb[k] - Ho[k]) <= 1e-4 * np.outer(dd, dd) + 1e-9)
+    ba.close()
+    ctx.close()
