@@ -218,11 +218,15 @@ def run_b200(args, rank, world, local_rank):
         ctx.make_images(1, pin_imgs[i % N_FRAMES])
         return ctx.track(0, 1, p0, [0.0, 0.0])
 
+    ctx.set_profiling(True)  # CUDA events around the tracking kernel (roofline.kernel_ms); off again for the e2e arm
     for i in range(Wu):
         ctx.flush_l2()
         step_dev(i)
     torch.cuda.synchronize()
     if dist:
+        warm = torch.zeros((K, 16), dtype=torch.float64, device="cuda")
+        dist.all_gather([torch.empty_like(warm) for _ in range(world)], warm)  # NCCL warm-up (communicator setup), untimed
+        torch.cuda.synchronize()
         dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -270,6 +274,7 @@ def run_b200(args, rank, world, local_rank):
         job_res, job_iters, job_launches = float(tot_res), float(tot_iters), float(launches)
 
     # ---- e2e arm: host image in, pose out, wall clock, through the C ABI
+    ctx.set_profiling(False)
     for i in range(min(Wu, 3)):
         step_host(i)
     if dist:

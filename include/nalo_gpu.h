@@ -76,6 +76,9 @@ int nalo_destroy(nalo_ctx* ctx);
 const char* nalo_last_error(const nalo_ctx* ctx); /* ctx may be NULL: last creation error */
 int nalo_set_params(nalo_ctx* ctx, const NaloParams* p);
 int nalo_get_params(const nalo_ctx* ctx, NaloParams* p);
+/* Record CUDA events around the tracking kernel so NaloTrackStats::kernel_ms is filled (off by default: it adds an
+ * event synchronisation to every nalo_track call). */
+int nalo_set_profiling(nalo_ctx* ctx, int on);
 int nalo_sync(nalo_ctx* ctx);            /* cudaStreamSynchronize on the context stream */
 void* nalo_stream(nalo_ctx* ctx);        /* the context's cudaStream_t (for event timing by the caller) */
 long long nalo_kernel_launches(const nalo_ctx* ctx); /* kernels launched so far by this context */

@@ -179,6 +179,9 @@ class Context:
             setattr(p, k, v)
         self._ck(self.L.nalo_set_params(self.h_, C.byref(p)))
 
+    def set_profiling(self, on=True):
+        self._ck(self.L.nalo_set_profiling(self.h_, C.c_int(1 if on else 0)))
+
     def sync(self):
         self._ck(self.L.nalo_sync(self.h_))
 

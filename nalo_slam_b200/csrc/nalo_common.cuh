@@ -100,6 +100,11 @@ struct nalo_ctx {
   NaloTrackResult* d_results = nullptr;
   NaloTrackProblem* h_problems = nullptr;  // pinned
   NaloTrackResult* h_results = nullptr;    // pinned
+  NaloTrackResult* h_resMapped = nullptr;  // mapped pinned: single-track result + completion word
+  NaloTrackResult* d_resMapped = nullptr;  // its device alias
+  uint32_t trackLaunchId = 0;
+  uint32_t doneToken = 0;
+  bool profiling = false;                  // record CUDA events around the tracking kernel (NaloTrackStats::kernel_ms)
   unsigned long long* d_xchg = nullptr;  // flagged 64-bit exchange words of the tracking groups
   size_t xchgBytes = 0;
   int maxGroups = 0;
