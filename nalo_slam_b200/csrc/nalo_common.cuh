@@ -75,6 +75,7 @@ struct NaloTrackResult {
 
 struct NaloSettingsDev {
   float huberTH, coarseCutoffTH, affineOptModeA, affineOptModeB;
+  int stagedMinIters;  // evaluation loops with at least this many points per thread use the cp.async pipeline
 };
 
 struct nalo_ctx {
@@ -103,6 +104,7 @@ struct nalo_ctx {
   NaloTrackResult* h_resMapped = nullptr;  // mapped pinned: single-track result + completion word
   NaloTrackResult* d_resMapped = nullptr;  // its device alias
   uint32_t trackLaunchId = 0;
+  int* d_trackQueue = nullptr;             // atomic work queue of single-CTA groups (batched alignments)
   uint32_t doneToken = 0;
   bool profiling = false;                  // record CUDA events around the tracking kernel (NaloTrackStats::kernel_ms)
   unsigned long long* d_xchg = nullptr;  // flagged 64-bit exchange words of the tracking groups
@@ -158,4 +160,5 @@ void nalo_track_free(nalo_ctx* ctx);
 int nalo_select_init(nalo_ctx* ctx);
 void nalo_select_free(nalo_ctx* ctx);
 void nalo_fill_problem(nalo_ctx* ctx, int trk, NaloTrackProblem* P);
-int nalo_track_launch(nalo_ctx* ctx, int nProblems, int blocksPerProblem, const NaloTrackProblem* d_problems, NaloTrackResult* d_results);
+int nalo_track_launch(nalo_ctx* ctx, int nProblems, int blocksPerProblem, const NaloTrackProblem* d_problems, NaloTrackResult* d_results,
+                      bool streamed);

@@ -168,7 +168,7 @@ int nalo_track_multi(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, i
   }
   NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_problems, ctx->h_problems, sizeof(NaloTrackProblem) * nHyp, cudaMemcpyHostToDevice, ctx->stream));
   if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evA, ctx->stream));
-  rc = nalo_track_launch(ctx, nHyp, ctx->maxGroups / nHyp, ctx->d_problems, ctx->d_results);
+  rc = nalo_track_launch(ctx, nHyp, ctx->maxGroups / nHyp, ctx->d_problems, ctx->d_results, /*streamed=*/false);
   if (rc != NALO_OK) return rc;
   if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));
   NALO_CUDA(ctx, cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(NaloTrackResult) * nHyp, cudaMemcpyDeviceToHost, ctx->stream));
