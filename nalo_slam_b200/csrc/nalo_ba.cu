@@ -43,14 +43,19 @@ struct nalo_ba {
   float* d_ppSC = nullptr;       // [maxPts][4]  HdiF, bdSumF, idepth_hessian, (pad)
   int* d_ptHost = nullptr;       // [maxPts]
   int* d_ptOrder = nullptr;      // [maxPts] points sorted by host
-  int4* d_items = nullptr;       // work items
+  int4* d_items = nullptr;       // work items: [0, nTop) top items, [maxItems, maxItems + nSc) Schur items (uploaded once)
+  int* d_ptSlots = nullptr;      // [maxPts][8] per point in host-sorted order: record of the residual to target block tb (-1: none/inactive), [7] = point index
+  double* h_out = nullptr;       // pinned staging of the small fp64 results
   float* d_partials = nullptr;   // top: [items][96] ; sc: [items][72*72]
   double* d_out = nullptr;       // result staging (double)
   int* d_counter = nullptr;
+  int* d_itemRange = nullptr;    // [65] first item of every bucket / host
+  std::vector<int> topRange, scRange;
   std::vector<int4> topItems;    // (bucket, first, count, 0)
   std::vector<int4> scItems;     // (host, firstInOrder, count, 0)
   std::vector<int> hostBegin;    // [nf+1] into ptOrder
   bool haveA = false, haveL = false, haveJpJd = false;
+  bool haveJpJdDev = false;      // d_jpjd is current for the uploaded records
   size_t partialFloats = 0, outDoubles = 0;
   int maxItems = 0;
 };
@@ -97,6 +102,7 @@ struct TopArgs {
   float* contrib;
   float* partials;
   int* counter;
+  float* jpjd;  // nullable: also emit EFResidual::takeDataF's JpJdF of every record that streams through
   int nf, mode;
 };
 
@@ -226,6 +232,21 @@ __global__ void __launch_bounds__(TOP_THREADS) top_kernel(TopArgs A) {
       float4* co = reinterpret_cast<float4*>(A.contrib + (size_t)ri * 8);
       co[0] = make_float4(c6[0], c6[1], c6[2], c6[3]);
       co[1] = make_float4(c6[4], c6[5], 0.f, 0.f);
+      if (A.jpjd) {
+        // EFResidual::takeDataF (EnergyFunctionalStructs.cpp:39-50), exact-op fp32 like take_data_kernel: the record is
+        // in registers anyway, so the separate 304 B/residual pass over the records is saved
+        const float jd0 = r[O_JPDD], jd1 = r[O_JPDD + 1];
+        const float d0 = __fadd_rn(__fmul_rn(r[O_JIDX2], jd0), __fmul_rn(r[O_JIDX2 + 1], jd1));
+        const float d1 = __fadd_rn(__fmul_rn(r[O_JIDX2 + 1], jd0), __fmul_rn(r[O_JIDX2 + 2], jd1));
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < 6; q++) o[q] = __fadd_rn(__fmul_rn(r[O_JPDXI + q], d0), __fmul_rn(r[O_JPDXI + 6 + q], d1));
+        o[6] = __fadd_rn(__fmul_rn(r[O_JABJIDX + 0], jd0), __fmul_rn(r[O_JABJIDX + 1], jd1));
+        o[7] = __fadd_rn(__fmul_rn(r[O_JABJIDX + 2], jd0), __fmul_rn(r[O_JABJIDX + 3], jd1));
+        float4* jo = reinterpret_cast<float4*>(A.jpjd + (size_t)ri * 8);
+        jo[0] = make_float4(o[0], o[1], o[2], o[3]);
+        jo[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
     }
     __syncthreads();  // everyone is done with this stage's buffer
     if (threadIdx.x == 0 && s + 2 < nStages) issue(s + 2);
@@ -251,14 +272,26 @@ __global__ void __launch_bounds__(TOP_THREADS) top_kernel(TopArgs A) {
 }
 
 // per bucket: sum the partials of its items in order (fp64) and expand to the 13x13 symmetric block
-__global__ void top_finalize_kernel(const float* __restrict__ partials, const int4* __restrict__ items, int nItems, int nBuckets,
-                                    double* __restrict__ H_out) {
+// itemRange[b], itemRange[b+1]: the (contiguous, host-computed) items of bucket b. 8 x 96 threads: thread (q, j) sums
+// entry j of items q, q+8, ...; the 8 partial sums are folded in fixed order (fp64, deterministic).
+__global__ void __launch_bounds__(768) top_finalize_kernel(const float* __restrict__ partials, const int* __restrict__ itemRange, int nBuckets,
+                                                          double* __restrict__ H_out) {
   const int bucket = blockIdx.x;
+  __shared__ double part[8][96];
   __shared__ double s91[91];
-  if (threadIdx.x < 91) {
+  const int j = threadIdx.x % 96, q = threadIdx.x / 96;
+  {
     double s = 0.0;
-    for (int i = 0; i < nItems; i++)  // items are sorted by bucket; a linear scan is cheap (nItems ~ 1e3)
-      if (items[i].x == bucket) s += (double)partials[(size_t)i * 96 + threadIdx.x];
+    const int i1 = itemRange[bucket + 1];
+    if (j < 91)
+      for (int i = itemRange[bucket] + q; i < i1; i += 8) s += (double)partials[(size_t)i * 96 + j];
+    part[q][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 91) {
+    double s = part[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; k++) s += part[k][threadIdx.x];
     s91[threadIdx.x] = s;
   }
   __syncthreads();
@@ -272,8 +305,8 @@ __global__ void top_finalize_kernel(const float* __restrict__ partials, const in
     } else if (lo < 10) {
       v = s91[55 + 3 * lo + (hi - 10)];
     } else {
-      const int i = lo - 10, j = hi - 10;  // (10,10)=0 (10,11)=1 (10,12)=2 (11,11)=3 (11,12)=4 (12,12)=5
-      const int idx = (i == 0) ? j : (i == 1 ? 2 + j : 5);
+      const int i = lo - 10, jj = hi - 10;  // (10,10)=0 (10,11)=1 (10,12)=2 (11,11)=3 (11,12)=4 (12,12)=5
+      const int idx = (i == 0) ? jj : (i == 1 ? 2 + jj : 5);
       v = s91[85 + idx];
     }
     H_out[(size_t)bucket * 169 + threadIdx.x] = v;
@@ -311,17 +344,18 @@ __global__ void take_data_kernel(const float* __restrict__ rec, int nRes, float*
   out[1] = make_float4(o[4], o[5], o[6], o[7]);
 }
 
-// AccumulatedSCHessianSSE::addPoint prologue (:36-55): per point HdiF, bdSumF, idepth_hessian
-__global__ void sc_point_kernel(const float* __restrict__ rec, const int* __restrict__ ptBegin, const int* __restrict__ ptRes,
-                                const float* __restrict__ ppA, const float* __restrict__ ppL, const float* __restrict__ priorF,
-                                const float* __restrict__ deltaF, int shiftPriorToZero, int nPts, float* __restrict__ ppSC) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= nPts) return;
-  int ngood = 0;
-  for (int k = ptBegin[p]; k < ptBegin[p + 1]; k++) {
-    const uint32_t pack = __float_as_uint(rec[(size_t)ptRes[k] * REC + O_PACK]);
-    if ((pack >> 16) & 1) ngood++;
-  }
+// AccumulatedSCHessianSSE::addPoint prologue (:36-55): per point HdiF, bdSumF, idepth_hessian.
+// ptSlots: per point (host-sorted position) 8 ints — record index of the ACTIVE residual to target block tb = 0..6
+// (-1: none), and in [7] the point index. Built once per upload, so no pass of the Schur stage chases
+// point -> residual list -> record flags.
+__global__ void sc_point_kernel(const int* __restrict__ ptSlots, const float* __restrict__ ppA, const float* __restrict__ ppL,
+                                const float* __restrict__ priorF, const float* __restrict__ deltaF, int shiftPriorToZero, int nPts,
+                                float* __restrict__ ppSC) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= nPts) return;
+  const int4 s0 = __ldg(reinterpret_cast<const int4*>(ptSlots) + 2 * pos), s1 = __ldg(reinterpret_cast<const int4*>(ptSlots) + 2 * pos + 1);
+  const int p = s1.w;
+  const int ngood = (s0.x >= 0) + (s0.y >= 0) + (s0.z >= 0) + (s0.w >= 0) + (s1.x >= 0) + (s1.y >= 0) + (s1.z >= 0);
   float HdiF = 0.f, bdSum = 0.f, Hh = 0.f;
   if (ngood > 0) {
     const float HddL = ppL ? ppL[(size_t)p * 6] : 0.f, bdL = ppL ? ppL[(size_t)p * 6 + 1] : 0.f;
@@ -333,107 +367,196 @@ __global__ void sc_point_kernel(const float* __restrict__ rec, const int* __rest
     bdSum = __fadd_rn(ppA[(size_t)p * 6 + 1], bdL);
     if (shiftPriorToZero) bdSum = __fadd_rn(bdSum, __fmul_rn(pr, dl));
   }
-  ppSC[(size_t)p * 4 + 0] = HdiF;
-  ppSC[(size_t)p * 4 + 1] = bdSum;
-  ppSC[(size_t)p * 4 + 2] = Hh;
-  ppSC[(size_t)p * 4 + 3] = (float)ngood;
+  reinterpret_cast<float4*>(ppSC)[p] = make_float4(HdiF, bdSum, Hh, (float)ngood);
 }
 
-#define SC_DIM 72
+// ---- Schur-complement accumulation as a symmetric rank-k update ---------------------------------------------------
+// For the points hosted in frame h:  S_h = sum_p HdiF_p a_p a_p^T  with
+//   a_p = [ JpJdF(p -> target) for every target != h, 8 columns each | Hcd_p (4) | bdSumF_p (1) ],  dim = 8(nf-1)+5.
+// Its blocks are exactly accD[h,t1,t2] (8x8), accE[h,t] (8x4), accEB[h,t] (8), accHcc (4x4) and accbc (4)
+// (AccumulatedSCHessian.cpp:56-75). Only the upper triangle is computed, in 6x6 register tiles: nT = ceil(dim/6) tile
+// rows, nU = nT(nT+1)/2 tiles, each owned by `ks` threads that split the points of the chunk between them.
+// Rows are staged in shared memory 64 points at a time; the gather of the NEXT chunk (2 independent tasks per thread,
+// 2 dependent loads deep) is issued into registers before the current chunk is multiplied, so its latency is hidden.
 #define SC_TILE 6
-#define SC_TPB ((SC_DIM / SC_TILE) * (SC_DIM / SC_TILE))  // 144
-#define SC_ROWS 32
-// SYRK over a chunk of the points hosted in one frame: partial[item][72][72] = sum_p HdiF_p a_p a_p^T
-__global__ void __launch_bounds__(SC_TPB) sc_kernel(const float* __restrict__ rec, const float* __restrict__ JpJdF, const int* __restrict__ ptBegin,
-                                                    const int* __restrict__ ptRes, const int* __restrict__ ptOrder, const float* __restrict__ ppA,
+#define SC_MAXT 11                      // nf = 8: dim 61 -> 11 tile rows
+#define SC_MAXDIM (SC_MAXT * SC_TILE)   // 66
+#define SC_MAXU (SC_MAXT * (SC_MAXT + 1) / 2)
+#define SC_TPB 256
+#define SC_CHUNK 64                     // points staged per round (x 8 tasks = 2 per thread)
+#define SC_ITEM_PTS 256                 // points per work item (CTA)
+#define SC_PART (SC_MAXU * 36)          // floats per item partial (upper tiles, 36 each)
+
+struct ScTask {
+  float4 a, b;  // 8 columns
+  float w;      // point task only: HdiF
+};
+// task (row, slot): slot < 7 -> JpJdF of target block `slot`; slot == 7 -> the point's own columns {Hcd[4], bdSum} + weight
+__device__ __forceinline__ void sc_fetch(ScTask& t, int pos, int slot, bool inRange, const int* __restrict__ ptSlots,
+                                         const float* __restrict__ JpJdF, const float* __restrict__ ppA, const float* __restrict__ ppL,
+                                         const float* __restrict__ ppSC) {
+  t.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  t.b = t.a;
+  t.w = 0.f;
+  if (!inRange) return;
+  const int v = __ldg(ptSlots + (size_t)pos * 8 + slot);
+  if (slot < 7) {
+    if (v >= 0) {
+      const float4* j4 = reinterpret_cast<const float4*>(JpJdF + (size_t)v * 8);
+      t.a = __ldg(j4);
+      t.b = __ldg(j4 + 1);
+    }
+  } else {
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(ppSC) + v);
+    t.w = sc.x;
+    const float* A = ppA + (size_t)v * 6 + 2;
+    float h0 = __ldg(A), h1 = __ldg(A + 1), h2 = __ldg(A + 2), h3 = __ldg(A + 3);
+    if (ppL) {
+      const float* L = ppL + (size_t)v * 6 + 2;
+      h0 = __fadd_rn(h0, __ldg(L)); h1 = __fadd_rn(h1, __ldg(L + 1)); h2 = __fadd_rn(h2, __ldg(L + 2)); h3 = __fadd_rn(h3, __ldg(L + 3));
+    }
+    t.a = make_float4(h0, h1, h2, h3);
+    t.b = make_float4(sc.y, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(SC_TPB) sc_kernel(const float* __restrict__ JpJdF, const int* __restrict__ ptSlots, const float* __restrict__ ppA,
                                                     const float* __restrict__ ppL, const float* __restrict__ ppSC, const int4* __restrict__ items,
                                                     int nf, float* __restrict__ partials) {
-  __shared__ float rows[SC_ROWS][SC_DIM];
-  __shared__ float wts[SC_ROWS];
+  // one buffer, two lives: the staged rows [SC_CHUNK][SC_MAXDIM] during the update, the per-thread tiles for the final fold
+  __shared__ __align__(16) float buf[SC_TPB * 36];
+  __shared__ float wts[SC_CHUNK];
+  static_assert(SC_CHUNK * SC_MAXDIM <= SC_TPB * 36, "row staging must fit in the fold buffer");
+  static_assert(SC_CHUNK * 8 == 2 * SC_TPB, "two gather tasks per thread");
+  float (*rows)[SC_MAXDIM] = reinterpret_cast<float (*)[SC_MAXDIM]>(buf);
+  float* red = buf;
   const int4 item = items[blockIdx.x];
   const int first = item.y, count = item.z;
-  const int ti = threadIdx.x / (SC_DIM / SC_TILE), tj = threadIdx.x % (SC_DIM / SC_TILE);
+  const int dim = 8 * (nf - 1) + 5;
+  const int nT = (dim + SC_TILE - 1) / SC_TILE, nU = nT * (nT + 1) / 2;
+  int ks = SC_TPB / nU;
+  if (ks > 5) ks = 5;
+  // tile of this thread: u -> (ti <= tj)
+  const int u = threadIdx.x % nU, kq = threadIdx.x / nU;
+  const bool worker = kq < ks;
+  int ti = 0, rem = u;
+  while (rem >= nT - ti) { rem -= nT - ti; ti++; }
+  const int tj = ti + rem;
   float acc[SC_TILE][SC_TILE];
 #pragma unroll
   for (int i = 0; i < SC_TILE; i++)
 #pragma unroll
     for (int j = 0; j < SC_TILE; j++) acc[i][j] = 0.f;
-  const int colHcd = nf * 8, colB = nf * 8 + 4;
-  for (int base = 0; base < count; base += SC_ROWS) {
-    const int nrows = min(SC_ROWS, count - base);
-    for (int e = threadIdx.x; e < SC_ROWS * SC_DIM; e += SC_TPB) (&rows[0][0])[e] = 0.f;
-    __syncthreads();
-    // fill: thread (row, slot) copies one residual's JpJdF into its target's 8 columns
-    for (int e = threadIdx.x; e < nrows * 8; e += SC_TPB) {
-      const int row = e >> 3, slot = e & 7;
-      const int p = ptOrder[first + base + row];
-      const int k = ptBegin[p] + slot;
-      if (k < ptBegin[p + 1]) {
-        const int ri = ptRes[k];
-        const uint32_t pack = __float_as_uint(rec[(size_t)ri * REC + O_PACK]);
-        if ((pack >> 16) & 1) {
-          const int t = (pack >> 8) & 0xFF;
-          const float4* j4 = reinterpret_cast<const float4*>(JpJdF + (size_t)ri * 8);
-          const float4 a = __ldg(j4), b = __ldg(j4 + 1);
-          float* dst = &rows[row][t * 8];
-          dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
-        }
-      }
-      if (slot == 0) {
-        const float HdiF = ppSC[(size_t)p * 4 + 0];
-        wts[row] = HdiF;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-          rows[row][colHcd + i] = __fadd_rn(ppA[(size_t)p * 6 + 2 + i], ppL ? ppL[(size_t)p * 6 + 2 + i] : 0.f);
-        rows[row][colB] = ppSC[(size_t)p * 4 + 1];
+  const int colHcd = 8 * (nf - 1);
+  // gather tasks of this thread: e0 = tid, e1 = tid + 256 -> (row = e >> 3, slot = e & 7); slots >= nf-1 and < 7 are idle
+  const int row0 = threadIdx.x >> 3, row1 = row0 + SC_TPB / 8, slot = threadIdx.x & 7;
+  const bool slotUsed = (slot < nf - 1) || slot == 7;
+  const int col = (slot == 7) ? colHcd : slot * 8;
+  for (int e = threadIdx.x; e < SC_CHUNK * SC_MAXDIM; e += SC_TPB) buf[e] = 0.f;  // padding columns stay zero
+  ScTask t0, t1;
+  sc_fetch(t0, first + row0, slot, slotUsed && row0 < count, ptSlots, JpJdF, ppA, ppL, ppSC);
+  sc_fetch(t1, first + row1, slot, slotUsed && row1 < count, ptSlots, JpJdF, ppA, ppL, ppSC);
+  __syncthreads();
+  for (int base = 0; base < count; base += SC_CHUNK) {
+    const int nrows = min(SC_CHUNK, count - base);
+    // registers -> staged rows
+    if (slotUsed) {
+      if (slot == 7) {
+        // 66-float rows keep 8-byte alignment only: float2 stores
+        float2* d0 = reinterpret_cast<float2*>(&rows[row0][col]);
+        d0[0] = make_float2(t0.a.x, t0.a.y); d0[1] = make_float2(t0.a.z, t0.a.w);
+        rows[row0][col + 4] = t0.b.x;
+        wts[row0] = t0.w;
+        float2* d1 = reinterpret_cast<float2*>(&rows[row1][col]);
+        d1[0] = make_float2(t1.a.x, t1.a.y); d1[1] = make_float2(t1.a.z, t1.a.w);
+        rows[row1][col + 4] = t1.b.x;
+        wts[row1] = t1.w;
+      } else {
+        float2* d0 = reinterpret_cast<float2*>(&rows[row0][col]);
+        d0[0] = make_float2(t0.a.x, t0.a.y); d0[1] = make_float2(t0.a.z, t0.a.w); d0[2] = make_float2(t0.b.x, t0.b.y); d0[3] = make_float2(t0.b.z, t0.b.w);
+        float2* d1 = reinterpret_cast<float2*>(&rows[row1][col]);
+        d1[0] = make_float2(t1.a.x, t1.a.y); d1[1] = make_float2(t1.a.z, t1.a.w); d1[2] = make_float2(t1.b.x, t1.b.y); d1[3] = make_float2(t1.b.z, t1.b.w);
       }
     }
-    // residual lists longer than 8 (cannot happen with nf <= 8: one residual per target) are handled serially
     __syncthreads();
-    for (int rI = 0; rI < nrows; rI++) {
-      const float w = wts[rI];
-      float a[SC_TILE], b[SC_TILE];
+    // next chunk's gather in flight while this one is multiplied
+    const int nb2 = base + SC_CHUNK;
+    sc_fetch(t0, first + nb2 + row0, slot, slotUsed && nb2 + row0 < count, ptSlots, JpJdF, ppA, ppL, ppSC);
+    sc_fetch(t1, first + nb2 + row1, slot, slotUsed && nb2 + row1 < count, ptSlots, JpJdF, ppA, ppL, ppSC);
+    if (worker) {
+      for (int rI = kq; rI < nrows; rI += ks) {
+        const float w = wts[rI];
+        const float2* ra = reinterpret_cast<const float2*>(&rows[rI][ti * SC_TILE]);
+        const float2* rb = reinterpret_cast<const float2*>(&rows[rI][tj * SC_TILE]);
+        float a[SC_TILE], b[SC_TILE];
 #pragma unroll
-      for (int i = 0; i < SC_TILE; i++) { a[i] = rows[rI][ti * SC_TILE + i] * w; b[i] = rows[rI][tj * SC_TILE + i]; }
+        for (int i = 0; i < SC_TILE / 2; i++) {
+          const float2 va = ra[i], vb = rb[i];
+          a[2 * i] = va.x * w; a[2 * i + 1] = va.y * w;
+          b[2 * i] = vb.x; b[2 * i + 1] = vb.y;
+        }
 #pragma unroll
-      for (int i = 0; i < SC_TILE; i++)
+        for (int i = 0; i < SC_TILE; i++)
 #pragma unroll
-        for (int j = 0; j < SC_TILE; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < SC_TILE; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
     }
     __syncthreads();
   }
-  float* out = partials + (size_t)blockIdx.x * SC_DIM * SC_DIM;
+  // fold the ks point-splits of every tile (fixed order) and store the item's partial
+  if (worker) {
 #pragma unroll
-  for (int i = 0; i < SC_TILE; i++)
+    for (int i = 0; i < SC_TILE; i++)
 #pragma unroll
-    for (int j = 0; j < SC_TILE; j++) out[(ti * SC_TILE + i) * SC_DIM + tj * SC_TILE + j] = acc[i][j];
+      for (int j = 0; j < SC_TILE; j++) red[(kq * nU + u) * 36 + i * SC_TILE + j] = acc[i][j];
+  }
+  __syncthreads();
+  float* out = partials + (size_t)blockIdx.x * SC_PART;
+  for (int e = threadIdx.x; e < nU * 36; e += SC_TPB) {
+    float sv = red[e];
+    for (int q = 1; q < ks; q++) sv += red[q * nU * 36 + e];
+    out[e] = sv;
+  }
 }
 
-// per host: sum item partials (fp64, fixed order) and scatter into accD/accE/accEB ; accHcc/accbc summed over hosts
-__global__ void sc_finalize_kernel(const float* __restrict__ partials, const int4* __restrict__ items, int nItems, int nf,
-                                   double* __restrict__ accD, double* __restrict__ accE, double* __restrict__ accEB, double* __restrict__ hostHcc) {
+// per host: sum the partials of its items (fp64, fixed order) and scatter into accD / accE / accEB / per-host Hcc,bc.
+// grid = (nf, ceil(nU*36 / blockDim)); itemRange[h], itemRange[h+1] = the host's items.
+__global__ void sc_finalize_kernel(const float* __restrict__ partials, const int* __restrict__ itemRange, int nf, double* __restrict__ accD,
+                                   double* __restrict__ accE, double* __restrict__ accEB, double* __restrict__ hostHcc) {
   const int h = blockIdx.x;
-  const int colHcd = nf * 8, colB = nf * 8 + 4;
-  for (int e = threadIdx.x; e < SC_DIM * SC_DIM; e += blockDim.x) {
-    const int r = e / SC_DIM, c = e % SC_DIM;
-    if (r >= colB + 1 || c >= colB + 1) continue;
-    double s = 0.0;
-    for (int i = 0; i < nItems; i++)
-      if (items[i].x == h) s += (double)partials[(size_t)i * SC_DIM * SC_DIM + e];
-    if (r < colHcd) {
-      const int t1 = r >> 3, i8 = r & 7;
-      const int r1ht = h + t1 * nf;
-      if (c < colHcd) {
-        const int t2 = c >> 3, j8 = c & 7;
-        accD[((size_t)(r1ht + t2 * nf * nf)) * 64 + i8 * 8 + j8] = s;
-      } else if (c < colB) {
-        accE[(size_t)r1ht * 32 + i8 * 4 + (c - colHcd)] = s;
-      } else {
-        accEB[(size_t)r1ht * 8 + i8] = s;
-      }
-    } else if (r < colB) {
-      if (c >= colHcd && c < colB) hostHcc[(size_t)h * 20 + (r - colHcd) * 4 + (c - colHcd)] = s;  // Hcc
-      else if (c == colB) hostHcc[(size_t)h * 20 + 16 + (r - colHcd)] = s;                          // bc
+  const int dim = 8 * (nf - 1) + 5;
+  const int nT = (dim + SC_TILE - 1) / SC_TILE, nU = nT * (nT + 1) / 2;
+  const int e = blockIdx.y * blockDim.x + threadIdx.x;
+  if (e >= nU * 36) return;
+  const int u = e / 36, ij = e % 36;
+  int ti = 0, rem = u;
+  while (rem >= nT - ti) { rem -= nT - ti; ti++; }
+  const int tj = ti + rem;
+  const int r = ti * SC_TILE + ij / SC_TILE, c = tj * SC_TILE + ij % SC_TILE;
+  if (r > c || c >= dim) return;  // upper triangle only (diagonal tiles hold both halves); padding columns
+  double s = 0.0;
+  const int i1 = itemRange[h + 1];
+  for (int i = itemRange[h]; i < i1; i++) s += (double)partials[(size_t)i * SC_PART + e];
+  const int colHcd = 8 * (nf - 1), colB = colHcd + 4;
+  if (r < colHcd) {
+    const int tb1 = r >> 3, i8 = r & 7;
+    const int t1 = tb1 < h ? tb1 : tb1 + 1;
+    if (c < colHcd) {
+      const int tb2 = c >> 3, j8 = c & 7;
+      const int t2 = tb2 < h ? tb2 : tb2 + 1;
+      accD[((size_t)((h + t1 * nf) + t2 * nf * nf)) * 64 + i8 * 8 + j8] = s;
+      accD[((size_t)((h + t2 * nf) + t1 * nf * nf)) * 64 + j8 * 8 + i8] = s;
+    } else if (c < colB) {
+      accE[(size_t)(h + t1 * nf) * 32 + i8 * 4 + (c - colHcd)] = s;
+    } else {
+      accEB[(size_t)(h + t1 * nf) * 8 + i8] = s;
+    }
+  } else if (r < colB) {
+    if (c < colB) {
+      hostHcc[(size_t)h * 20 + (r - colHcd) * 4 + (c - colHcd)] = s;
+      hostHcc[(size_t)h * 20 + (c - colHcd) * 4 + (r - colHcd)] = s;
+    } else {
+      hostHcc[(size_t)h * 20 + 16 + (r - colHcd)] = s;
     }
   }
 }
@@ -473,13 +596,16 @@ int nalo_ba_create(nalo_ctx* ctx, int max_res, int max_pts, nalo_ba** out) {
   ACK(cudaMalloc(&ba->d_ppSC, sizeof(float) * 4 * (size_t)max_pts));
   ACK(cudaMalloc(&ba->d_ptHost, sizeof(int) * (size_t)max_pts));
   ACK(cudaMalloc(&ba->d_ptOrder, sizeof(int) * (size_t)max_pts));
-  ba->maxItems = max_res / 512 + max_pts / 512 + 64 * 4 + 64;
-  ACK(cudaMalloc(&ba->d_items, sizeof(int4) * (size_t)ba->maxItems));
-  ba->partialFloats = std::max((size_t)ba->maxItems * 96, (size_t)(max_pts / 1024 + 16) * SC_DIM * SC_DIM);
+  ba->maxItems = max_res / 512 + max_pts / SC_ITEM_PTS + 64 * 4 + 64 + NALO_BA_MAX_FRAMES;
+  ACK(cudaMalloc(&ba->d_items, sizeof(int4) * 2 * (size_t)ba->maxItems));
+  ACK(cudaMalloc(&ba->d_ptSlots, sizeof(int) * 8 * (size_t)max_pts));
+  ba->partialFloats = std::max((size_t)ba->maxItems * 96, (size_t)(max_pts / SC_ITEM_PTS + 2 * NALO_BA_MAX_FRAMES) * SC_PART);
   ACK(cudaMalloc(&ba->d_partials, sizeof(float) * ba->partialFloats));
   ba->outDoubles = (size_t)512 * 64 + 64 * 169 + 64 * 40 + 8 * 20 + 64;
   ACK(cudaMalloc(&ba->d_out, sizeof(double) * ba->outDoubles));
+  ACK(cudaHostAlloc(&ba->h_out, sizeof(double) * ba->outDoubles, cudaHostAllocDefault));
   ACK(cudaMalloc(&ba->d_counter, sizeof(int) * 4));
+  ACK(cudaMalloc(&ba->d_itemRange, sizeof(int) * 160));  // [0,80): bucket ranges of the top items, [80,160): host ranges of the Schur items
   ACK(cudaFuncSetAttribute(top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TOP_STAGE_RECS * REC * 4 + 64));
 #undef ACK
   *out = ba;
@@ -490,10 +616,10 @@ int nalo_ba_destroy(nalo_ba* ba) {
   if (!ba) return NALO_OK;
   cudaSetDevice(ba->ctx->device);
   cudaStreamSynchronize(ba->ctx->stream);
-  cudaFree(ba->d_rec); cudaFree(ba->d_rtz); cudaFree(ba->d_jpjd); cudaFree(ba->d_contrib); cudaFree(ba->d_ptBegin); cudaFree(ba->d_ptRes);
+  cudaFree(ba->d_rec); cudaFree(ba->d_rtz); cudaFree(ba->d_jpjd); cudaFree(ba->d_ptSlots); if (ba->h_out) cudaFreeHost(ba->h_out); cudaFree(ba->d_contrib); cudaFree(ba->d_ptBegin); cudaFree(ba->d_ptRes);
   cudaFree(ba->d_deltaF); cudaFree(ba->d_priorF); cudaFree(ba->d_adHT); cudaFree(ba->d_cDelta); cudaFree(ba->d_ppA); cudaFree(ba->d_ppL);
   cudaFree(ba->d_ppSC); cudaFree(ba->d_ptHost); cudaFree(ba->d_ptOrder); cudaFree(ba->d_items); cudaFree(ba->d_partials); cudaFree(ba->d_out);
-  cudaFree(ba->d_counter);
+  cudaFree(ba->d_counter); cudaFree(ba->d_itemRange);
   delete ba;
   return NALO_OK;
 }
@@ -506,7 +632,7 @@ int nalo_ba_upload(nalo_ba* ba, const NaloBAProblem* p) {
   if (!p->rec || !p->bucket_begin || !p->pt_begin || !p->pt_res || !p->adHTdeltaF || !p->cDeltaF) return NALO_E_ARG;
   NALO_CUDA(ctx, cudaSetDevice(ctx->device));
   ba->nf = p->nf; ba->nPts = p->n_pts; ba->nRes = p->n_res;
-  ba->haveA = ba->haveL = ba->haveJpJd = false;
+  ba->haveA = ba->haveL = ba->haveJpJd = ba->haveJpJdDev = false;
   cudaStream_t st = ctx->stream;
   const int nb = p->nf * p->nf;
   NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_rec, p->rec, sizeof(float) * REC * (size_t)p->n_res, cudaMemcpyHostToDevice, st));
@@ -524,10 +650,13 @@ int nalo_ba_upload(nalo_ba* ba, const NaloBAProblem* p) {
   NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_cDelta, p->cDeltaF, sizeof(float) * 4, cudaMemcpyHostToDevice, st));
   // top work items: runs of <= 1024 records inside one bucket
   ba->topItems.clear();
+  ba->topRange.assign(nb + 1, 0);
   for (int b = 0; b < nb; b++) {
+    ba->topRange[b] = (int)ba->topItems.size();
     for (int s = p->bucket_begin[b]; s < p->bucket_begin[b + 1]; s += 1024)
       ba->topItems.push_back(make_int4(b, s, std::min(1024, p->bucket_begin[b + 1] - s), 0));
   }
+  ba->topRange[nb] = (int)ba->topItems.size();
   // point -> host (from its first record) and the host-sorted point order for the Schur kernel
   std::vector<int> ptHost(p->n_pts, 0), cnt(p->nf + 1, 0);
   const uint32_t* recw = reinterpret_cast<const uint32_t*>(p->rec);
@@ -546,13 +675,39 @@ int nalo_ba_upload(nalo_ba* ba, const NaloBAProblem* p) {
   std::vector<int> order(p->n_pts), fill(ba->hostBegin.begin(), ba->hostBegin.end() - 1);
   for (int q = 0; q < p->n_pts; q++) order[fill[ptHost[q]]++] = q;
   NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_ptOrder, order.data(), sizeof(int) * (size_t)p->n_pts, cudaMemcpyHostToDevice, st));
+  // per point (host-sorted): record of the active residual to each target block, and the point index
+  std::vector<int> slots((size_t)p->n_pts * 8, -1);
+  for (int pos = 0; pos < p->n_pts; pos++) {
+    const int q = order[pos], h = ptHost[q];
+    for (int k = p->pt_begin[q]; k < p->pt_begin[q + 1]; k++) {
+      const int ri = p->pt_res[k];
+      if (ri < 0 || ri >= p->n_res) return nalo_fail(ctx, NALO_E_ARG, "pt_res[%d] = %d out of range", k, ri);
+      const uint32_t pk = recw[(size_t)ri * REC + O_PACK];
+      const int t = (pk >> 8) & 0xFF;
+      if (((pk >> 16) & 1) && t != h && t < p->nf) slots[(size_t)pos * 8 + (t < h ? t : t - 1)] = ri;
+    }
+    slots[(size_t)pos * 8 + 7] = q;
+  }
+  if (p->n_pts > 0)
+    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_ptSlots, slots.data(), sizeof(int) * 8 * (size_t)p->n_pts, cudaMemcpyHostToDevice, st));
   ba->scItems.clear();
-  for (int h = 0; h < p->nf; h++)
-    for (int s = ba->hostBegin[h]; s < ba->hostBegin[h + 1]; s += 1024)
-      ba->scItems.push_back(make_int4(h, s, std::min(1024, ba->hostBegin[h + 1] - s), 0));
+  ba->scRange.assign(p->nf + 1, 0);
+  for (int h = 0; h < p->nf; h++) {
+    ba->scRange[h] = (int)ba->scItems.size();
+    for (int s = ba->hostBegin[h]; s < ba->hostBegin[h + 1]; s += SC_ITEM_PTS)
+      ba->scItems.push_back(make_int4(h, s, std::min(SC_ITEM_PTS, ba->hostBegin[h + 1] - s), 0));
+  }
+  ba->scRange[p->nf] = (int)ba->scItems.size();
   if ((int)ba->topItems.size() > ba->maxItems || (int)ba->scItems.size() > ba->maxItems ||
-      ba->scItems.size() * SC_DIM * SC_DIM > ba->partialFloats)
+      ba->scItems.size() * SC_PART > ba->partialFloats)
     return nalo_fail(ctx, NALO_E_ARG, "BA work list larger than the capacity given to nalo_ba_create");
+  // work lists and their per-bucket / per-host ranges live on the device from here on (no per-call H2D)
+  if (!ba->topItems.empty())
+    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_items, ba->topItems.data(), sizeof(int4) * ba->topItems.size(), cudaMemcpyHostToDevice, st));
+  if (!ba->scItems.empty())
+    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_items + ba->maxItems, ba->scItems.data(), sizeof(int4) * ba->scItems.size(), cudaMemcpyHostToDevice, st));
+  NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_itemRange, ba->topRange.data(), sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, st));
+  NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_itemRange + 80, ba->scRange.data(), sizeof(int) * (p->nf + 1), cudaMemcpyHostToDevice, st));
   NALO_CUDA(ctx, cudaStreamSynchronize(st));  // host vectors above go out of scope
   return NALO_OK;
 }
@@ -568,15 +723,16 @@ int nalo_ba_accumulate_top(nalo_ba* ba, int mode, double* H_out, float* perPoint
   float* pp = (mode == 0) ? ba->d_ppA : ba->d_ppL;
   NALO_CUDA(ctx, cudaMemsetAsync(ba->d_counter, 0, sizeof(int) * 4, st));
   if (nItems > 0) {
-    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_items, ba->topItems.data(), sizeof(int4) * nItems, cudaMemcpyHostToDevice, st));
     TopArgs A;
     A.rec = ba->d_rec; A.rtz = ba->d_rtz; A.deltaF = ba->d_deltaF; A.adHT = ba->d_adHT; A.cDelta = ba->d_cDelta;
     A.items = ba->d_items; A.contrib = ba->d_contrib; A.partials = ba->d_partials; A.counter = ba->d_counter;
+    A.jpjd = ba->haveJpJdDev ? nullptr : ba->d_jpjd;  // first pass over the records also yields takeDataF's JpJdF
     A.nf = ba->nf; A.mode = mode;
     top_kernel<<<nItems, TOP_THREADS, 2 * TOP_STAGE_RECS * REC * 4 + 64, st>>>(A);
     NALO_CHECK_LAUNCH(ctx);
+    ba->haveJpJdDev = true;
   }
-  top_finalize_kernel<<<nb, 192, 0, st>>>(ba->d_partials, ba->d_items, nItems, nb, ba->d_out);
+  top_finalize_kernel<<<nb, 768, 0, st>>>(ba->d_partials, ba->d_itemRange, nb, ba->d_out);
   NALO_CHECK_LAUNCH(ctx);
   if (ba->nPts > 0) {
     point_sum_kernel<<<(ba->nPts + 255) / 256, 256, 0, st>>>(ba->d_contrib, ba->d_ptBegin, ba->d_ptRes, ba->nPts, pp);
@@ -587,13 +743,16 @@ int nalo_ba_accumulate_top(nalo_ba* ba, int mode, double* H_out, float* perPoint
     ba->haveA = true;
   }
   if (mode == 0) ba->haveA = true; else ba->haveL = true;
-  if (H_out) NALO_CUDA(ctx, cudaMemcpyAsync(H_out, ba->d_out, sizeof(double) * 169 * nb, cudaMemcpyDeviceToHost, st));
+  // small results go through pinned staging (a D2H copy into pageable memory would be staged by the driver anyway)
+  double* hH = ba->h_out;
+  int* hN = reinterpret_cast<int*>(ba->h_out + 169 * 64);
+  if (H_out) NALO_CUDA(ctx, cudaMemcpyAsync(hH, ba->d_out, sizeof(double) * 169 * nb, cudaMemcpyDeviceToHost, st));
   if (perPoint_out && ba->nPts > 0)
     NALO_CUDA(ctx, cudaMemcpyAsync(perPoint_out, pp, sizeof(float) * 6 * (size_t)ba->nPts, cudaMemcpyDeviceToHost, st));
-  int h_n = 0;
-  NALO_CUDA(ctx, cudaMemcpyAsync(&h_n, ba->d_counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+  NALO_CUDA(ctx, cudaMemcpyAsync(hN, ba->d_counter, sizeof(int), cudaMemcpyDeviceToHost, st));
   NALO_CUDA(ctx, cudaStreamSynchronize(st));
-  if (nres_out) *nres_out = h_n;
+  if (H_out) memcpy(H_out, hH, sizeof(double) * 169 * nb);
+  if (nres_out) *nres_out = *hN;
   return NALO_OK;
 }
 
@@ -602,9 +761,11 @@ int nalo_ba_take_data(nalo_ba* ba, float* JpJdF_out) {
   nalo_ctx* ctx = ba->ctx;
   if (ba->nf == 0) return nalo_fail(ctx, NALO_E_STATE, "nalo_ba_upload first");
   NALO_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (ba->nRes > 0) {
+  // JpJdF depends on the records only; if an accumulate_top pass has already streamed them, it is on the device
+  if (ba->nRes > 0 && !ba->haveJpJdDev) {
     take_data_kernel<<<(ba->nRes + 255) / 256, 256, 0, ctx->stream>>>(ba->d_rec, ba->nRes, ba->d_jpjd);
     NALO_CHECK_LAUNCH(ctx);
+    ba->haveJpJdDev = true;
   }
   ba->haveJpJd = true;
   if (JpJdF_out && ba->nRes > 0) {
@@ -626,8 +787,8 @@ int nalo_ba_accumulate_sc(nalo_ba* ba, int shiftPriorToZero, int useL, double* a
   const int nf = ba->nf, nItems = (int)ba->scItems.size();
   const float* ppL = useL ? ba->d_ppL : nullptr;
   if (ba->nPts > 0) {
-    sc_point_kernel<<<(ba->nPts + 255) / 256, 256, 0, st>>>(ba->d_rec, ba->d_ptBegin, ba->d_ptRes, ba->d_ppA, ppL, ba->d_priorF, ba->d_deltaF,
-                                                            shiftPriorToZero, ba->nPts, ba->d_ppSC);
+    sc_point_kernel<<<(ba->nPts + 255) / 256, 256, 0, st>>>(ba->d_ptSlots, ba->d_ppA, ppL, ba->d_priorF, ba->d_deltaF, shiftPriorToZero, ba->nPts,
+                                                            ba->d_ppSC);
     NALO_CHECK_LAUNCH(ctx);
   }
   double* dD = ba->d_out;                      // nf^3 * 64
@@ -637,24 +798,27 @@ int nalo_ba_accumulate_sc(nalo_ba* ba, int shiftPriorToZero, int useL, double* a
   const size_t totalD = (size_t)nf * nf * nf * 64 + (size_t)nf * nf * 40 + (size_t)nf * 20;
   NALO_CUDA(ctx, cudaMemsetAsync(ba->d_out, 0, sizeof(double) * totalD, st));
   if (nItems > 0) {
-    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_items, ba->scItems.data(), sizeof(int4) * nItems, cudaMemcpyHostToDevice, st));
-    sc_kernel<<<nItems, SC_TPB, 0, st>>>(ba->d_rec, ba->d_jpjd, ba->d_ptBegin, ba->d_ptRes, ba->d_ptOrder, ba->d_ppA, ppL, ba->d_ppSC,
-                                         ba->d_items, nf, ba->d_partials);
+    sc_kernel<<<nItems, SC_TPB, 0, st>>>(ba->d_jpjd, ba->d_ptSlots, ba->d_ppA, ppL, ba->d_ppSC, ba->d_items + ba->maxItems, nf, ba->d_partials);
     NALO_CHECK_LAUNCH(ctx);
-    sc_finalize_kernel<<<nf, 256, 0, st>>>(ba->d_partials, ba->d_items, nItems, nf, dD, dE, dEB, dHost);
+    const int dim = 8 * (nf - 1) + 5, nT = (dim + SC_TILE - 1) / SC_TILE, nU = nT * (nT + 1) / 2;
+    sc_finalize_kernel<<<dim3(nf, (nU * 36 + 255) / 256), 256, 0, st>>>(ba->d_partials, ba->d_itemRange + 80, nf, dD, dE, dEB, dHost);
     NALO_CHECK_LAUNCH(ctx);
   }
-  std::vector<double> host((size_t)nf * 20);
-  if (accD) NALO_CUDA(ctx, cudaMemcpyAsync(accD, dD, sizeof(double) * (size_t)nf * nf * nf * 64, cudaMemcpyDeviceToHost, st));
-  if (accE) NALO_CUDA(ctx, cudaMemcpyAsync(accE, dE, sizeof(double) * (size_t)nf * nf * 32, cudaMemcpyDeviceToHost, st));
-  if (accEB) NALO_CUDA(ctx, cudaMemcpyAsync(accEB, dEB, sizeof(double) * (size_t)nf * nf * 8, cudaMemcpyDeviceToHost, st));
-  NALO_CUDA(ctx, cudaMemcpyAsync(host.data(), dHost, sizeof(double) * (size_t)nf * 20, cudaMemcpyDeviceToHost, st));
+  // one D2H of the whole fp64 result block into pinned staging, then plain memcpy to the caller's arrays
+  NALO_CUDA(ctx, cudaMemcpyAsync(ba->h_out, ba->d_out, sizeof(double) * totalD, cudaMemcpyDeviceToHost, st));
   std::vector<float> sc4;
   if (perPoint_out && ba->nPts > 0) {
     sc4.resize((size_t)ba->nPts * 4);
     NALO_CUDA(ctx, cudaMemcpyAsync(sc4.data(), ba->d_ppSC, sizeof(float) * 4 * (size_t)ba->nPts, cudaMemcpyDeviceToHost, st));
   }
   NALO_CUDA(ctx, cudaStreamSynchronize(st));
+  const double* hD = ba->h_out;
+  const double* hE = hD + (size_t)nf * nf * nf * 64;
+  const double* hEB = hE + (size_t)nf * nf * 32;
+  const double* host = hEB + (size_t)nf * nf * 8;
+  if (accD) memcpy(accD, hD, sizeof(double) * (size_t)nf * nf * nf * 64);
+  if (accE) memcpy(accE, hE, sizeof(double) * (size_t)nf * nf * 32);
+  if (accEB) memcpy(accEB, hEB, sizeof(double) * (size_t)nf * nf * 8);
   if (accHcc) {
     for (int i = 0; i < 16; i++) accHcc[i] = 0;
     for (int h = 0; h < nf; h++)

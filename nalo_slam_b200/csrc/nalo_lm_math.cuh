@@ -19,6 +19,34 @@ __device__ __forceinline__ void quat_to_R_exact(const double* q, double* R) {
   R[6] = __dsub_rn(txz, twy); R[7] = __dadd_rn(tyz, twx); R[8] = __dsub_rn(1.0, __dadd_rn(txx, tyy));
 }
 
+__device__ __forceinline__ double fast_rsqrt_fwd(double x);
+// sin/cos for the half-angle of an LM increment. |x| < 0.25: Taylor series to x^15 / x^16 (truncation < 2e-25) evaluated
+// with Estrin's scheme (6 dependent operations instead of the ~25 of the library's range reduction + Horner chain);
+// larger arguments take the library path.
+__device__ __forceinline__ void sincos_small(double x, double* s, double* c) {
+  if (fabs(x) < 0.25) {
+    const double z = x * x, z2 = z * z, z4 = z2 * z2;
+    // sin(x)/x = sum (-1)^k z^k / (2k+1)!
+    const double s01 = fma(z, -1.0 / 6.0, 1.0), s23 = fma(z, -1.0 / 5040.0, 1.0 / 120.0);
+    const double s45 = fma(z, -1.0 / 39916800.0, 1.0 / 362880.0), s67 = fma(z, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
+    const double sp = fma(z4, fma(z2, s67, s45), fma(z2, s23, s01));
+    // cos(x) = sum (-1)^k z^k / (2k)!
+    const double c01 = fma(z, -0.5, 1.0), c23 = fma(z, -1.0 / 720.0, 1.0 / 24.0);
+    const double c45 = fma(z, -1.0 / 3628800.0, 1.0 / 40320.0), c67 = fma(z, -1.0 / 87178291200.0, 1.0 / 479001600.0);
+    const double c8 = 1.0 / 20922789888000.0;
+    *c = fma(z4, fma(z4, c8, fma(z2, c67, c45)), fma(z2, c23, c01));
+    *s = x * sp;
+  } else {
+    sincos(x, s, c);
+  }
+}
+// 1/sqrt(n) for n = |q|^2 of a quaternion that is unit up to rounding: second-order series around 1 (error < 1e-21 for
+// |n-1| < 1e-7), otherwise the general routine.
+__device__ __forceinline__ double rsqrt_near_one(double n) {
+  const double d = n - 1.0;
+  if (fabs(d) < 1e-7) return fma(d, fma(d, 0.375, -0.5), 1.0);
+  return fast_rsqrt_fwd(n);
+}
 __device__ __forceinline__ void quat_mul_d(const double* a, const double* b, double* r) {
   const double ax = a[0], ay = a[1], az = a[2], aw = a[3];
   const double bx = b[0], by = b[1], bz = b[2], bw = b[3];
@@ -28,7 +56,7 @@ __device__ __forceinline__ void quat_mul_d(const double* a, const double* b, dou
   r[2] = aw * bz + az * bw + ax * by - ay * bx;
 }
 __device__ __forceinline__ void quat_normalize_d(double* q) {
-  const double rl = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double rl = rsqrt_near_one(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   q[0] *= rl; q[1] *= rl; q[2] *= rl; q[3] *= rl;
 }
 __device__ __forceinline__ void quat_rotate_d(const double* q, const double* v, double* out) {
@@ -46,7 +74,8 @@ __device__ __forceinline__ void se3_exp_mul(const double* xi, const double* cur,
   const double* om = xi + 3;
   const double* v = xi;
   const double theta_sq = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
-  const double theta = sqrt(theta_sq);
+  const double rt_ = (theta_sq > 1e-200) ? fast_rsqrt_fwd(theta_sq) : 0.0;
+  const double theta = theta_sq * rt_;
   double imag, real, c1, c2;
   const bool small = theta < 1e-10;
   if (small) {
@@ -57,8 +86,8 @@ __device__ __forceinline__ void se3_exp_mul(const double* xi, const double* cur,
     c2 = 0.0;
   } else {
     double s, c;
-    sincos(0.5 * theta, &s, &c);
-    const double rt = 1.0 / theta;
+    sincos_small(0.5 * theta, &s, &c);
+    const double rt = rt_;
     imag = s * rt;
     real = c;
     const double rt2 = rt * rt;
@@ -230,6 +259,89 @@ __device__ __forceinline__ bool ldlt_solve_fast8(const double* A, int n, const d
   }
 #pragma unroll
   for (int i = 0; i < 8; i++) x[i] = y[i];
+  return ok;
+}
+
+
+// ---- fast fp64 reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~20 bits) + Newton
+// steps. Faithful to ~1 ulp, not correctly rounded: used only where the LM step tolerates it (pivot reciprocals,
+// quaternion normalisation), i.e. where the result already differs from Eigen's by the summation/pivoting order.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  // seed error e <= 2^-20; one cubic step r*(1 + e + e^2) leaves e^3 = 2^-60, below the fp64 rounding of the step itself
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  // e = 1 - x r^2; 1/sqrt(1-e) = 1 + e/2 + 3e^2/8 + O(e^3): one cubic step
+  const double e = fma(-x * r, r, 1.0);
+  return fma(r, e * fma(e, 0.375, 0.5), r);
+}
+
+__device__ __forceinline__ double fast_rsqrt_fwd(double x) { return fast_rsqrt(x); }
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// Unpivoted LDL^T + solve of an 8x8 SPD system distributed over the lanes of ONE warp: lane i (0..7) holds row i of
+// the matrix in a[0..7] (lower triangle used) and rhs_i in y; lanes 8..31 must call with finite dummy rows.
+// Right-looking elimination: per pivot one broadcast of the diagonal, one reciprocal (computed redundantly by every
+// lane), and the column's pre-division values broadcast off the critical path. On return lane i holds x_i in y and
+// every lane holds the whole solution in x[0..7]. Returns false (uniformly) when a pivot is not strictly positive
+// and finite; the caller then falls back to the Eigen-faithful pivoted factorisation (ldlt_solve_warp).
+__device__ __forceinline__ bool ldlt_solve_rows8(double* a, double y, double* x) {
+  const int lane = threadIdx.x & 31;
+  bool ok = true;
+  double rD[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const double dk = shfl_d(a[k], k);
+    ok = ok && (dk > 0.0) && (dk < 1.7976931348623157e308);
+    const double rk = fast_rcp(dk);
+    rD[k] = rk;
+    const double lik = a[k] * rk;
+#pragma unroll
+    for (int j = k + 1; j < 8; j++) {
+      const double cj = shfl_d(a[k], j);  // A[j][k] before division
+      a[j] = fma(-lik, cj, a[j]);         // rows i >= j use it; for i < j it touches the unused upper triangle
+    }
+    a[k] = lik;  // L[i][k] on lanes i > k
+  }
+  // T[j] on lane i = L[j][i] (j > i): the transposed factor for the back substitution
+  double T[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) T[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+#pragma unroll
+    for (int j = i + 1; j < 8; j++) {
+      const double t = shfl_d(a[i], j);
+      if (lane == i) T[j] = t;
+    }
+  }
+  // forward substitution (unit lower L)
+#pragma unroll
+  for (int j = 0; j < 7; j++) {
+    const double yj = shfl_d(y, j);
+    if (lane > j) y = fma(-a[j], yj, y);
+  }
+  // diagonal
+  {
+    double r = rD[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++)
+      if (lane == i) r = rD[i];
+    y *= r;
+  }
+  // back substitution (L^T)
+#pragma unroll
+  for (int j = 7; j >= 1; j--) {
+    const double xj = shfl_d(y, j);
+    if (lane < j) y = fma(-T[j], xj, y);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = shfl_d(y, i);
   return ok;
 }
 
