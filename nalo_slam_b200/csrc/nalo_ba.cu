@@ -391,21 +391,23 @@ struct ScTask {
   float4 a, b;  // 8 columns
   float w;      // point task only: HdiF
 };
-// task (row, slot): slot < 7 -> JpJdF of target block `slot`; slot == 7 -> the point's own columns {Hcd[4], bdSum} + weight
-__device__ __forceinline__ void sc_fetch(ScTask& t, int pos, int slot, bool inRange, const int* __restrict__ ptSlots,
-                                         const float* __restrict__ JpJdF, const float* __restrict__ ppA, const float* __restrict__ ppL,
-                                         const float* __restrict__ ppSC) {
+// task (row, slot): slot < 7 -> JpJdF of target block `slot`; slot == 7 -> the point's own columns {Hcd[4], bdSum} + weight.
+// Two dependent loads (slot table entry -> data), issued one chunk apart so that neither is waited for:
+//   sc_slot : the table entry (record index / point index), -2 when the task is idle
+//   sc_data : the 8 columns, given the entry
+__device__ __forceinline__ int sc_slot(int pos, int slot, bool inRange, const int* __restrict__ ptSlots) {
+  return inRange ? __ldg(ptSlots + (size_t)pos * 8 + slot) : -2;
+}
+__device__ __forceinline__ void sc_data(ScTask& t, int v, int slot, const float* __restrict__ JpJdF, const float* __restrict__ ppA,
+                                        const float* __restrict__ ppL, const float* __restrict__ ppSC) {
   t.a = make_float4(0.f, 0.f, 0.f, 0.f);
   t.b = t.a;
   t.w = 0.f;
-  if (!inRange) return;
-  const int v = __ldg(ptSlots + (size_t)pos * 8 + slot);
+  if (v < 0) return;
   if (slot < 7) {
-    if (v >= 0) {
-      const float4* j4 = reinterpret_cast<const float4*>(JpJdF + (size_t)v * 8);
-      t.a = __ldg(j4);
-      t.b = __ldg(j4 + 1);
-    }
+    const float4* j4 = reinterpret_cast<const float4*>(JpJdF + (size_t)v * 8);
+    t.a = __ldg(j4);
+    t.b = __ldg(j4 + 1);
   } else {
     const float4 sc = __ldg(reinterpret_cast<const float4*>(ppSC) + v);
     t.w = sc.x;
@@ -420,7 +422,7 @@ __device__ __forceinline__ void sc_fetch(ScTask& t, int pos, int slot, bool inRa
   }
 }
 
-__global__ void __launch_bounds__(SC_TPB) sc_kernel(const float* __restrict__ JpJdF, const int* __restrict__ ptSlots, const float* __restrict__ ppA,
+__global__ void __launch_bounds__(SC_TPB, 3) sc_kernel(const float* __restrict__ JpJdF, const int* __restrict__ ptSlots, const float* __restrict__ ppA,
                                                     const float* __restrict__ ppL, const float* __restrict__ ppSC, const int4* __restrict__ items,
                                                     int nf, float* __restrict__ partials) {
   // one buffer, two lives: the staged rows [SC_CHUNK][SC_MAXDIM] during the update, the per-thread tiles for the final fold
@@ -454,8 +456,12 @@ __global__ void __launch_bounds__(SC_TPB) sc_kernel(const float* __restrict__ Jp
   const int col = (slot == 7) ? colHcd : slot * 8;
   for (int e = threadIdx.x; e < SC_CHUNK * SC_MAXDIM; e += SC_TPB) buf[e] = 0.f;  // padding columns stay zero
   ScTask t0, t1;
-  sc_fetch(t0, first + row0, slot, slotUsed && row0 < count, ptSlots, JpJdF, ppA, ppL, ppSC);
-  sc_fetch(t1, first + row1, slot, slotUsed && row1 < count, ptSlots, JpJdF, ppA, ppL, ppSC);
+  int v0 = sc_slot(first + row0, slot, slotUsed && row0 < count, ptSlots);
+  int v1 = sc_slot(first + row1, slot, slotUsed && row1 < count, ptSlots);
+  int n0 = sc_slot(first + SC_CHUNK + row0, slot, slotUsed && SC_CHUNK + row0 < count, ptSlots);
+  int n1 = sc_slot(first + SC_CHUNK + row1, slot, slotUsed && SC_CHUNK + row1 < count, ptSlots);
+  sc_data(t0, v0, slot, JpJdF, ppA, ppL, ppSC);
+  sc_data(t1, v1, slot, JpJdF, ppA, ppL, ppSC);
   __syncthreads();
   for (int base = 0; base < count; base += SC_CHUNK) {
     const int nrows = min(SC_CHUNK, count - base);
@@ -479,10 +485,13 @@ __global__ void __launch_bounds__(SC_TPB) sc_kernel(const float* __restrict__ Jp
       }
     }
     __syncthreads();
-    // next chunk's gather in flight while this one is multiplied
-    const int nb2 = base + SC_CHUNK;
-    sc_fetch(t0, first + nb2 + row0, slot, slotUsed && nb2 + row0 < count, ptSlots, JpJdF, ppA, ppL, ppSC);
-    sc_fetch(t1, first + nb2 + row1, slot, slotUsed && nb2 + row1 < count, ptSlots, JpJdF, ppA, ppL, ppSC);
+    // next chunk's columns (their table entries arrived a chunk ago) and the table entries of the chunk after it go in
+    // flight while this chunk is multiplied
+    sc_data(t0, n0, slot, JpJdF, ppA, ppL, ppSC);
+    sc_data(t1, n1, slot, JpJdF, ppA, ppL, ppSC);
+    const int nb2 = base + 2 * SC_CHUNK;
+    n0 = sc_slot(first + nb2 + row0, slot, slotUsed && nb2 + row0 < count, ptSlots);
+    n1 = sc_slot(first + nb2 + row1, slot, slotUsed && nb2 + row1 < count, ptSlots);
     if (worker) {
       for (int rI = kq; rI < nrows; rI += ks) {
         const float w = wts[rI];

@@ -112,6 +112,142 @@ __global__ void __launch_bounds__(256) grad_kernel(const float* __restrict__ col
   pix[L.pixOff[lvl] + idx] = make_float4(I, dx, dy, ag);
 }
 
+// ---- fused single-launch version (levels <= 5): pyramid + gradients of one 64x32 level-0 tile per CTA -------------
+// The CTA stages the 96x64 level-0 neighbourhood of its tile (16-pixel margin = one level-4 pixel) in shared memory,
+// cascades the 2x2 box means down to level 4 over the whole neighbourhood (so every level has a >= 1 pixel halo; the
+// halo values are recomputed, bit-identically, instead of exchanged), then evaluates the reference's flat-index central
+// differences of all levels for its own tile and writes one float4 per pixel. Level-0 data is read ~3x (from L2), the
+// 9.9 MB of output is written once; there is no planar intermediate and no second launch.
+// The flat-index wrap at the image's left/right border (idx-1 of x = 0 is the last pixel of the previous row) is
+// served by recomputing that one level-l value from level 0 in global memory (value_at<l>).
+template <int LVL>
+__device__ __forceinline__ float value_at(const float* __restrict__ color, int w0, int x, int y) {
+  if constexpr (LVL == 0) {
+    return __ldg(color + (size_t)y * w0 + x);
+  } else {
+    return box4(value_at<LVL - 1>(color, w0, 2 * x, 2 * y), value_at<LVL - 1>(color, w0, 2 * x + 1, 2 * y),
+                value_at<LVL - 1>(color, w0, 2 * x, 2 * y + 1), value_at<LVL - 1>(color, w0, 2 * x + 1, 2 * y + 1));
+  }
+}
+__device__ __forceinline__ float value_at_lvl(int lvl, const float* __restrict__ color, int w0, int x, int y) {
+  switch (lvl) {
+    case 0: return value_at<0>(color, w0, x, y);
+    case 1: return value_at<1>(color, w0, x, y);
+    case 2: return value_at<2>(color, w0, x, y);
+    case 3: return value_at<3>(color, w0, x, y);
+    default: return value_at<4>(color, w0, x, y);
+  }
+}
+
+constexpr int FT_W = 64, FT_H = 32, FT_M = 16;             // tile and margin at level 0
+constexpr int FR_W = FT_W + 2 * FT_M, FR_H = FT_H + 2 * FT_M;  // staged region 96 x 64
+
+// gradient + store of one pixel of level LVL: (lx, ly) inside the tile, S = staged level with margin m and pitch rw
+template <int LVL>
+__device__ __forceinline__ void fused_grad_store(const float* __restrict__ S, int lx, int ly, int tx0, int ty0, const float* __restrict__ color,
+                                                 const float* __restrict__ B, int useB, float4* __restrict__ pix, const PyrLevels& L) {
+  constexpr int m = FT_M >> LVL, rw = FR_W >> LVL;
+  const int X = (tx0 >> LVL) + lx, Y = (ty0 >> LVL) + ly;
+  const int w = L.w[LVL], h = L.h[LVL];
+  if (X >= w || Y >= h) return;
+  const float* c = S + (ly + m) * rw + (lx + m);
+  const float I = c[0];
+  float dx = 0.f, dy = 0.f, ag = 0.f;
+  if (Y >= 1 && Y < h - 1) {  // idx in [w, w(h-1))
+    const float left = (X > 0) ? c[-1] : value_at<LVL>(color, L.w[0], w - 1, Y - 1);
+    const float right = (X < w - 1) ? c[1] : value_at<LVL>(color, L.w[0], 0, Y + 1);
+    dx = __fmul_rn(0.5f, __fsub_rn(right, left));
+    dy = __fmul_rn(0.5f, __fsub_rn(c[rw], c[-rw]));
+    if (!isfinite(dx)) dx = 0.f;
+    if (!isfinite(dy)) dy = 0.f;
+    ag = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (useB) {
+      int cc = (int)__fadd_rn(I, 0.5f);
+      if (cc < 5) cc = 5;
+      if (cc > 250) cc = 250;
+      const float gw = __fsub_rn(__ldg(B + cc + 1), __ldg(B + cc));
+      ag = __fmul_rn(ag, __fmul_rn(gw, gw));
+    }
+  }
+  pix[L.pixOff[LVL] + (size_t)Y * w + X] = make_float4(I, dx, dy, ag);
+}
+
+__global__ void __launch_bounds__(512) make_images_fused_kernel(const float* __restrict__ color, const float* __restrict__ B, int useB,
+                                                                float4* __restrict__ pix, const __grid_constant__ PyrLevels L) {
+  __shared__ float s0[FR_H * FR_W];
+  __shared__ float s1[(FR_H / 2) * (FR_W / 2)];
+  __shared__ float s2[(FR_H / 4) * (FR_W / 4)];
+  __shared__ float s3[(FR_H / 8) * (FR_W / 8)];
+  __shared__ float s4[(FR_H / 16) * (FR_W / 16)];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tx0 = blockIdx.x * FT_W, ty0 = blockIdx.y * FT_H;
+  const int rx0 = tx0 - FT_M, ry0 = ty0 - FT_M;
+  const int w0 = L.w[0], h0 = L.h[0];
+  // stage the 96 x 64 neighbourhood: warp `wid` takes rows wid, wid+16, wid+32, wid+48; 3 coalesced loads per row.
+  // All 12 loads of a thread are issued before the first store (one DRAM round trip, not twelve).
+  {
+    float v[12];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int gy = ry0 + wid + 16 * r;
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const int gx = rx0 + lane + 32 * q;
+        v[3 * r + q] = (gx >= 0 && gx < w0 && gy >= 0 && gy < h0) ? __ldg(color + (size_t)gy * w0 + gx) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int q = 0; q < 3; q++) s0[(wid + 16 * r) * FR_W + lane + 32 * q] = v[3 * r + q];
+  }
+  __syncthreads();
+  if (L.levels > 1) {  // 48 x 32 = 1536 = 3 per thread: row = tid / 16 (+32 rows? no: 32 rows x 48 cols) -> x = k % 48 via 3 x 16 columns
+    const int y = tid >> 4, xb = tid & 15;  // 32 rows x 16 threads, each thread 3 columns xb, xb+16, xb+32
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const int x = xb + 16 * q;
+      const float* p = s0 + (2 * y) * FR_W + 2 * x;
+      s1[y * (FR_W / 2) + x] = box4(p[0], p[1], p[FR_W], p[FR_W + 1]);
+    }
+    __syncthreads();
+  }
+  if (L.levels > 2) {  // 24 x 16 = 384
+    if (tid < 384) {
+      const int y = tid / 24, x = tid - 24 * y;
+      const float* p = s1 + (2 * y) * (FR_W / 2) + 2 * x;
+      s2[tid] = box4(p[0], p[1], p[FR_W / 2], p[FR_W / 2 + 1]);
+    }
+    __syncthreads();
+  }
+  if (L.levels > 3) {  // 12 x 8 = 96
+    if (tid < 96) {
+      const int y = tid / 12, x = tid - 12 * y;
+      const float* p = s2 + (2 * y) * (FR_W / 4) + 2 * x;
+      s3[tid] = box4(p[0], p[1], p[FR_W / 4], p[FR_W / 4 + 1]);
+    }
+    __syncthreads();
+  }
+  if (L.levels > 4) {  // 6 x 4 = 24
+    if (tid < 24) {
+      const int y = tid / 6, x = tid - 6 * y;
+      const float* p = s3 + (2 * y) * (FR_W / 8) + 2 * x;
+      s4[tid] = box4(p[0], p[1], p[FR_W / 8], p[FR_W / 8 + 1]);
+    }
+    __syncthreads();
+  }
+  // gradients of every level for this tile: level 0 = 64 x 32 (4 rows per thread), level 1 = 32 x 16 (1 per thread), ...
+  {
+    const int lx = tid & 63, lyb = tid >> 6;
+#pragma unroll
+    for (int r = 0; r < 4; r++) fused_grad_store<0>(s0, lx, lyb + 8 * r, tx0, ty0, color, B, useB, pix, L);
+  }
+  if (L.levels > 1) fused_grad_store<1>(s1, tid & 31, tid >> 5, tx0, ty0, color, B, useB, pix, L);
+  if (L.levels > 2 && tid < 128) fused_grad_store<2>(s2, tid & 15, tid >> 4, tx0, ty0, color, B, useB, pix, L);
+  if (L.levels > 3 && tid < 32) fused_grad_store<3>(s3, tid & 7, tid >> 3, tx0, ty0, color, B, useB, pix, L);
+  if (L.levels > 4 && tid < 8) fused_grad_store<4>(s4, tid & 3, tid >> 2, tx0, ty0, color, B, useB, pix, L);
+}
+
 // float4 frame -> reference host layout: stage[0 .. 3*total) = AoS {I,dx,dy}, stage[3*total ..) = absgrad
 __global__ void __launch_bounds__(256) export_kernel(const float4* __restrict__ pix, float* __restrict__ stage, PyrLevels L) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,6 +295,15 @@ int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float
     NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_B, B256_host, sizeof(float) * 256, cudaMemcpyHostToDevice, ctx->stream));
     useB = 1;
   }
+  if (ctx->levels <= 5) {
+    dim3 fgrid((ctx->w0 + FT_W - 1) / FT_W, (ctx->h0 + FT_H - 1) / FT_H);
+    make_images_fused_kernel<<<fgrid, 512, 0, ctx->stream>>>(color_dev, ctx->d_B, useB, ctx->frames[slot].pix, L);
+    NALO_CHECK_LAUNCH(ctx);
+    ctx->frames[slot].valid = true;
+    if (ctx->histFrameSlot == slot) ctx->histFrameSlot = -1;
+    return NALO_OK;
+  }
+  // 6-level pyramids: two-kernel path (a level-5 pixel is coarser than the fused kernel's halo)
   float* planar = ctx->d_stage;
   dim3 grid((ctx->w0 + 31) / 32, (ctx->h0 + 15) / 16);
   pyr_down_kernel<<<grid, 512, 0, ctx->stream>>>(color_dev, planar, L);
