@@ -259,6 +259,11 @@ def run_b200(args, rank, world, local_rank):
     # single tiny gather of the per-frame results (inside the timed region)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     res_dev = torch.from_numpy(results).cuda()
+    if dist:
+        # align the ranks first: without it the timed collective would mostly measure how far apart the ranks finished
+        # their K steps (already covered by taking the max over ranks of the step times), not the gather itself
+        torch.cuda.synchronize()
+        dist.barrier()
     g0.record()
     if dist:
         gathered = [torch.empty_like(res_dev) for _ in range(world)]
@@ -268,6 +273,9 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms)) + (g0.elapsed_time(g1) if dist else 0.0)
+    if os.environ.get("NALO_BENCH_DEBUG"):
+        log(f"[rank {rank}] steps ms: mean {np.mean(step_ms):.4f} min {np.min(step_ms):.4f} max {np.max(step_ms):.4f} p50 {np.median(step_ms):.4f}; "
+            f"kernel ms mean {np.mean(kern_ms):.4f}; gather ms {g0.elapsed_time(g1) if dist else 0.0:.4f}; evals {tot_evals / K:.1f}")
     if dist:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
