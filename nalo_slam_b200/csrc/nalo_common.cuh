@@ -104,6 +104,8 @@ struct nalo_ctx {
   NaloTrackResult* h_resMapped = nullptr;  // mapped pinned: single-track result + completion word
   NaloTrackResult* d_resMapped = nullptr;  // its device alias
   uint32_t trackLaunchId = 0;
+  void* d_help = nullptr;                  // chunk-mode help area of batched launches (slots + per-chunk partials)
+  int* h_gridInit = nullptr;               // pinned table h_gridInit[g] == g
   int* d_trackQueue = nullptr;             // atomic work queue of single-CTA groups (batched alignments)
   uint32_t doneToken = 0;
   bool profiling = false;                  // record CUDA events around the tracking kernel (NaloTrackStats::kernel_ms)
