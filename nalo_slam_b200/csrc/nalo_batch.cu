@@ -262,7 +262,7 @@ int nalo_batch_track(nalo_batch* b, int first, int count, double* poses7, double
   // group size: 1 CTA per pair when there are at least as many pairs as co-resident CTAs, else spread the SMs
   int G = ctx->maxGroups / count;
   if (G < 1) G = 1;
-  int rc = nalo_track_launch(ctx, count, G, b->d_problems, b->d_results, /*streamed=*/true);
+  int rc = nalo_track_launch(ctx, count, G, b->d_problems, b->d_results, /*streamed=*/true, /*helpAll=*/false);
   if (rc != NALO_OK) return rc;
   if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));
   pack_results<<<(count + 127) / 128, 128, 0, ctx->stream>>>(b->d_results, b->d_packed, count);

@@ -163,4 +163,4 @@ int nalo_select_init(nalo_ctx* ctx);
 void nalo_select_free(nalo_ctx* ctx);
 void nalo_fill_problem(nalo_ctx* ctx, int trk, NaloTrackProblem* P);
 int nalo_track_launch(nalo_ctx* ctx, int nProblems, int blocksPerProblem, const NaloTrackProblem* d_problems, NaloTrackResult* d_results,
-                      bool streamed);
+                      bool streamed, bool helpAll);

@@ -11,6 +11,8 @@
 //                            the sequential loop exactly — including its early break.
 // On several GPUs the candidates are partitioned across ranks, every rank calls nalo_track_multi on its share,
 // the small per-candidate records are gathered (NCCL, see bench.py / INTEGRATION.md) and rank 0 replays the rule.
+#include <cstdlib>
+
 #include "nalo_common.cuh"
 
 namespace {
@@ -168,7 +170,16 @@ int nalo_track_multi(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, i
   }
   NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_problems, ctx->h_problems, sizeof(NaloTrackProblem) * nHyp, cudaMemcpyHostToDevice, ctx->stream));
   if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evA, ctx->stream));
-  rc = nalo_track_launch(ctx, nHyp, ctx->maxGroups / nHyp, ctx->d_problems, ctx->d_results, /*streamed=*/false);
+  // Group size: every evaluation costs a fixed ~9 us (grid-wide exchange + serial LM step) on top of its share of the
+  // points, so few large groups that each run several candidates one after the other beat one small group per candidate
+  // (measured on 31 candidates: see profiles/r01_suite.md). NALO_MULTI_G / NALO_MULTI_HELP are measurement switches.
+  static const int envG = getenv("NALO_MULTI_G") ? atoi(getenv("NALO_MULTI_G")) : 0;
+  static const bool envHelp = getenv("NALO_MULTI_HELP") != nullptr;
+  int G = ctx->maxGroups / nHyp;
+  if (nHyp > 8) G = ctx->maxGroups / ((nHyp + 2) / 3);  // ~three candidates per group, handed out through the dynamic queue
+  if (envG > 0) G = envG;
+  if (G < 1) G = 1;
+  rc = nalo_track_launch(ctx, nHyp, G, ctx->d_problems, ctx->d_results, /*streamed=*/false, /*helpAll=*/envHelp);
   if (rc != NALO_OK) return rc;
   if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));
   NALO_CUDA(ctx, cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(NaloTrackResult) * nHyp, cudaMemcpyDeviceToHost, ctx->stream));
