@@ -94,6 +94,13 @@ int nalo_flush_l2(nalo_ctx* ctx);
  * dIp = AoS {I,dx,dy} (Eigen::Vector3f), absgrad = float. */
 int nalo_make_images(nalo_ctx* ctx, int slot, const float* color_host, const float* B256, float* dIp_host, float* absgrad_host);
 int nalo_make_images_dev(nalo_ctx* ctx, int slot, const float* color_dev, const float* B256_host);
+/* Asynchronous host copies: the pyramid is built on the context stream, the reference-layout copies of the first
+ * `levels_host` levels (ImmaturePoint / PointFrameResidual::linearize read level 0 only: levels_host = 1) are exported on
+ * a second stream, so nalo_track of the new frame overlaps the D2H. The buffers (same layout as nalo_make_images, only
+ * the first levels filled) must be pinned (nalo_host_alloc) and stay valid until nalo_frame_host_wait(slot) returns. */
+int nalo_make_images_async(nalo_ctx* ctx, int slot, const float* color_host, const float* B256, float* dIp_host, float* absgrad_host,
+                           int levels_host);
+int nalo_frame_host_wait(nalo_ctx* ctx, int slot);
 int nalo_get_frame(nalo_ctx* ctx, int slot, float* dIp_host, float* absgrad_host);
 
 /* ---- a2-a4: PixelSelector (FullSystem/PixelSelector2.cpp) ---------------------------------------------- */

@@ -72,6 +72,26 @@ class FrameHessian {
       check(ctx.get(), nalo_make_images(ctx.get(), slot, color, B256, nullptr, nullptr), "nalo_make_images");
     }
   }
+  // Same, but the host copies (first `levelsHost` levels) arrive asynchronously in pinned memory owned by this object:
+  // call waitHost() before the CPU-side consumers (ImmaturePoint, PointFrameResidual::linearize) read dIpPinned /
+  // absSquaredGradPinned; trackNewestCoarse of this frame can run in between and overlaps the D2H.
+  void makeImagesAsync(const float* color, const float* B256 = nullptr, int levelsHost = 1) {
+    size_t tot = 0;
+    for (int l = 0; l < ctx.levels(); l++) tot += (size_t)(ctx.w() >> l) * (ctx.h() >> l);
+    if (!dIpPinned) {
+      dIpPinned = static_cast<float*>(nalo_host_alloc(sizeof(float) * 3 * tot));
+      absSquaredGradPinned = static_cast<float*>(nalo_host_alloc(sizeof(float) * tot));
+      if (!dIpPinned || !absSquaredGradPinned) throw std::runtime_error("nalo_host_alloc failed");
+    }
+    check(ctx.get(), nalo_make_images_async(ctx.get(), slot, color, B256, dIpPinned, absSquaredGradPinned, levelsHost), "nalo_make_images_async");
+  }
+  void waitHost() { check(ctx.get(), nalo_frame_host_wait(ctx.get(), slot), "nalo_frame_host_wait"); }
+  ~FrameHessian() {
+    if (dIpPinned) nalo_host_free(dIpPinned);
+    if (absSquaredGradPinned) nalo_host_free(absSquaredGradPinned);
+  }
+  float* dIpPinned = nullptr;
+  float* absSquaredGradPinned = nullptr;
   Context& ctx;
   int slot;
   float ab_exposure = 1.f;

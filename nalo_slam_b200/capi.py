@@ -207,6 +207,16 @@ class Context:
         self._ck(self.L.nalo_make_images(self.h_, C.c_int(slot), _ptr(color), _ptr(B), None, None))
         return None
 
+    def make_images_async(self, slot, color, dIp_pinned, ag_pinned, levels_host=None, B256=None):
+        """nalo_make_images_async: host copies land in the given PINNED arrays (capi.pinned_array) after frame_host_wait(slot)."""
+        color = np.ascontiguousarray(color, dtype=_f32).reshape(-1)
+        B = None if B256 is None else np.ascontiguousarray(B256, dtype=_f32)
+        lv = self.levels if levels_host is None else levels_host
+        self._ck(self.L.nalo_make_images_async(self.h_, C.c_int(slot), _ptr(color), _ptr(B), _ptr(dIp_pinned), _ptr(ag_pinned), C.c_int(lv)))
+
+    def frame_host_wait(self, slot):
+        self._ck(self.L.nalo_frame_host_wait(self.h_, C.c_int(slot)))
+
     def make_images_dev(self, slot, color_dev_ptr, B256=None):
         B = None if B256 is None else np.ascontiguousarray(B256, dtype=_f32)
         self._ck(self.L.nalo_make_images_dev(self.h_, C.c_int(slot), _P(color_dev_ptr), _ptr(B)))

@@ -26,6 +26,9 @@ struct NaloLevelGeom {
 struct NaloFrame {
   float4* pix = nullptr;
   bool valid = false;
+  cudaEvent_t built = nullptr;      // recorded on the context stream after the pyramid kernel
+  cudaEvent_t hostReady = nullptr;  // recorded on the copy stream after the last asynchronous host copy of this slot
+  bool hostPending = false;
 };
 
 struct NaloTrackerState {
@@ -87,6 +90,10 @@ struct nalo_ctx {
   int denseOff[NALO_MAX_LEVELS];
   int numSMs = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copyStream = nullptr;  // asynchronous export of the reference-layout host copies (nalo_make_images_async)
+  float* d_exportStage = nullptr;     // its own staging buffer (d_stage is scratch of the main stream)
+  cudaEvent_t exportDone = nullptr;   // last D2H out of d_exportStage
+  bool exportBusy = false;
   NaloParams params;
   std::vector<NaloFrame> frames;
   NaloTrackerState trk[NALO_MAX_TRACKERS];
@@ -154,7 +161,7 @@ int nalo_fail(nalo_ctx* ctx, int code, const char* fmt, ...);
   } while (0)
 
 // internal cross-file entry points
-int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float* B256_host);
+int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float* B256_host, float* exportStage = nullptr, int exportLevels = 0);
 int nalo_images_to_host(nalo_ctx* ctx, int slot, float* dIp_host, float* absgrad_host);
 int nalo_depth_finish(nalo_ctx* ctx, int trk, int ref_slot);
 int nalo_track_init(nalo_ctx* ctx);

@@ -76,15 +76,20 @@ int nalo_create(int w, int h, int levels, int device, int max_frames, nalo_ctx**
   CK(cudaGetDeviceProperties(&prop, device));
   ctx->numSMs = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->exportDone, cudaEventDisableTiming));
   ctx->frames.resize(max_frames);
   for (int i = 0; i < max_frames; i++) {
     CK(cudaMalloc(&ctx->frames[i].pix, sizeof(float4) * (size_t)ctx->totPix));
     CK(cudaMemsetAsync(ctx->frames[i].pix, 0, sizeof(float4) * (size_t)ctx->totPix, ctx->stream));
+    CK(cudaEventCreateWithFlags(&ctx->frames[i].built, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->frames[i].hostReady, cudaEventDisableTiming));
   }
   const size_t n0 = (size_t)w * h;
   CK(cudaMalloc(&ctx->d_color, sizeof(float) * n0));
   CK(cudaMalloc(&ctx->d_B, sizeof(float) * 256));
   CK(cudaMalloc(&ctx->d_stage, sizeof(float) * 4 * (size_t)ctx->totPixDense));
+  CK(cudaMalloc(&ctx->d_exportStage, sizeof(float) * 4 * (size_t)ctx->totPixDense));
   CK(cudaMalloc(&ctx->d_mask, n0));
   CK(cudaMalloc(&ctx->d_mask_all, (size_t)ctx->totPixDense));
   CK(cudaMalloc(&ctx->d_ptlist, sizeof(float) * 4 * n0));
@@ -124,6 +129,10 @@ int nalo_destroy(nalo_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& f : ctx->frames) cudaFree(f.pix);
+  for (auto& f : ctx->frames) { if (f.built) cudaEventDestroy(f.built); if (f.hostReady) cudaEventDestroy(f.hostReady); }
+  if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
+  cudaFree(ctx->d_exportStage);
+  if (ctx->exportDone) cudaEventDestroy(ctx->exportDone);
   cudaFree(ctx->d_color); cudaFree(ctx->d_B); cudaFree(ctx->d_stage); cudaFree(ctx->d_mask); cudaFree(ctx->d_mask_all); cudaFree(ctx->d_ptlist); cudaFree(ctx->d_owner);
   cudaFree(ctx->d_scan); cudaFree(ctx->d_counts); cudaFree(ctx->d_flush);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);

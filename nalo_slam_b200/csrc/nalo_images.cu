@@ -145,7 +145,8 @@ constexpr int FR_W = FT_W + 2 * FT_M, FR_H = FT_H + 2 * FT_M;  // staged region 
 // gradient + store of one pixel of level LVL: (lx, ly) inside the tile, S = staged level with margin m and pitch rw
 template <int LVL>
 __device__ __forceinline__ void fused_grad_store(const float* __restrict__ S, int lx, int ly, int tx0, int ty0, const float* __restrict__ color,
-                                                 const float* __restrict__ B, int useB, float4* __restrict__ pix, const PyrLevels& L) {
+                                                 const float* __restrict__ B, int useB, float4* __restrict__ pix, const PyrLevels& L,
+                                                 float* __restrict__ exportStage, int exportLevels) {
   constexpr int m = FT_M >> LVL, rw = FR_W >> LVL;
   const int X = (tx0 >> LVL) + lx, Y = (ty0 >> LVL) + ly;
   const int w = L.w[LVL], h = L.h[LVL];
@@ -170,10 +171,21 @@ __device__ __forceinline__ void fused_grad_store(const float* __restrict__ S, in
     }
   }
   pix[L.pixOff[LVL] + (size_t)Y * w + X] = make_float4(I, dx, dy, ag);
+  if (exportStage != nullptr && LVL < exportLevels) {
+    // reference host layout (AoS Vector3f {I,dx,dy}, levels concatenated; absSquaredGrad behind it) written in the same
+    // pass, so the asynchronous D2H of nalo_make_images_async needs no kernel of its own (which could not run beside
+    // the all-SM tracking kernel anyway)
+    const size_t g = (size_t)L.denseOff[LVL] + (size_t)Y * w + X;
+    exportStage[3 * g + 0] = I;
+    exportStage[3 * g + 1] = dx;
+    exportStage[3 * g + 2] = dy;
+    exportStage[3 * (size_t)L.total + g] = ag;
+  }
 }
 
 __global__ void __launch_bounds__(512) make_images_fused_kernel(const float* __restrict__ color, const float* __restrict__ B, int useB,
-                                                                float4* __restrict__ pix, const __grid_constant__ PyrLevels L) {
+                                                                float4* __restrict__ pix, const __grid_constant__ PyrLevels L,
+                                                                float* __restrict__ exportStage, int exportLevels) {
   __shared__ float s0[FR_H * FR_W];
   __shared__ float s1[(FR_H / 2) * (FR_W / 2)];
   __shared__ float s2[(FR_H / 4) * (FR_W / 4)];
@@ -240,18 +252,18 @@ __global__ void __launch_bounds__(512) make_images_fused_kernel(const float* __r
   {
     const int lx = tid & 63, lyb = tid >> 6;
 #pragma unroll
-    for (int r = 0; r < 4; r++) fused_grad_store<0>(s0, lx, lyb + 8 * r, tx0, ty0, color, B, useB, pix, L);
+    for (int r = 0; r < 4; r++) fused_grad_store<0>(s0, lx, lyb + 8 * r, tx0, ty0, color, B, useB, pix, L, exportStage, exportLevels);
   }
-  if (L.levels > 1) fused_grad_store<1>(s1, tid & 31, tid >> 5, tx0, ty0, color, B, useB, pix, L);
-  if (L.levels > 2 && tid < 128) fused_grad_store<2>(s2, tid & 15, tid >> 4, tx0, ty0, color, B, useB, pix, L);
-  if (L.levels > 3 && tid < 32) fused_grad_store<3>(s3, tid & 7, tid >> 3, tx0, ty0, color, B, useB, pix, L);
-  if (L.levels > 4 && tid < 8) fused_grad_store<4>(s4, tid & 3, tid >> 2, tx0, ty0, color, B, useB, pix, L);
+  if (L.levels > 1) fused_grad_store<1>(s1, tid & 31, tid >> 5, tx0, ty0, color, B, useB, pix, L, exportStage, exportLevels);
+  if (L.levels > 2 && tid < 128) fused_grad_store<2>(s2, tid & 15, tid >> 4, tx0, ty0, color, B, useB, pix, L, exportStage, exportLevels);
+  if (L.levels > 3 && tid < 32) fused_grad_store<3>(s3, tid & 7, tid >> 3, tx0, ty0, color, B, useB, pix, L, exportStage, exportLevels);
+  if (L.levels > 4 && tid < 8) fused_grad_store<4>(s4, tid & 3, tid >> 2, tx0, ty0, color, B, useB, pix, L, exportStage, exportLevels);
 }
 
 // float4 frame -> reference host layout: stage[0 .. 3*total) = AoS {I,dx,dy}, stage[3*total ..) = absgrad
-__global__ void __launch_bounds__(256) export_kernel(const float4* __restrict__ pix, float* __restrict__ stage, PyrLevels L) {
+__global__ void __launch_bounds__(256) export_kernel(const float4* __restrict__ pix, float* __restrict__ stage, PyrLevels L, int nExport) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= L.total) return;
+  if (g >= nExport) return;
   int lvl = 0;
 #pragma unroll
   for (int l = 1; l < NALO_MAX_LEVELS; l++)
@@ -286,10 +298,14 @@ PyrLevels make_levels(const nalo_ctx* ctx) {
 }  // namespace
 
 // color_dev: w0*h0 floats on the device. Planar scratch lives in ctx->d_stage (>= sum_{l>=1} w_l h_l floats).
-int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float* B256_host) {
+int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float* B256_host, float* exportStage, int exportLevels) {
   if (slot < 0 || slot >= ctx->maxFrames) return nalo_fail(ctx, NALO_E_ARG, "frame slot %d out of range", slot);
   NALO_CUDA(ctx, cudaSetDevice(ctx->device));
   PyrLevels L = make_levels(ctx);
+  if (ctx->frames[slot].hostPending) {  // an asynchronous export still reads this slot: order the overwrite after it
+    NALO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->frames[slot].hostReady, 0));
+    ctx->frames[slot].hostPending = false;
+  }
   int useB = 0;
   if (B256_host) {
     NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_B, B256_host, sizeof(float) * 256, cudaMemcpyHostToDevice, ctx->stream));
@@ -297,8 +313,9 @@ int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float
   }
   if (ctx->levels <= 5) {
     dim3 fgrid((ctx->w0 + FT_W - 1) / FT_W, (ctx->h0 + FT_H - 1) / FT_H);
-    make_images_fused_kernel<<<fgrid, 512, 0, ctx->stream>>>(color_dev, ctx->d_B, useB, ctx->frames[slot].pix, L);
+    make_images_fused_kernel<<<fgrid, 512, 0, ctx->stream>>>(color_dev, ctx->d_B, useB, ctx->frames[slot].pix, L, exportStage, exportLevels);
     NALO_CHECK_LAUNCH(ctx);
+    NALO_CUDA(ctx, cudaEventRecord(ctx->frames[slot].built, ctx->stream));
     ctx->frames[slot].valid = true;
     if (ctx->histFrameSlot == slot) ctx->histFrameSlot = -1;
     return NALO_OK;
@@ -315,6 +332,12 @@ int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float
   }
   grad_kernel<<<(L.total + 255) / 256, 256, 0, ctx->stream>>>(color_dev, planar, ctx->d_B, useB, ctx->frames[slot].pix, L);
   NALO_CHECK_LAUNCH(ctx);
+  if (exportStage != nullptr && exportLevels > 0) {
+    const int nExport = (exportLevels >= ctx->levels) ? L.total : ctx->denseOff[exportLevels];
+    export_kernel<<<(nExport + 255) / 256, 256, 0, ctx->stream>>>(ctx->frames[slot].pix, exportStage, L, nExport);
+    NALO_CHECK_LAUNCH(ctx);
+  }
+  NALO_CUDA(ctx, cudaEventRecord(ctx->frames[slot].built, ctx->stream));
   ctx->frames[slot].valid = true;
   if (ctx->histFrameSlot == slot) ctx->histFrameSlot = -1;
   return NALO_OK;
@@ -323,7 +346,7 @@ int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float
 int nalo_images_to_host(nalo_ctx* ctx, int slot, float* dIp_host, float* absgrad_host) {
   if (slot < 0 || slot >= ctx->maxFrames || !ctx->frames[slot].valid) return nalo_fail(ctx, NALO_E_STATE, "frame slot %d not built", slot);
   PyrLevels L = make_levels(ctx);
-  export_kernel<<<(L.total + 255) / 256, 256, 0, ctx->stream>>>(ctx->frames[slot].pix, ctx->d_stage, L);
+  export_kernel<<<(L.total + 255) / 256, 256, 0, ctx->stream>>>(ctx->frames[slot].pix, ctx->d_stage, L, L.total);
   NALO_CHECK_LAUNCH(ctx);
   if (dIp_host)
     NALO_CUDA(ctx, cudaMemcpyAsync(dIp_host, ctx->d_stage, sizeof(float) * 3 * (size_t)L.total, cudaMemcpyDeviceToHost, ctx->stream));
@@ -340,15 +363,55 @@ int nalo_make_images(nalo_ctx* ctx, int slot, const float* color_host, const flo
   if (!ctx || !color_host) return NALO_E_ARG;
   NALO_CUDA(ctx, cudaSetDevice(ctx->device));
   NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_color, color_host, sizeof(float) * (size_t)ctx->w0 * ctx->h0, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = nalo_images_run(ctx, slot, ctx->d_color, B256);
+  int rc = nalo_images_run(ctx, slot, ctx->d_color, B256, nullptr, 0);
   if (rc != NALO_OK) return rc;
   if (dIp_host || absgrad_host) return nalo_images_to_host(ctx, slot, dIp_host, absgrad_host);
   return NALO_OK;
 }
 
+// Asynchronous variant: the pyramid is built on the context stream as usual; the reference-layout host copies of the
+// first `levels_host` levels are exported and copied on a SECOND stream, so tracking of the new frame (context stream)
+// overlaps the 7.5-9.9 MB D2H. The host buffers must stay valid until nalo_frame_host_wait(slot) returns; they should be
+// pinned (nalo_host_alloc) — with pageable memory the driver stages the copy and the call blocks.
+int nalo_make_images_async(nalo_ctx* ctx, int slot, const float* color_host, const float* B256, float* dIp_host, float* absgrad_host,
+                           int levels_host) {
+  if (!ctx || !color_host) return NALO_E_ARG;
+  if (levels_host < 0 || levels_host > ctx->levels) return nalo_fail(ctx, NALO_E_ARG, "levels_host %d out of range", levels_host);
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_color, color_host, sizeof(float) * (size_t)ctx->w0 * ctx->h0, cudaMemcpyHostToDevice, ctx->stream));
+  const bool wantHost = (dIp_host || absgrad_host) && levels_host > 0;
+  if (wantHost && ctx->exportBusy) {  // the single export staging buffer is still being copied out for another frame
+    NALO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->exportDone, 0));
+    ctx->exportBusy = false;
+  }
+  int rc = nalo_images_run(ctx, slot, ctx->d_color, B256, wantHost ? ctx->d_exportStage : nullptr, levels_host);
+  if (rc != NALO_OK) return rc;
+  if (!wantHost) return NALO_OK;
+  PyrLevels L = make_levels(ctx);
+  const int nExport = (levels_host >= ctx->levels) ? L.total : ctx->denseOff[levels_host];
+  cudaStream_t cs = ctx->copyStream;
+  NALO_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->frames[slot].built, 0));  // the pyramid kernel wrote the staging copy too
+  // staging layout: [0, 3*total) AoS {I,dx,dy} of the exported pixels, [3*total, 4*total) absSquaredGrad
+  if (dIp_host) NALO_CUDA(ctx, cudaMemcpyAsync(dIp_host, ctx->d_exportStage, sizeof(float) * 3 * (size_t)nExport, cudaMemcpyDeviceToHost, cs));
+  if (absgrad_host)
+    NALO_CUDA(ctx, cudaMemcpyAsync(absgrad_host, ctx->d_exportStage + 3 * (size_t)L.total, sizeof(float) * (size_t)nExport, cudaMemcpyDeviceToHost, cs));
+  NALO_CUDA(ctx, cudaEventRecord(ctx->frames[slot].hostReady, cs));
+  NALO_CUDA(ctx, cudaEventRecord(ctx->exportDone, cs));
+  ctx->frames[slot].hostPending = true;
+  ctx->exportBusy = true;
+  return NALO_OK;
+}
+
+int nalo_frame_host_wait(nalo_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= ctx->maxFrames) return NALO_E_ARG;
+  if (!ctx->frames[slot].hostPending) return NALO_OK;
+  NALO_CUDA(ctx, cudaEventSynchronize(ctx->frames[slot].hostReady));
+  return NALO_OK;  // hostPending stays set until the slot is rebuilt: a later overwrite still orders itself after the event
+}
+
 int nalo_make_images_dev(nalo_ctx* ctx, int slot, const float* color_dev, const float* B256_host) {
   if (!ctx || !color_dev) return NALO_E_ARG;
-  return nalo_images_run(ctx, slot, color_dev, B256_host);
+  return nalo_images_run(ctx, slot, color_dev, B256_host, nullptr, 0);
 }
 
 int nalo_get_frame(nalo_ctx* ctx, int slot, float* dIp_host, float* absgrad_host) {

@@ -209,3 +209,41 @@ def test_track_idempotent_at_convergence(kitti_pair, gpu_ctx_kitti, oracle):
     dt, dr = synth.pose_distance(pose, pose2)
     assert dt < 1e-5 and dr < 1e-5, (dt, dr)
     assert st2["evals"] <= st["evals"]
+
+
+def test_make_images_async_host_copies(kitti_pair, gpu_ctx_kitti, oracle):
+    """nalo_make_images_async: the host copies exported on the second stream equal the synchronous ones; tracking the
+    new frame in between does not disturb them; rebuilding a slot orders itself after a pending export."""
+    from conftest import make_oracle_tracker
+
+    P = kitti_pair
+    ctx = gpu_ctx_kitti
+    w, h = P["w"], P["h"]
+    n0, tot = w * h, ctx.tot
+    _, idw, ws = make_oracle_tracker(oracle, P)
+    ctx.make_images(0, P["ref"])
+    ctx.make_k(0, *P["scene"].K)
+    ctx.set_ref_dense(0, 0, idw, ws)
+    pin_d = capi.pinned_array((tot, 3), np.float32)
+    pin_a = capi.pinned_array((tot,), np.float32)
+    # level 0 only, with a track of the same frame running while the copy is in flight
+    pin_d[...] = -7.0
+    pin_a[...] = -7.0
+    ctx.make_images_async(1, P["new"], pin_d, pin_a, levels_host=1)
+    ok, pose, aff, lr, fl, st = ctx.track(0, 1, synth.pose_identity(), [0, 0])
+    ctx.frame_host_wait(1)
+    assert ok
+    assert np.array_equal(_bits(pin_d[:n0]), _bits(P["dnew"][:n0])) and np.array_equal(_bits(pin_a[:n0]), _bits(P["agnew"][:n0]))
+    assert np.all(pin_d[n0:] == -7.0) and np.all(pin_a[n0:] == -7.0)
+    # all levels
+    ctx.make_images_async(1, P["new"], pin_d, pin_a)
+    ctx.frame_host_wait(1)
+    assert np.array_equal(_bits(pin_d), _bits(P["dnew"])) and np.array_equal(_bits(pin_a), _bits(P["agnew"]))
+    # back-to-back rebuilds of the same slot: the second image wins, nothing is torn
+    pin_d2 = capi.pinned_array((tot, 3), np.float32)
+    pin_a2 = capi.pinned_array((tot,), np.float32)
+    ctx.make_images_async(1, P["new"], pin_d, pin_a)
+    ctx.make_images_async(1, P["ref"], pin_d2, pin_a2)
+    ctx.frame_host_wait(1)
+    assert np.array_equal(_bits(pin_d2), _bits(P["dref"])) and np.array_equal(_bits(pin_a2), _bits(P["agref"]))
+    assert np.array_equal(_bits(pin_d), _bits(P["dnew"]))

@@ -150,7 +150,29 @@ def main():
         d, wl, _ = T.run(lambda i: ctx.make_images(1, pins[i % 4]))
         add("a1 makeImages (pinned host image)", d, wl, alg, 1, "frame", c, 1, "H2D 1.87 MB inside")
         d, wl, _ = T.run(lambda i: ctx.make_images(1, pins[i % 4], want_host=True), reps=8)
-        add("a1 makeImages + host dIp/absgrad", d, wl, alg, 1, "frame", c, 1, "plus D2H 9.9 MB (reference layout)")
+        add("a1 makeImages + host dIp/absgrad", d, wl, alg, 1, "frame", c, 1, "plus D2H 9.9 MB (reference layout) into pageable memory")
+        pin_d = capi.pinned_array((tot_px, 3), np.float32)
+        pin_a = capi.pinned_array((tot_px,), np.float32)
+
+        def f_async(lv):
+            def f(i):
+                ctx.make_images_async(1, pins[i % 4], pin_d, pin_a, levels_host=lv)
+                ctx.frame_host_wait(1)
+            return f
+
+        d, wl, _ = T.run(f_async(L), reps=10)
+        add("a1 makeImages + pinned host copies, all levels", d, wl, alg, 1, "frame", c, 1, "async export on a 2nd stream, waited for (9.9 MB D2H)")
+        d, wl, _ = T.run(f_async(1), reps=10)
+        add("a1 makeImages + pinned host copies, level 0", d, wl, alg, 1, "frame", c, 1, "7.5 MB D2H; what ImmaturePoint / linearize read")
+
+        def f_overlap(i):
+            ctx.make_images_async(1, pins[i % 4], pin_d, pin_a, levels_host=1)
+            r = ctx.track(0, 1, p0, [0.0, 0.0])
+            ctx.frame_host_wait(1)
+            return r
+
+        d, wl, _ = T.run(f_overlap, reps=10)
+        add("frame: makeImages(async host copies L0) + track + wait", d, wl, alg, 1, "frame", None, None, "D2H overlapped with the tracking kernel")
 
     # ------------------------------------------------------------------ a2-a4
     if "select" in rows_wanted:
