@@ -20,6 +20,8 @@
 // Arithmetic that feeds a comparison is un-contracted fp32 in the reference's order, so the selection map is
 // bit-identical to the CPU oracle. randomPattern is glibc's rand() restated (TYPE_3 additive feedback), so the
 // product does not depend on the host libc.
+#include <cstdlib>
+
 #include "nalo_common.cuh"
 
 namespace {
@@ -304,6 +306,137 @@ __global__ void __launch_bounds__(128) select_kernel(const float4* __restrict__ 
   if (c4) atomicAdd(&counts[2], c4);
 }
 
+// ---- warp-parallel form of the same selection -----------------------------------------------------------------------
+// The nested loops of the reference (:608-703) carry state across pixels (bestIdx3/bestIdx4 turn to -2 and stay there),
+// but that state machine has a closed form. With "visit order" = 2pot blocks row-major, pot blocks row-major inside,
+// pixels raster inside, and dirNorm_k(x) = |grad0(x) . dir_k| (or the level's absSquaredGrad without direction
+// distribution):
+//   label 1, per pot block : the first arg-max of dirNorm_2 over pixels with absgrad0 > TH0 (and dirNorm_2 > 0);
+//                            the block "triggers" iff such a pixel exists;
+//   label 2, per 2pot block: only if none of its pot blocks triggers (a trigger sets bestIdx3 = -2 for the rest of the
+//                            2pot block and the final test is bestIdx3 > 0): the first arg-max of dirNorm_3 over pixels
+//                            with absgrad1 > TH1 (and dirNorm_3 > 0);
+//   label 4, per 4pot block: only if bestIdx4 never became -2, i.e. no pot block triggers AND no level-2 candidate was
+//                            ever recorded — a candidate is recorded at pixel x of a 2pot block iff x comes before that
+//                            block's first trigger and passes the level-1 test with dirNorm_3 > 0: the first arg-max of
+//                            dirNorm_4 over pixels with absgrad2 > TH2 (and dirNorm_4 > 0).
+// One WARP per 4pot block: lanes stride over the block's pixels in visit order; arg-max-first reductions are 64-bit
+// atomicMax in shared memory on {float bits, ~visit index}. Two sweeps (the second needs each 2pot block's first
+// trigger). Bit-identical to select_kernel (tests/test_gpu_selector.py compares both with the oracle).
+constexpr int kSelWarps = 8;
+struct SelWarpScratch {
+  unsigned long long best1[16];
+  unsigned long long best3[4];
+  unsigned long long best4;
+  int firstTrig[4];
+  int upd3;
+  float dir[21][2];  // 0..15: pot blocks (dir2), 16..19: 2pot blocks (dir3), 20: the 4pot block (dir4)
+};
+__device__ __forceinline__ unsigned long long sel_key(float val, int v) {
+  return ((unsigned long long)__float_as_uint(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)v);
+}
+__global__ void __launch_bounds__(kSelWarps * 32) select_warp_kernel(const float4* __restrict__ pix, const float* __restrict__ thsSmoothed, SelGeom g,
+                                                                    const int* __restrict__ n2Prefix, const unsigned char* __restrict__ randomPattern,
+                                                                    float* __restrict__ map_out, int* __restrict__ counts) {
+  __shared__ SelWarpScratch scr[kSelWarps];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b4 = blockIdx.x * kSelWarps + wid;
+  if (b4 >= g.nX4 * g.nY4) return;  // whole warps leave together; no block-wide barrier below
+  SelWarpScratch& S = scr[wid];
+  const int pot = g.pot, w = g.w, h = g.h, pot2 = pot * pot;
+  const int x4 = (b4 % g.nX4) * 4 * pot, y4 = (b4 / g.nX4) * 4 * pot;
+  const float4* pix1 = pix + g.off1;
+  const float4* pix2 = pix + g.off2;
+  if (lane < 16) S.best1[lane] = 0ull;
+  if (lane < 4) { S.best3[lane] = 0ull; S.firstTrig[lane] = 0x7fffffff; }
+  if (lane == 0) { S.best4 = 0ull; S.upd3 = 0; }
+  // directions: lane l < 16 -> pot block l (dir2), lanes 16..19 -> 2pot block (dir3), lane 20 -> dir4
+  int dsel = 0;
+  if (lane < 16) dsel = randomPattern[n2Prefix[b4 * 16 + lane]] & 0xF;
+  else if (lane < 20) dsel = randomPattern[n2Prefix[b4 * 16 + (lane - 16) * 4]] & 0xF;
+  else if (lane == 20) dsel = randomPattern[n2Prefix[b4 * 16]] & 0xF;
+  if (lane <= 20) { S.dir[lane][0] = kDir[dsel][0]; S.dir[lane][1] = kDir[dsel][1]; }
+  __syncwarp();
+  const int nV = 16 * pot2;
+  for (int sweep = 0; sweep < 2; sweep++) {
+    for (int v = lane; v < nV; v += 32) {
+      const int B = v / (4 * pot2), r = v - B * 4 * pot2;
+      const int p = r / pot2, q = r - p * pot2;
+      const int y1 = q / pot, x1 = q - y1 * pot;
+      const int xf = x4 + (B & 1) * 2 * pot + (p & 1) * pot + x1;
+      const int yf = y4 + (B >> 1) * 2 * pot + (p >> 1) * pot + y1;
+      if (xf >= w || yf >= h || border_skip(g, xf, yf)) continue;
+      const int slot = B * 4 + p;
+      const float pixelTH0 = thsSmoothed[(xf >> 5) + (yf >> 5) * g.thsStep];
+      const float pixelTH1 = __fmul_rn(pixelTH0, g.dw1);
+      const float pixelTH2 = __fmul_rn(pixelTH1, g.dw2);
+      const float4 px = pix[xf + w * yf];
+      const float ag0 = px.w;
+      const float dir2x = S.dir[slot][0], dir2y = S.dir[slot][1];
+      const float dir3x = S.dir[16 + B][0], dir3y = S.dir[16 + B][1];
+      const float dir4x = S.dir[20][0], dir4y = S.dir[20][1];
+      bool trig = false;
+      float dn2 = 0.f;
+      if (ag0 > __fmul_rn(pixelTH0, g.thFactor)) {
+        dn2 = fabsf(__fadd_rn(__fmul_rn(px.y, dir2x), __fmul_rn(px.z, dir2y)));
+        if (!g.dirDist) dn2 = ag0;
+        trig = dn2 > 0.f;
+      }
+      if (sweep == 0) {
+        if (trig) {
+          atomicMax(&S.best1[slot], sel_key(dn2, v));
+          atomicMin(&S.firstTrig[B], v);
+        }
+      } else {
+        const float ag1 = pix1[(int)(xf * 0.5f + 0.25f) + (int)(yf * 0.5f + 0.25f) * g.w1].w;
+        if (ag1 > __fmul_rn(pixelTH1, g.thFactor)) {
+          float dn3 = fabsf(__fadd_rn(__fmul_rn(px.y, dir3x), __fmul_rn(px.z, dir3y)));
+          if (!g.dirDist) dn3 = ag1;
+          if (dn3 > 0.f) {
+            atomicMax(&S.best3[B], sel_key(dn3, v));
+            if (v < S.firstTrig[B]) S.upd3 = 1;  // a level-2 candidate recorded before the block's first trigger
+          }
+        }
+        const float ag2 = pix2[(int)(xf * 0.25f + 0.125f) + (int)(yf * 0.25f + 0.125f) * g.w2].w;
+        if (ag2 > __fmul_rn(pixelTH2, g.thFactor)) {
+          float dn4 = fabsf(__fadd_rn(__fmul_rn(px.y, dir4x), __fmul_rn(px.z, dir4y)));
+          if (!g.dirDist) dn4 = ag2;
+          if (dn4 > 0.f) atomicMax(&S.best4, sel_key(dn4, v));
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // decode a visit index back to the pixel index
+  auto idx_of = [&](unsigned long long key) {
+    const int v = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+    const int B = v / (4 * pot2), r = v - B * 4 * pot2;
+    const int p = r / pot2, q = r - p * pot2;
+    const int y1 = q / pot, x1 = q - y1 * pot;
+    const int xf = x4 + (B & 1) * 2 * pot + (p & 1) * pot + x1;
+    const int yf = y4 + (B >> 1) * 2 * pot + (p >> 1) * pot + y1;
+    return xf + w * yf;
+  };
+  int c2 = 0, c3 = 0, c4 = 0;
+  if (lane < 16 && S.best1[lane] != 0ull) { map_out[idx_of(S.best1[lane])] = 1.f; c2 = 1; }
+  if (lane >= 16 && lane < 20) {
+    const int B = lane - 16;
+    if (S.firstTrig[B] == 0x7fffffff && S.best3[B] != 0ull) { map_out[idx_of(S.best3[B])] = 2.f; c3 = 1; }
+  }
+  if (lane == 20) {
+    const bool anyTrig = S.firstTrig[0] != 0x7fffffff || S.firstTrig[1] != 0x7fffffff || S.firstTrig[2] != 0x7fffffff || S.firstTrig[3] != 0x7fffffff;
+    if (!anyTrig && !S.upd3 && S.best4 != 0ull) { map_out[idx_of(S.best4)] = 4.f; c4 = 1; }
+  }
+  c2 = __reduce_add_sync(0xffffffffu, c2);
+  c3 = __reduce_add_sync(0xffffffffu, c3);
+  c4 = __reduce_add_sync(0xffffffffu, c4);
+  if (lane == 0) {
+    if (c2) atomicAdd(&counts[0], c2);
+    if (c3) atomicAdd(&counts[1], c3);
+    if (c4) atomicAdd(&counts[2], c4);
+  }
+}
+
 // makeMaps random drop (:231-249): rn = exclusive scan of (map != 0)
 __global__ void nonzero_kernel(const float* __restrict__ map, int n, int* __restrict__ flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -407,7 +540,12 @@ int run_select(nalo_ctx* ctx, int slot, int pot, float thFactor, int n3[3]) {
     rc = exclusive_scan(ctx, selUnamb, prefix, nSlots, blockSums, counts + 4);
     if (rc != NALO_OK) return rc;
   }
-  select_kernel<<<(nB4 + 127) / 128, 128, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, prefix, ctx->d_randomPattern, ctx->d_map, counts);
+  static const bool serialSelect = getenv("NALO_SELECT_SERIAL") != nullptr;  // the verbatim one-thread-per-block replay (kept as a cross-check)
+  if (serialSelect)
+    select_kernel<<<(nB4 + 127) / 128, 128, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, prefix, ctx->d_randomPattern, ctx->d_map, counts);
+  else
+    select_warp_kernel<<<(nB4 + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, prefix, ctx->d_randomPattern,
+                                                                                          ctx->d_map, counts);
   NALO_CHECK_LAUNCH(ctx);
   NALO_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts + 32, counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, ctx->stream));
   NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -101,3 +101,33 @@ def test_select_no_direction_distribution(small_pair, gpu_ctx_small, oracle):
         assert np.array_equal(n_g, n_o) and np.array_equal(m_g, m_o)
     finally:
         ctx.set_params(selectDirectionDistribution=1, minGradHistAdd=7.0)
+
+
+def test_select_coarse_labels(small_pair, gpu_ctx_small, oracle):
+    """Mostly flat image with a few soft blobs and weak texture: many pot blocks select nothing at level 0, so the
+    label-2 / label-4 branches (level-1 / level-2 gradient tests, the bestIdx3 / bestIdx4 sentinels) decide the map.
+    Large potentials make every warp walk hundreds of pixels per 4pot block."""
+    P = small_pair
+    w, h, L = P["w"], P["h"], P["L"]
+    rng = np.random.default_rng(4)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.full((h, w), 120.0, dtype=np.float32)
+    for _ in range(25):
+        cx, cy, s, a = rng.uniform(0, w), rng.uniform(0, h), rng.uniform(4, 30), rng.uniform(-60, 60)
+        img += (a * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))).astype(np.float32)
+    img += rng.normal(0, 0.6, (h, w)).astype(np.float32)
+    img[:, : w // 3] = np.round(img[:, : w // 3] / 8) * 8  # plateaus: exact zero gradients and exact ties
+    ctx = gpu_ctx_small
+    ctx.make_images(0, img)
+    d_o, ag_o = oracle.make_images(img, w, h, L)
+    S = oracle.Selector(w, h)
+    S.make_hists(ag_o[: w * h])
+    seen = np.zeros(3, dtype=np.int64)
+    for pot in (1, 2, 3, 4, 7, 10, 13):
+        for thF in (1.0, 2.0, 0.5):
+            m_o, n_o = S.select(d_o, ag_o, _offs(P), pot, thF)
+            m_g, n_g = ctx.selector_select(0, pot, thF)
+            assert np.array_equal(n_g, n_o), (pot, thF, n_g, n_o)
+            assert np.array_equal(m_g, m_o), (pot, thF, int(np.count_nonzero(m_g != m_o)))
+            seen += n_o
+    assert seen[1] > 50 and seen[2] > 10, seen  # the coarse labels really occurred
