@@ -278,3 +278,110 @@ def make_ba_problem(nf=7, pts_per_frame=100, seed=DEFAULT_SEED, lin_fraction=0.0
         adHTdeltaF=rng.normal(0, 1e-3, (nf * nf, 8)).astype(np.float32),
         cDeltaF=rng.normal(0, 1e-2, 4).astype(np.float32),
     )
+
+
+# ---------------------------------------------------------------- linearize (f1) synthetic problem
+LIN_PATTERN = np.array([[0, -2], [-1, -1], [1, -1], [-2, 0], [0, 0], [2, 0], [-1, 1], [0, 2]], dtype=np.int32)  # staticPattern[8]
+LIN_PAIR_WORDS = 32
+
+
+def _pose_Rt(pose7):
+    return quat_to_R(pose7[:4]), np.asarray(pose7[4:], dtype=np.float64)
+
+
+def _bilinear(img, x, y):
+    ix, iy = np.floor(x).astype(int), np.floor(y).astype(int)
+    dx, dy = x - ix, y - iy
+    return (img[iy, ix] * (1 - dx) * (1 - dy) + img[iy, ix + 1] * dx * (1 - dy) + img[iy + 1, ix] * (1 - dx) * dy + img[iy + 1, ix + 1] * dx * dy)
+
+
+def make_lin_problem(scene: Scene, nf=4, pts_per_frame=500, seed=DEFAULT_SEED, bad_depth_fraction=0.05, fej_noise=1e-3):
+    """Inputs of PointFrameResidual::linearize (src/FullSystem/Residuals.cpp:78-274) for a window of nf keyframes that all
+    see the analytic scene: frame k is the reference view warped by a small random motion T_k (frame 0 = identity).
+    Points are sampled in frame 0, moved into their host frame h (pixel and inverse depth), and get one residual to every
+    other frame, flattened and bucket-sorted like the BA records (include/nalo_gpu.h). A few points get a wrong depth
+    (-> OUTLIER) and some lie near the border (-> OOB), so all three result states occur.
+    Returns a dict with the flat arrays, the nf images, and the per-(host,target) precalc table."""
+    rng = np.random.default_rng(seed)
+    w, h = scene.w, scene.h
+    fx, fy, cx, cy = scene.K
+    Kmat = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    Ki = np.linalg.inv(Kmat)
+    poses, affs, imgs = [], [], []
+    for k in range(nf):
+        if k == 0:
+            pose, aff = pose_identity(), np.zeros(2)
+        else:
+            xi, aff = random_motion(rng)
+            pose = se3_exp(xi)
+        poses.append(pose)
+        affs.append(aff)
+        imgs.append(render_new(scene, pose, aff) if k else render_ref(scene))
+    # frame-frame precalc (HessianBlocks.cpp:192-222); the evaluation point differs slightly from the current state (FEJ)
+    pairs = np.zeros((nf * nf, LIN_PAIR_WORDS), dtype=np.float32)
+    rel = {}
+    for hst in range(nf):
+        Rh, th = _pose_Rt(poses[hst])
+        for tgt in range(nf):
+            Rt_, tt = _pose_Rt(poses[tgt])
+            R = Rt_ @ Rh.T
+            t = tt - R @ th
+            rel[(hst, tgt)] = (R, t)
+            om = rng.normal(0, fej_noise, 3)
+            R0 = quat_to_R(so3_exp_quat(om)) @ R
+            t0 = t + rng.normal(0, fej_noise * 0.1, 3)
+            P = pairs[hst + tgt * nf]
+            P[0:9] = R0.astype(np.float32).ravel()
+            P[9:12] = t0
+            P[12:21] = (Kmat @ R @ Ki).astype(np.float32).ravel()
+            P[21:24] = Kmat @ t
+            a = np.exp(affs[tgt][0] - affs[hst][0])
+            P[24] = a
+            P[25] = affs[tgt][1] - a * affs[hst][1]
+            P[26] = affs[hst][1]
+            P[27] = 8 * 12 * 12.0  # frameEnergyTH ~ patternNum * setting_outlierTH of a fresh frame (FullSystem.cpp setNewFrameEnergyTH)
+            P.view(np.int32)[28] = tgt
+    pt4, color, weights, pack, point = [], [], [], [], []
+    pt_id = 0
+    per_bucket = {}
+    for hst in range(nf):
+        x0 = rng.uniform(8, w - 9, pts_per_frame)
+        y0 = rng.uniform(8, h - 9, pts_per_frame)
+        border = rng.random(pts_per_frame) < 0.04
+        x0[border] = rng.choice([2.5, w - 3.5], border.sum())
+        id0 = scene.idepth(x0, y0)
+        # into the host frame
+        Rh, th = _pose_Rt(poses[hst])
+        X = np.stack([(x0 - cx) / fx, (y0 - cy) / fy, np.ones_like(x0)])
+        p = Rh @ X + th[:, None] * id0
+        uh = fx * p[0] / p[2] + cx
+        vh = fy * p[1] / p[2] + cy
+        idh = id0 / p[2]
+        bad = rng.random(pts_per_frame) < bad_depth_fraction
+        idh_used = np.where(bad, idh * rng.uniform(1.5, 3.0, pts_per_frame), idh)
+        inside = (uh > 3) & (uh < w - 4) & (vh > 3) & (vh < h - 4)
+        gyh, gxh = np.gradient(imgs[hst].astype(np.float64))
+        for k in range(pts_per_frame):
+            if not inside[k]:
+                continue
+            cols = np.array([_bilinear(imgs[hst].astype(np.float64), uh[k] + d[0], vh[k] + d[1]) for d in LIN_PATTERN])
+            g2 = np.array([_bilinear(gxh, uh[k] + d[0], vh[k] + d[1]) ** 2 + _bilinear(gyh, uh[k] + d[0], vh[k] + d[1]) ** 2 for d in LIN_PATTERN])
+            wts = np.sqrt(2500.0 / (2500.0 + g2))
+            for tgt in range(nf):
+                if tgt == hst:
+                    continue
+                per_bucket.setdefault(hst + tgt * nf, []).append(
+                    (uh[k], vh[k], idh_used[k] * (1 + rng.normal(0, fej_noise)), idh_used[k], cols, wts, hst | (tgt << 8) | (1 << 16), pt_id))
+            pt_id += 1
+    for b in sorted(per_bucket):
+        for (u, v, idz, idc, cols, wts, pk, pid) in per_bucket[b]:
+            pt4.append((u, v, idz, idc))
+            color.append(cols)
+            weights.append(wts)
+            pack.append(pk)
+            point.append(pid)
+    n = len(pack)
+    return dict(nf=nf, n_res=n, n_pts=pt_id, w=w, h=h, K=(fx, fy, cx, cy), images=imgs, pairs=pairs,
+                pt4=np.array(pt4, dtype=np.float32).reshape(n, 4), color=np.array(color, dtype=np.float32).reshape(n, 8),
+                weights=np.array(weights, dtype=np.float32).reshape(n, 8), pack=np.array(pack, dtype=np.uint32),
+                point=np.array(point, dtype=np.int32), state_in=np.zeros(n, dtype=np.uint8), energy_in=np.zeros(n, dtype=np.float32))

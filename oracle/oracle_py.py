@@ -386,3 +386,25 @@ def ba_sc(prob, JpJdF, ppA, ppL=None, shiftPriorToZero=True, nThreads=1, fast=Fa
         C.c_int(1 if shiftPriorToZero else 0), _ptr(accD), _ptr(accE), _ptr(accEB), _ptr(accHcc), _ptr(accbc), _ptr(pp),
     )
     return dict(accD=accD, accE=accE, accEB=accEB, accHcc=accHcc, accbc=accbc, perPoint=pp)
+
+
+def linearize(prob, dI_frames, rec_init=None, huberTH=9.0, outlierTHSumComponent=2500.0, affineOptModeA=0.0, affineOptModeB=0.0):
+    """PointFrameResidual::linearize over the flat problem of synth.make_lin_problem. dI_frames: per frame the level-0
+    AoS {I,dx,dy} image ([w*h,3] float32, e.g. from make_images). Returns dict(rec, state, energy, energy_outlier, center, proj)."""
+    n, nf = prob["n_res"], prob["nf"]
+    frames = [np.ascontiguousarray(f[: prob["w"] * prob["h"]], dtype=_f32) for f in dI_frames]
+    fp = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
+    rec = np.zeros((n, 76), dtype=_f32) if rec_init is None else np.ascontiguousarray(rec_init, dtype=_f32).copy()
+    state = np.zeros(n, dtype=np.uint8)
+    en = np.zeros(n, dtype=_f32)
+    eno = np.zeros(n, dtype=_f32)
+    center = np.zeros((n, 3), dtype=_f32)
+    proj = np.zeros((n, 16), dtype=_f32)
+    fx, fy, cx, cy = prob["K"]
+    lib().oracle_linearize(
+        C.c_int(n), C.c_int(nf), C.c_int(prob["w"]), C.c_int(prob["h"]), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
+        C.c_float(huberTH), C.c_float(outlierTHSumComponent), C.c_float(affineOptModeA), C.c_float(affineOptModeB), fp,
+        _ptr(prob["pairs"]), _ptr(prob["pt4"]), _ptr(prob["color"]), _ptr(prob["weights"]), _ptr(prob["pack"]), _ptr(prob["point"]),
+        _ptr(prob["state_in"]), _ptr(prob["energy_in"]), _ptr(rec), _ptr(state), _ptr(en), _ptr(eno), _ptr(center), _ptr(proj),
+    )
+    return dict(rec=rec, state=state, energy=en, energy_outlier=eno, center=center, proj=proj)
