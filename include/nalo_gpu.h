@@ -210,6 +210,39 @@ int nalo_ba_take_data(nalo_ba* ba, float* JpJdF_out /* nullable [n_res][8] */);
 int nalo_ba_accumulate_sc(nalo_ba* ba, int shiftPriorToZero, int useL, double* accD, double* accE, double* accEB, double* accHcc,
                           double* accbc, float* perPoint_out /* [n_pts][3] HdiF,bdSumF,idepth_hessian */);
 
+/* ---- f1 (SURVEY.md §8 f, "next"): PointFrameResidual::linearize (FullSystem/Residuals.cpp:78-274) -----------------
+ * Produces the residual records ON THE DEVICE, in place of the handle's records (same order as uploaded: bucket-sorted,
+ * n_res must equal the uploaded problem's n_res for the accumulators that follow), so a BA iteration uploads 88 B per
+ * residual (point data) instead of 304 B (Jacobians). Inputs are flat per-residual arrays:
+ *   pt4     [n][4]  point->u, point->v, point->idepth_zero_scaled, point->idepth_scaled
+ *   color   [n][8]  point->color          weights [n][8] point->weights
+ *   pack    [n]     host | target<<8 | flags<<16 (= record word 73)      point [n] point index (= record word 72)
+ *   state_in[n]     ResState of the residual (0 IN, 1 OOB, 2 OUTLIER; OOB residuals are skipped, :82-83), nullable = all IN
+ *   energy_in[n]    state_energy (returned unchanged for OOB), nullable
+ *   pairs [nf*nf][32] FrameFramePrecalc of bucket host + target*nf (HessianBlocks.cpp:192-222), floats:
+ *           0..8 PRE_RTll_0 (row-major) | 9..11 PRE_tTll_0 | 12..20 PRE_KRKiTll | 21..23 PRE_KtTll | 24..25 PRE_aff_mode |
+ *           26 PRE_b0_mode | 27 max(host,target frameEnergyTH) | 28 (int32) context frame slot of the TARGET pyramid
+ *   rec_init (nullable) [n][76] initial records (what OOB residuals keep); default: the handle's current records.
+ * huberTH / affineOptModeA,B come from the context's NaloParams. Outputs (nullable): new_state [n] (state_NewState),
+ * energy [n] (state_NewEnergy, resp. unchanged state_energy), energy_with_outlier [n], center3 [n][3]
+ * (centerProjectedTo), projected16 [n][16] (projectedTo), rec_out [n][76] (host copy of the records, for parity tests). */
+typedef struct NaloLinInput {
+  int n_res, nf;
+  const float* pt4;
+  const float* color;
+  const float* weights;
+  const uint32_t* pack;
+  const int* point;
+  const uint8_t* state_in;
+  const float* energy_in;
+  const float* pairs;
+  const float* rec_init;
+  float fx, fy, cx, cy;          /* HCalib->fxl(), fyl(), cxl(), cyl() */
+  float outlierTHSumComponent;   /* setting_outlierTHSumComponent = 50*50 */
+} NaloLinInput;
+int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, float* energy, float* energy_with_outlier, float* center3,
+                      float* projected16, float* rec_out);
+
 #ifdef __cplusplus
 }
 #endif

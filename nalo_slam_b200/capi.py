@@ -66,6 +66,12 @@ class NaloBAProblem(C.Structure):
     ]
 
 
+class NaloLinInput(C.Structure):
+    _fields_ = [("n_res", C.c_int), ("nf", C.c_int), ("pt4", _P), ("color", _P), ("weights", _P), ("pack", _P), ("point", _P),
+                ("state_in", _P), ("energy_in", _P), ("pairs", _P), ("rec_init", _P),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("outlierTHSumComponent", C.c_float)]
+
+
 _lib = None
 
 
@@ -475,6 +481,29 @@ class BA:
         out = np.zeros((max(self.prob["n_res"], 1), 8), dtype=_f32)
         self.ctx._ck(self.L.nalo_ba_take_data(self.h_, _ptr(out)))
         return out[: self.prob["n_res"]]
+
+    def linearize(self, prob, slots, rec_init=None, want_proj=True, want_rec=True, outlierTHSumComponent=2500.0):
+        """nalo_ba_linearize on a synth.make_lin_problem dict; slots[k] = context frame slot holding frame k's pyramid."""
+        n, nf = prob["n_res"], prob["nf"]
+        pairs = prob["pairs"].copy()
+        pairs.view(np.int32)[:, 28] = np.asarray(slots, dtype=np.int32)[pairs.view(np.int32)[:, 28]]
+        I = NaloLinInput()
+        I.n_res, I.nf = n, nf
+        keep = [np.ascontiguousarray(prob[k]) for k in ("pt4", "color", "weights", "pack", "point", "state_in", "energy_in")] + [pairs]
+        I.pt4, I.color, I.weights, I.pack, I.point, I.state_in, I.energy_in, I.pairs = [a.ctypes.data for a in keep]
+        ri = None if rec_init is None else np.ascontiguousarray(rec_init, dtype=_f32)
+        I.rec_init = None if ri is None else ri.ctypes.data
+        I.fx, I.fy, I.cx, I.cy = prob["K"]
+        I.outlierTHSumComponent = outlierTHSumComponent
+        st = np.zeros(max(n, 1), dtype=np.uint8)
+        en = np.zeros(max(n, 1), dtype=_f32)
+        eno = np.zeros(max(n, 1), dtype=_f32)
+        ce = np.zeros((max(n, 1), 3), dtype=_f32)
+        pr = np.zeros((max(n, 1), 16), dtype=_f32) if want_proj else None
+        rec = np.zeros((max(n, 1), BA_RECORD_WORDS), dtype=_f32) if want_rec else None
+        self.ctx._ck(self.L.nalo_ba_linearize(self.h_, C.byref(I), _ptr(st), _ptr(en), _ptr(eno), _ptr(ce), _ptr(pr), _ptr(rec)))
+        return dict(state=st[:n], energy=en[:n], energy_outlier=eno[:n], center=ce[:n], proj=None if pr is None else pr[:n],
+                    rec=None if rec is None else rec[:n])
 
     def accumulate_sc(self, shiftPriorToZero=True, useL=False):
         nf, nP = self.prob["nf"], self.prob["n_pts"]

@@ -46,6 +46,13 @@ struct nalo_ba {
   int4* d_items = nullptr;       // work items: [0, nTop) top items, [maxItems, maxItems + nSc) Schur items (uploaded once)
   int* d_ptSlots = nullptr;      // [maxPts][8] per point in host-sorted order: record of the residual to target block tb (-1: none/inactive), [7] = point index
   double* h_out = nullptr;       // pinned staging of the small fp64 results
+  // f1 (nalo_ba_linearize) inputs/outputs, allocated on first use
+  bool linAlloc = false;
+  float *d_linPt4 = nullptr, *d_linColor = nullptr, *d_linWeights = nullptr, *d_linEnergyIn = nullptr, *d_linPairs = nullptr;
+  uint32_t* d_linPack = nullptr;
+  int* d_linPoint = nullptr;
+  uint8_t *d_linStateIn = nullptr, *d_linState = nullptr;
+  float *d_linEnergy = nullptr, *d_linEnergyOut = nullptr, *d_linCenter = nullptr, *d_linProj = nullptr;
   float* d_partials = nullptr;   // top: [items][96] ; sc: [items][72*72]
   double* d_out = nullptr;       // result staging (double)
   int* d_counter = nullptr;
@@ -570,6 +577,216 @@ __global__ void sc_finalize_kernel(const float* __restrict__ partials, const int
   }
 }
 
+// ---- f1: PointFrameResidual::linearize (src/FullSystem/Residuals.cpp:78-274) ------------------------------------------
+// One thread per residual, same operation order as the CPU oracle (un-contracted fp32), so records, states and energies
+// are bit-identical to it. Inputs are flat per-residual arrays (bucket-sorted like the records); the target image is the
+// level-0 float4 frame already resident in the context's frame slot. The record is written straight into the BA
+// handle's device records: the accumulators that follow never see a host copy (removes the
+// 304 B/residual upload per iteration). Partial-write semantics of the reference are kept: a residual that leaves the
+// image at pattern pixel k has J's geometric part and the entries of pixels < k overwritten, the rest untouched.
+struct LinArgs {
+  int n, nf, w, h;
+  float fx, fy, cx, cy, huberTH, outlierTHSum, modeA, modeB;
+  const float4* pt4;
+  const float4* color;    // [n][2]
+  const float4* weights;  // [n][2]
+  const uint32_t* pack;
+  const int* point;
+  const uint8_t* stateIn;
+  const float* energyIn;
+  const float* pairs;     // [nf*nf][32]
+  const float4* frames[NALO_BA_MAX_FRAMES];  // level-0 pyramids by frame slot listed in pairs[..][28] (resolved on the host)
+  float* rec;
+  uint8_t* newState;
+  float* energy;
+  float* energyOutlier;
+  float* center;     // [n][3]
+  float* projected;  // [n][16] nullable
+};
+__device__ __forceinline__ float lin_row3(const float* m, int r, float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(m[3 * r], x), __fmul_rn(m[3 * r + 1], y)), __fmul_rn(m[3 * r + 2], z));
+}
+__global__ void __launch_bounds__(128) linearize_kernel(const LinArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int kPat[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {0, 2}};
+  float* R_ = A.rec + (size_t)i * REC;
+  const uint32_t pk = A.pack[i];
+  reinterpret_cast<int*>(R_)[O_PT] = A.point[i];
+  reinterpret_cast<uint32_t*>(R_)[O_PACK] = pk;
+  R_[74] = 0.f;
+  R_[75] = 0.f;
+  A.energyOutlier[i] = -1.f;
+  if (A.stateIn[i] == 1) { A.newState[i] = 1; A.energy[i] = A.energyIn[i]; return; }
+  const int hst = pk & 0xFF, tgt = (pk >> 8) & 0xFF;
+  const float* P = A.pairs + (size_t)(hst + tgt * A.nf) * 32;
+  float RT0[9], tT0[3], KRKi[9], Kt[3];
+#pragma unroll
+  for (int k = 0; k < 9; k++) { RT0[k] = __ldg(P + k); KRKi[k] = __ldg(P + 12 + k); }
+#pragma unroll
+  for (int k = 0; k < 3; k++) { tT0[k] = __ldg(P + 9 + k); Kt[k] = __ldg(P + 21 + k); }
+  const float affLL0 = __ldg(P + 24), affLL1 = __ldg(P + 25), b0 = __ldg(P + 26), frameEnergyTH = __ldg(P + 27);
+  const int tslot = __float_as_int(__ldg(P + 28));
+  const float4* __restrict__ img = A.frames[tslot];
+  const float4 pt = __ldg(A.pt4 + i);
+  const float u_pt = pt.x, v_pt = pt.y, idepth_zero = pt.z, idepth = pt.w;
+  float col[8], wts[8];
+  {
+    const float4 c0 = __ldg(A.color + 2 * (size_t)i), c1 = __ldg(A.color + 2 * (size_t)i + 1);
+    const float4 w0 = __ldg(A.weights + 2 * (size_t)i), w1 = __ldg(A.weights + 2 * (size_t)i + 1);
+    col[0] = c0.x; col[1] = c0.y; col[2] = c0.z; col[3] = c0.w; col[4] = c1.x; col[5] = c1.y; col[6] = c1.z; col[7] = c1.w;
+    wts[0] = w0.x; wts[1] = w0.y; wts[2] = w0.z; wts[3] = w0.w; wts[4] = w1.x; wts[5] = w1.y; wts[6] = w1.z; wts[7] = w1.w;
+  }
+  const float fx = A.fx, fy = A.fy, cx = A.cx, cy = A.cy;
+  const float fxi = __fdiv_rn(1.0f, fx), fyi = __fdiv_rn(1.0f, fy);
+  const float wM3G = (float)(A.w - 3), hM3G = (float)(A.h - 3);
+  const int w = A.w;
+  // ---- projectPoint with derivatives (ResidualProjections.h:62-87)
+  const float K0 = __fmul_rn(__fsub_rn(__fadd_rn(u_pt, 0.f), cx), fxi), K1 = __fmul_rn(__fsub_rn(__fadd_rn(v_pt, 0.f), cy), fyi);
+  const float p0 = __fadd_rn(lin_row3(RT0, 0, K0, K1, 1.f), __fmul_rn(tT0[0], idepth_zero));
+  const float p1 = __fadd_rn(lin_row3(RT0, 1, K0, K1, 1.f), __fmul_rn(tT0[1], idepth_zero));
+  const float p2 = __fadd_rn(lin_row3(RT0, 2, K0, K1, 1.f), __fmul_rn(tT0[2], idepth_zero));
+  const float drescale = __fdiv_rn(1.0f, p2);
+  const float new_idepth = __fmul_rn(idepth_zero, drescale);
+  bool ok = drescale > 0.f;
+  float u = 0.f, v = 0.f, Ku = 0.f, Kv = 0.f;
+  if (ok) {
+    u = __fmul_rn(p0, drescale);
+    v = __fmul_rn(p1, drescale);
+    Ku = __fadd_rn(__fmul_rn(u, fx), cx);
+    Kv = __fadd_rn(__fmul_rn(v, fy), cy);
+    ok = Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G;
+  }
+  if (!ok) { A.newState[i] = 1; A.energy[i] = A.energyIn[i]; return; }
+  A.center[3 * (size_t)i] = Ku;
+  A.center[3 * (size_t)i + 1] = Kv;
+  A.center[3 * (size_t)i + 2] = new_idepth;
+  float r[72];  // record words 0..71 as they are produced
+  // SCALE_IDEPTH = 1, SCALE_F = SCALE_C = 50 (HessianBlocks.h:61-66)
+  const float d_d_x = __fmul_rn(__fmul_rn(__fmul_rn(drescale, __fsub_rn(tT0[0], __fmul_rn(tT0[2], u))), 1.0f), fx);
+  const float d_d_y = __fmul_rn(__fmul_rn(__fmul_rn(drescale, __fsub_rn(tT0[1], __fmul_rn(tT0[2], v))), 1.0f), fy);
+  float dCx[4], dCy[4];
+  dCx[2] = __fmul_rn(drescale, __fsub_rn(__fmul_rn(RT0[6], u), RT0[0]));
+  dCx[3] = __fmul_rn(__fmul_rn(__fmul_rn(fx, drescale), __fsub_rn(__fmul_rn(RT0[7], u), RT0[1])), fyi);
+  dCx[0] = __fmul_rn(K0, dCx[2]);
+  dCx[1] = __fmul_rn(K1, dCx[3]);
+  dCy[2] = __fmul_rn(__fmul_rn(__fmul_rn(fy, drescale), __fsub_rn(__fmul_rn(RT0[6], v), RT0[3])), fxi);
+  dCy[3] = __fmul_rn(drescale, __fsub_rn(__fmul_rn(RT0[7], v), RT0[4]));
+  dCy[0] = __fmul_rn(K0, dCy[2]);
+  dCy[1] = __fmul_rn(K1, dCy[3]);
+  dCx[0] = __fmul_rn(__fadd_rn(dCx[0], u), 50.0f);
+  dCx[1] = __fmul_rn(dCx[1], 50.0f);
+  dCx[2] = __fmul_rn(__fadd_rn(dCx[2], 1.f), 50.0f);
+  dCx[3] = __fmul_rn(dCx[3], 50.0f);
+  dCy[0] = __fmul_rn(dCy[0], 50.0f);
+  dCy[1] = __fmul_rn(__fadd_rn(dCy[1], v), 50.0f);
+  dCy[2] = __fmul_rn(dCy[2], 50.0f);
+  dCy[3] = __fmul_rn(__fadd_rn(dCy[3], 1.f), 50.0f);
+  r[O_JPDXI + 0] = __fmul_rn(new_idepth, fx);
+  r[O_JPDXI + 1] = 0.f;
+  r[O_JPDXI + 2] = __fmul_rn(__fmul_rn(-new_idepth, u), fx);
+  r[O_JPDXI + 3] = __fmul_rn(__fmul_rn(-u, v), fx);
+  r[O_JPDXI + 4] = __fmul_rn(__fadd_rn(1.f, __fmul_rn(u, u)), fx);
+  r[O_JPDXI + 5] = __fmul_rn(-v, fx);
+  r[O_JPDXI + 6] = 0.f;
+  r[O_JPDXI + 7] = __fmul_rn(new_idepth, fy);
+  r[O_JPDXI + 8] = __fmul_rn(__fmul_rn(-new_idepth, v), fy);
+  r[O_JPDXI + 9] = __fmul_rn(-__fadd_rn(1.f, __fmul_rn(v, v)), fy);
+  r[O_JPDXI + 10] = __fmul_rn(__fmul_rn(u, v), fy);
+  r[O_JPDXI + 11] = __fmul_rn(u, fy);
+#pragma unroll
+  for (int k = 0; k < 4; k++) { r[O_JPDC + k] = dCx[k]; r[O_JPDC + 4 + k] = dCy[k]; }
+  r[O_JPDD] = d_d_x;
+  r[O_JPDD + 1] = d_d_y;
+
+  float J00 = 0.f, J11 = 0.f, J10 = 0.f, A00 = 0.f, A01 = 0.f, A10 = 0.f, A11 = 0.f, B00 = 0.f, B01 = 0.f, B11 = 0.f;
+  float wJI2 = 0.f, energyLeft = 0.f;
+  int done = 0;  // pattern pixels completed
+#pragma unroll
+  for (int idx = 0; idx < 8; idx++) {
+    if (done == idx) {
+      const float x = __fadd_rn(u_pt, (float)kPat[idx][0]), y = __fadd_rn(v_pt, (float)kPat[idx][1]);
+      const float q0 = __fadd_rn(lin_row3(KRKi, 0, x, y, 1.f), __fmul_rn(Kt[0], idepth));
+      const float q1 = __fadd_rn(lin_row3(KRKi, 1, x, y, 1.f), __fmul_rn(Kt[1], idepth));
+      const float q2 = __fadd_rn(lin_row3(KRKi, 2, x, y, 1.f), __fmul_rn(Kt[2], idepth));
+      const float Kup = __fdiv_rn(q0, q2), Kvp = __fdiv_rn(q1, q2);
+      if (Kup > 1.1f && Kvp > 1.1f && Kup < wM3G && Kvp < hM3G) {
+        if (A.projected) { A.projected[16 * (size_t)i + 2 * idx] = Kup; A.projected[16 * (size_t)i + 2 * idx + 1] = Kvp; }
+        const int ix = (int)Kup, iy = (int)Kvp;
+        const float dx = __fsub_rn(Kup, (float)ix), dy = __fsub_rn(Kvp, (float)iy), dxdy = __fmul_rn(dx, dy);
+        const float w11 = dxdy, w01 = __fsub_rn(dy, dxdy), w10 = __fsub_rn(dx, dxdy);
+        const float w00 = __fadd_rn(__fsub_rn(__fsub_rn(1.f, dx), dy), dxdy);
+        const float4* bp = img + ix + iy * w;
+        const float4 t00 = __ldg(bp), t10 = __ldg(bp + 1), t01 = __ldg(bp + w), t11 = __ldg(bp + w + 1);
+        const float h0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w11, t11.x), __fmul_rn(w01, t01.x)), __fmul_rn(w10, t10.x)), __fmul_rn(w00, t00.x));
+        float h1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w11, t11.y), __fmul_rn(w01, t01.y)), __fmul_rn(w10, t10.y)), __fmul_rn(w00, t00.y));
+        float h2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w11, t11.z), __fmul_rn(w01, t01.z)), __fmul_rn(w10, t10.z)), __fmul_rn(w00, t00.z));
+        if (isfinite(h0)) {
+          const float residual = __fsub_rn(h0, __fadd_rn(__fmul_rn(affLL0, col[idx]), affLL1));
+          const float drdA = __fsub_rn(col[idx], b0);
+          float wgt = sqrtf(__fdiv_rn(A.outlierTHSum, __fadd_rn(A.outlierTHSum, __fadd_rn(__fmul_rn(h1, h1), __fmul_rn(h2, h2)))));
+          wgt = __fmul_rn(0.5f, __fadd_rn(wgt, wts[idx]));
+          const float ar = fabsf(residual);
+          float hw = ar < A.huberTH ? 1.f : __fdiv_rn(A.huberTH, ar);
+          energyLeft = __fadd_rn(energyLeft, __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(wgt, wgt), hw), residual), residual), __fsub_rn(2.f, hw)));
+          if (hw < 1.f) hw = sqrtf(hw);
+          hw = __fmul_rn(hw, wgt);
+          h1 = __fmul_rn(h1, hw);
+          h2 = __fmul_rn(h2, hw);
+          const float dA = __fmul_rn(drdA, hw);
+          r[O_RES + idx] = __fmul_rn(residual, hw);
+          r[O_JIDX + idx] = h1;
+          r[O_JIDX + 8 + idx] = h2;
+          r[O_JAB + idx] = (A.modeA < 0.f) ? 0.f : dA;
+          r[O_JAB + 8 + idx] = (A.modeB < 0.f) ? 0.f : hw;
+          J00 = __fadd_rn(J00, __fmul_rn(h1, h1));
+          J11 = __fadd_rn(J11, __fmul_rn(h2, h2));
+          J10 = __fadd_rn(J10, __fmul_rn(h1, h2));
+          A00 = __fadd_rn(A00, __fmul_rn(dA, h1));
+          A01 = __fadd_rn(A01, __fmul_rn(dA, h2));
+          A10 = __fadd_rn(A10, __fmul_rn(hw, h1));
+          A11 = __fadd_rn(A11, __fmul_rn(hw, h2));
+          B00 = __fadd_rn(B00, __fmul_rn(__fmul_rn(__fmul_rn(drdA, drdA), hw), hw));
+          B01 = __fadd_rn(B01, __fmul_rn(__fmul_rn(drdA, hw), hw));
+          B11 = __fadd_rn(B11, __fmul_rn(hw, hw));
+          wJI2 = __fadd_rn(wJI2, __fmul_rn(__fmul_rn(hw, hw), __fadd_rn(__fmul_rn(h1, h1), __fmul_rn(h2, h2))));
+          done = idx + 1;
+        }
+      }
+    }
+  }
+  // geometric part of J is written in any case (:161-171)
+  float4* R4 = reinterpret_cast<float4*>(R_);
+  if (done == 8) {
+    r[O_JIDX2] = J00; r[O_JIDX2 + 1] = J10; r[O_JIDX2 + 2] = J11;
+    r[O_JABJIDX] = A00; r[O_JABJIDX + 1] = A01; r[O_JABJIDX + 2] = A10; r[O_JABJIDX + 3] = A11;
+    r[O_JAB2] = B00; r[O_JAB2 + 1] = B01; r[O_JAB2 + 2] = B11;
+#pragma unroll
+    for (int q = 0; q < 18; q++) R4[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    A.energyOutlier[i] = energyLeft;
+    uint8_t st = 0;
+    if (energyLeft > frameEnergyTH || wJI2 < 2.f) { energyLeft = frameEnergyTH; st = 2; }
+    A.newState[i] = st;
+    A.energy[i] = energyLeft;
+  } else {
+    // left the image (or hit a non-finite pixel) at pattern pixel `done`: the reference has overwritten J's geometric
+    // part and the per-pixel entries of the pixels before it, nothing else
+#pragma unroll
+    for (int k = O_JPDXI; k < O_JIDX; k++) R_[k] = r[k];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k < done) {
+        R_[O_RES + k] = r[O_RES + k];
+        R_[O_JIDX + k] = r[O_JIDX + k];
+        R_[O_JIDX + 8 + k] = r[O_JIDX + 8 + k];
+        R_[O_JAB + k] = r[O_JAB + k];
+        R_[O_JAB + 8 + k] = r[O_JAB + 8 + k];
+      }
+    A.newState[i] = 1;
+    A.energy[i] = A.energyIn[i];
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -629,6 +846,9 @@ int nalo_ba_destroy(nalo_ba* ba) {
   cudaFree(ba->d_deltaF); cudaFree(ba->d_priorF); cudaFree(ba->d_adHT); cudaFree(ba->d_cDelta); cudaFree(ba->d_ppA); cudaFree(ba->d_ppL);
   cudaFree(ba->d_ppSC); cudaFree(ba->d_ptHost); cudaFree(ba->d_ptOrder); cudaFree(ba->d_items); cudaFree(ba->d_partials); cudaFree(ba->d_out);
   cudaFree(ba->d_counter); cudaFree(ba->d_itemRange);
+  cudaFree(ba->d_linPt4); cudaFree(ba->d_linColor); cudaFree(ba->d_linWeights); cudaFree(ba->d_linEnergyIn); cudaFree(ba->d_linPairs);
+  cudaFree(ba->d_linPack); cudaFree(ba->d_linPoint); cudaFree(ba->d_linStateIn); cudaFree(ba->d_linState); cudaFree(ba->d_linEnergy);
+  cudaFree(ba->d_linEnergyOut); cudaFree(ba->d_linCenter); cudaFree(ba->d_linProj);
   delete ba;
   return NALO_OK;
 }
@@ -841,6 +1061,82 @@ int nalo_ba_accumulate_sc(nalo_ba* ba, int shiftPriorToZero, int useL, double* a
   if (perPoint_out)
     for (int p = 0; p < ba->nPts; p++)
       for (int i = 0; i < 3; i++) perPoint_out[(size_t)p * 3 + i] = sc4[(size_t)p * 4 + i];
+  return NALO_OK;
+}
+
+int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, float* energy, float* energy_with_outlier, float* center3,
+                      float* projected16, float* rec_out) {
+  if (!ba || !in) return NALO_E_ARG;
+  nalo_ctx* ctx = ba->ctx;
+  const int n = in->n_res, nf = in->nf;
+  if (n < 0 || n > ba->maxRes || nf < 1 || nf > NALO_BA_MAX_FRAMES) return nalo_fail(ctx, NALO_E_ARG, "nalo_ba_linearize: n_res=%d nf=%d out of range", n, nf);
+  if (!in->pt4 || !in->color || !in->weights || !in->pack || !in->point || !in->pairs) return NALO_E_ARG;
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (!ba->linAlloc) {
+    const size_t m = (size_t)ba->maxRes;
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linPt4, sizeof(float) * 4 * m));
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linColor, sizeof(float) * 8 * m));
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linWeights, sizeof(float) * 8 * m));
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linEnergyIn, sizeof(float) * m));
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linPairs, sizeof(float) * 32 * NALO_BA_MAX_FRAMES * NALO_BA_MAX_FRAMES));
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linPack, sizeof(uint32_t) * m));
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linPoint, sizeof(int) * m));
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linStateIn, m));
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linState, m));
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linEnergy, sizeof(float) * m));
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linEnergyOut, sizeof(float) * m));
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linCenter, sizeof(float) * 3 * m));
+    NALO_CUDA(ctx, cudaMalloc(&ba->d_linProj, sizeof(float) * 16 * m));
+    ba->linAlloc = true;
+  }
+  LinArgs A;
+  memset(&A, 0, sizeof(A));
+  // frame slots named by the precalc table -> device pyramids
+  const int* pairsI = reinterpret_cast<const int*>(in->pairs);
+  for (int b = 0; b < nf * nf; b++) {
+    const int slot = pairsI[(size_t)b * 32 + 28];
+    if (slot < 0 || slot >= ctx->maxFrames || slot >= NALO_BA_MAX_FRAMES)
+      return nalo_fail(ctx, NALO_E_ARG, "nalo_ba_linearize: pair %d names frame slot %d (must be < %d and < max_frames)", b, slot, NALO_BA_MAX_FRAMES);
+    if ((b % nf) != (b / nf) && !ctx->frames[slot].valid) return nalo_fail(ctx, NALO_E_STATE, "nalo_ba_linearize: frame slot %d has no pyramid", slot);
+    A.frames[slot] = ctx->frames[slot].pix;
+  }
+  if (n > 0) {
+    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPt4, in->pt4, sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linColor, in->color, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linWeights, in->weights, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPack, in->pack, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPoint, in->point, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (in->state_in) NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linStateIn, in->state_in, (size_t)n, cudaMemcpyHostToDevice, st));
+    else NALO_CUDA(ctx, cudaMemsetAsync(ba->d_linStateIn, 0, (size_t)n, st));
+    if (in->energy_in) NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linEnergyIn, in->energy_in, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+    else NALO_CUDA(ctx, cudaMemsetAsync(ba->d_linEnergyIn, 0, sizeof(float) * (size_t)n, st));
+  }
+  NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPairs, in->pairs, sizeof(float) * 32 * nf * nf, cudaMemcpyHostToDevice, st));
+  if (in->rec_init && n > 0) NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_rec, in->rec_init, sizeof(float) * REC * (size_t)n, cudaMemcpyHostToDevice, st));
+  A.n = n; A.nf = nf; A.w = ctx->w0; A.h = ctx->h0;
+  A.fx = in->fx; A.fy = in->fy; A.cx = in->cx; A.cy = in->cy;
+  A.huberTH = ctx->params.huberTH; A.outlierTHSum = in->outlierTHSumComponent;
+  A.modeA = ctx->params.affineOptModeA; A.modeB = ctx->params.affineOptModeB;
+  A.pt4 = reinterpret_cast<const float4*>(ba->d_linPt4);
+  A.color = reinterpret_cast<const float4*>(ba->d_linColor);
+  A.weights = reinterpret_cast<const float4*>(ba->d_linWeights);
+  A.pack = ba->d_linPack; A.point = ba->d_linPoint; A.stateIn = ba->d_linStateIn; A.energyIn = ba->d_linEnergyIn; A.pairs = ba->d_linPairs;
+  A.rec = ba->d_rec; A.newState = ba->d_linState; A.energy = ba->d_linEnergy; A.energyOutlier = ba->d_linEnergyOut; A.center = ba->d_linCenter;
+  A.projected = projected16 ? ba->d_linProj : nullptr;
+  if (n > 0) {
+    linearize_kernel<<<(n + 127) / 128, 128, 0, st>>>(A);
+    NALO_CHECK_LAUNCH(ctx);
+    if (new_state) NALO_CUDA(ctx, cudaMemcpyAsync(new_state, ba->d_linState, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (energy) NALO_CUDA(ctx, cudaMemcpyAsync(energy, ba->d_linEnergy, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (energy_with_outlier) NALO_CUDA(ctx, cudaMemcpyAsync(energy_with_outlier, ba->d_linEnergyOut, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (center3) NALO_CUDA(ctx, cudaMemcpyAsync(center3, ba->d_linCenter, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (projected16) NALO_CUDA(ctx, cudaMemcpyAsync(projected16, ba->d_linProj, sizeof(float) * 16 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (rec_out) NALO_CUDA(ctx, cudaMemcpyAsync(rec_out, ba->d_rec, sizeof(float) * REC * (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  NALO_CUDA(ctx, cudaStreamSynchronize(st));
+  // the records changed under the accumulators: per-point sums, JpJdF have to be recomputed
+  ba->haveA = ba->haveL = ba->haveJpJd = ba->haveJpJdDev = false;
   return NALO_OK;
 }
 
