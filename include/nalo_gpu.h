@@ -222,6 +222,7 @@ int nalo_ba_accumulate_sc(nalo_ba* ba, int shiftPriorToZero, int useL, double* a
  *   pairs [nf*nf][32] FrameFramePrecalc of bucket host + target*nf (HessianBlocks.cpp:192-222), floats:
  *           0..8 PRE_RTll_0 (row-major) | 9..11 PRE_tTll_0 | 12..20 PRE_KRKiTll | 21..23 PRE_KtTll | 24..25 PRE_aff_mode |
  *           26 PRE_b0_mode | 27 max(host,target frameEnergyTH) | 28 (int32) context frame slot of the TARGET pyramid
+ *   color, weights, pack, point are static per window: pass NULL for all four to reuse what the previous call uploaded.
  *   rec_init (nullable) [n][76] initial records (what OOB residuals keep); default: the handle's current records.
  * huberTH / affineOptModeA,B come from the context's NaloParams. Outputs (nullable): new_state [n] (state_NewState),
  * energy [n] (state_NewEnergy, resp. unchanged state_energy), energy_with_outlier [n], center3 [n][3]

@@ -482,7 +482,7 @@ class BA:
         self.ctx._ck(self.L.nalo_ba_take_data(self.h_, _ptr(out)))
         return out[: self.prob["n_res"]]
 
-    def linearize(self, prob, slots, rec_init=None, want_proj=True, want_rec=True, outlierTHSumComponent=2500.0):
+    def linearize(self, prob, slots, rec_init=None, want_proj=True, want_rec=True, outlierTHSumComponent=2500.0, reuse_static=False, want_center=True):
         """nalo_ba_linearize on a synth.make_lin_problem dict; slots[k] = context frame slot holding frame k's pyramid."""
         n, nf = prob["n_res"], prob["nf"]
         pairs = prob["pairs"].copy()
@@ -491,6 +491,8 @@ class BA:
         I.n_res, I.nf = n, nf
         keep = [np.ascontiguousarray(prob[k]) for k in ("pt4", "color", "weights", "pack", "point", "state_in", "energy_in")] + [pairs]
         I.pt4, I.color, I.weights, I.pack, I.point, I.state_in, I.energy_in, I.pairs = [a.ctypes.data for a in keep]
+        if reuse_static:
+            I.color = I.weights = I.pack = I.point = None
         ri = None if rec_init is None else np.ascontiguousarray(rec_init, dtype=_f32)
         I.rec_init = None if ri is None else ri.ctypes.data
         I.fx, I.fy, I.cx, I.cy = prob["K"]
@@ -498,11 +500,11 @@ class BA:
         st = np.zeros(max(n, 1), dtype=np.uint8)
         en = np.zeros(max(n, 1), dtype=_f32)
         eno = np.zeros(max(n, 1), dtype=_f32)
-        ce = np.zeros((max(n, 1), 3), dtype=_f32)
+        ce = np.zeros((max(n, 1), 3), dtype=_f32) if want_center else None
         pr = np.zeros((max(n, 1), 16), dtype=_f32) if want_proj else None
         rec = np.zeros((max(n, 1), BA_RECORD_WORDS), dtype=_f32) if want_rec else None
-        self.ctx._ck(self.L.nalo_ba_linearize(self.h_, C.byref(I), _ptr(st), _ptr(en), _ptr(eno), _ptr(ce), _ptr(pr), _ptr(rec)))
-        return dict(state=st[:n], energy=en[:n], energy_outlier=eno[:n], center=ce[:n], proj=None if pr is None else pr[:n],
+        self.ctx._ck(self.L.nalo_ba_linearize(self.h_, C.byref(I), _ptr(st), _ptr(en), _ptr(eno) if want_center else None, _ptr(ce), _ptr(pr), _ptr(rec)))
+        return dict(state=st[:n], energy=en[:n], energy_outlier=eno[:n], center=None if ce is None else ce[:n], proj=None if pr is None else pr[:n],
                     rec=None if rec is None else rec[:n])
 
     def accumulate_sc(self, shiftPriorToZero=True, useL=False):

@@ -48,6 +48,7 @@ struct nalo_ba {
   double* h_out = nullptr;       // pinned staging of the small fp64 results
   // f1 (nalo_ba_linearize) inputs/outputs, allocated on first use
   bool linAlloc = false;
+  int linN = -1;                 // n_res of the static inputs (color, weights, pack, point) resident on the device
   float *d_linPt4 = nullptr, *d_linColor = nullptr, *d_linWeights = nullptr, *d_linEnergyIn = nullptr, *d_linPairs = nullptr;
   uint32_t* d_linPack = nullptr;
   int* d_linPoint = nullptr;
@@ -1070,7 +1071,10 @@ int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, f
   nalo_ctx* ctx = ba->ctx;
   const int n = in->n_res, nf = in->nf;
   if (n < 0 || n > ba->maxRes || nf < 1 || nf > NALO_BA_MAX_FRAMES) return nalo_fail(ctx, NALO_E_ARG, "nalo_ba_linearize: n_res=%d nf=%d out of range", n, nf);
-  if (!in->pt4 || !in->color || !in->weights || !in->pack || !in->point || !in->pairs) return NALO_E_ARG;
+  if (!in->pt4 || !in->pairs) return NALO_E_ARG;
+  // color / weights / pack / point are static per window: NULL = reuse what the previous call uploaded (same n_res)
+  const bool reuse = !in->color || !in->weights || !in->pack || !in->point;
+  if (reuse && (!ba->linAlloc || ba->linN != n)) return nalo_fail(ctx, NALO_E_STATE, "nalo_ba_linearize: static inputs omitted but none of matching size are resident");
   NALO_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   if (!ba->linAlloc) {
@@ -1103,10 +1107,13 @@ int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, f
   }
   if (n > 0) {
     NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPt4, in->pt4, sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice, st));
-    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linColor, in->color, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, st));
-    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linWeights, in->weights, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, st));
-    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPack, in->pack, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPoint, in->point, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (!reuse) {
+      NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linColor, in->color, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+      NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linWeights, in->weights, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+      NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPack, in->pack, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+      NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPoint, in->point, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+      ba->linN = n;
+    }
     if (in->state_in) NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linStateIn, in->state_in, (size_t)n, cudaMemcpyHostToDevice, st));
     else NALO_CUDA(ctx, cudaMemsetAsync(ba->d_linStateIn, 0, (size_t)n, st));
     if (in->energy_in) NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linEnergyIn, in->energy_in, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));

@@ -341,9 +341,9 @@ def make_lin_problem(scene: Scene, nf=4, pts_per_frame=500, seed=DEFAULT_SEED, b
             P[26] = affs[hst][1]
             P[27] = 8 * 12 * 12.0  # frameEnergyTH ~ patternNum * setting_outlierTH of a fresh frame (FullSystem.cpp setNewFrameEnergyTH)
             P.view(np.int32)[28] = tgt
-    pt4, color, weights, pack, point = [], [], [], [], []
     pt_id = 0
     per_bucket = {}
+    pat = LIN_PATTERN.astype(np.float64)
     for hst in range(nf):
         x0 = rng.uniform(8, w - 9, pts_per_frame)
         y0 = rng.uniform(8, h - 9, pts_per_frame)
@@ -360,26 +360,28 @@ def make_lin_problem(scene: Scene, nf=4, pts_per_frame=500, seed=DEFAULT_SEED, b
         bad = rng.random(pts_per_frame) < bad_depth_fraction
         idh_used = np.where(bad, idh * rng.uniform(1.5, 3.0, pts_per_frame), idh)
         inside = (uh > 3) & (uh < w - 4) & (vh > 3) & (vh < h - 4)
-        gyh, gxh = np.gradient(imgs[hst].astype(np.float64))
-        for k in range(pts_per_frame):
-            if not inside[k]:
+        uh, vh, idh_used = uh[inside], vh[inside], idh_used[inside]
+        m = len(uh)
+        img64 = imgs[hst].astype(np.float64)
+        gyh, gxh = np.gradient(img64)
+        px, py = uh[:, None] + pat[None, :, 0], vh[:, None] + pat[None, :, 1]
+        cols = _bilinear(img64, px, py)
+        g2 = _bilinear(gxh, px, py) ** 2 + _bilinear(gyh, px, py) ** 2
+        wts = np.sqrt(2500.0 / (2500.0 + g2))
+        ids = np.arange(pt_id, pt_id + m)
+        pt_id += m
+        for tgt in range(nf):
+            if tgt == hst:
                 continue
-            cols = np.array([_bilinear(imgs[hst].astype(np.float64), uh[k] + d[0], vh[k] + d[1]) for d in LIN_PATTERN])
-            g2 = np.array([_bilinear(gxh, uh[k] + d[0], vh[k] + d[1]) ** 2 + _bilinear(gyh, uh[k] + d[0], vh[k] + d[1]) ** 2 for d in LIN_PATTERN])
-            wts = np.sqrt(2500.0 / (2500.0 + g2))
-            for tgt in range(nf):
-                if tgt == hst:
-                    continue
-                per_bucket.setdefault(hst + tgt * nf, []).append(
-                    (uh[k], vh[k], idh_used[k] * (1 + rng.normal(0, fej_noise)), idh_used[k], cols, wts, hst | (tgt << 8) | (1 << 16), pt_id))
-            pt_id += 1
-    for b in sorted(per_bucket):
-        for (u, v, idz, idc, cols, wts, pk, pid) in per_bucket[b]:
-            pt4.append((u, v, idz, idc))
-            color.append(cols)
-            weights.append(wts)
-            pack.append(pk)
-            point.append(pid)
+            idz = idh_used * (1 + rng.normal(0, fej_noise, m)) if fej_noise > 0 else idh_used.copy()
+            per_bucket[hst + tgt * nf] = (np.stack([uh, vh, idz, idh_used], 1), cols, wts,
+                                          np.full(m, hst | (tgt << 8) | (1 << 16), dtype=np.uint32), ids)
+    keys = sorted(per_bucket)
+    pt4 = np.concatenate([per_bucket[k][0] for k in keys]) if keys else np.zeros((0, 4))
+    color = np.concatenate([per_bucket[k][1] for k in keys]) if keys else np.zeros((0, 8))
+    weights = np.concatenate([per_bucket[k][2] for k in keys]) if keys else np.zeros((0, 8))
+    pack = np.concatenate([per_bucket[k][3] for k in keys]) if keys else np.zeros(0, dtype=np.uint32)
+    point = np.concatenate([per_bucket[k][4] for k in keys]) if keys else np.zeros(0, dtype=np.int64)
     n = len(pack)
     return dict(nf=nf, n_res=n, n_pts=pt_id, w=w, h=h, K=(fx, fy, cx, cy), images=imgs, pairs=pairs,
                 pt4=np.array(pt4, dtype=np.float32).reshape(n, 4), color=np.array(color, dtype=np.float32).reshape(n, 8),

@@ -80,7 +80,7 @@ def cpu_time(fn, budget_s=3.0, min_reps=3):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--rows", default="a1,select,ref,eval,track,multi,batch,ba")
+    ap.add_argument("--rows", default="a1,select,ref,eval,track,multi,batch,ba,lin")
     ap.add_argument("--batch-pairs", type=int, default=296)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "suite.json"))
@@ -372,6 +372,29 @@ def main():
                 c = cpu_time(lambda: O.ba_sc(prob, J, ppA, ppL, True, nThreads=6, fast=True), budget_s=2.0)[0]
             add(f"a10 AccumulatedSCHessian nres={nres}", d, wl, 40 * nres + 32 * npts, nres, "residual", c, 6)
             ba.close()
+
+    # ------------------------------------------------------------------ f1 linearize
+    if "lin" in rows_wanted:
+        ctxl = capi.Context(W, H, L, device=0, max_frames=7)
+        Tl = Timer(ctxl)
+        Pl = synth.make_lin_problem(sc, nf=7, pts_per_frame=28571, seed=2)
+        dIl = []
+        for k, img in enumerate(Pl["images"]):
+            dd, _ = ctxl.make_images(k, img, want_host=True)
+            dIl.append(dd)
+        nres = Pl["n_res"]
+        bal = capi.BA(ctxl, nres + 16, Pl["n_pts"] + 16)
+        bal.linearize(Pl, list(range(7)), want_proj=False, want_rec=False)  # uploads the static per-residual inputs
+        d, wl, _ = Tl.run(lambda i: bal.linearize(Pl, list(range(7)), want_proj=False, want_rec=False, reuse_static=True, want_center=False), reps=8)
+        c = None
+        if cpu:
+            dIs_o = [O.make_images(img, W, H, L, fast=True)[0] for img in Pl["images"]]
+            c = cpu_time(lambda: O.linearize(Pl, dIs_o), budget_s=3.0)[0]
+        # algorithmic bytes: 16 (pt4) + 64 (color, weights) + 8 (pack, point) + 5 in + 8*4*16 texels (L2-resident images) ; out 304 + 21
+        add(f"f1 linearize nres={nres} (7 keyframes)", d, wl, (16 + 64 + 8 + 5 + 304 + 21) * nres, nres, "residual", c, 1,
+            "per iteration: H2D 21 B/res (pt4, state, energy) + D2H 5 B/res (new state, energy), pageable, static point data resident; records stay on the device")
+        bal.close()
+        ctxl.close()
 
     doc = dict(peak_hbm_gbs=peak, peak_source="MEASURED_PEAKS.json" if peaks else "fallback", gpu=torch.cuda.get_device_name(0),
                host_cores=os.cpu_count(), pc_n=pc_n, rows=rows)
