@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -157,9 +158,12 @@ class Context:
         if rc != NALO_OK:
             raise NaloError(rc, self.L.nalo_last_error(None).decode())
         self.h_ = h_
+        self._children = weakref.WeakSet()  # Batch / BA handles: they hold pointers into the context and must go first
 
     def close(self):
         if getattr(self, "h_", None):
+            for c in list(getattr(self, "_children", ())):
+                c.close()
             self.L.nalo_destroy(self.h_)
             self.h_ = None
 
@@ -401,10 +405,12 @@ class Batch:
         h_ = _P()
         ctx._ck(self.L.nalo_batch_create(ctx.h_, C.c_int(capacity), C.byref(h_)))
         self.h_ = h_
+        ctx._children.add(self)
 
     def close(self):
         if getattr(self, "h_", None):
-            self.L.nalo_batch_destroy(self.h_)
+            if getattr(self.ctx, "h_", None):  # (a closed context has already released its children)
+                self.L.nalo_batch_destroy(self.h_)
             self.h_ = None
 
     def __del__(self):
@@ -447,10 +453,12 @@ class BA:
         ctx._ck(self.L.nalo_ba_create(ctx.h_, C.c_int(max_res), C.c_int(max_pts), C.byref(h_)))
         self.h_ = h_
         self.prob = None
+        ctx._children.add(self)
 
     def close(self):
         if getattr(self, "h_", None):
-            self.L.nalo_ba_destroy(self.h_)
+            if getattr(self.ctx, "h_", None):
+                self.L.nalo_ba_destroy(self.h_)
             self.h_ = None
 
     def __del__(self):

@@ -29,3 +29,13 @@ for rep in range(2):
     ctx._ck(ctx.L.nalo_ba_take_data(ba.h_, None))
     ctx._ck(ctx.L.nalo_ba_accumulate_sc(ba.h_, C.c_int(1), C.c_int(1), vp(accD), vp(accE), vp(accEB), vp(accH), vp(accb), None))
 print('ba', prob['n_res'], n_.value, float(np.abs(accD).sum()))
+# f1 linearize (7 keyframes) on the device
+Pl = synth.make_lin_problem(sc, nf=7, pts_per_frame=max(ppf // 4, 50), seed=2)
+ctxl = capi.Context(W, H, 5, 0, 7)
+for k, img in enumerate(Pl['images']):
+    ctxl.make_images(k, img)
+bal = capi.BA(ctxl, Pl['n_res'] + 16, Pl['n_pts'] + 16)
+for rep in range(2):
+    rl = bal.linearize(Pl, list(range(7)), want_proj=False, want_rec=False, reuse_static=rep > 0, want_center=False)
+print('lin', Pl['n_res'], np.bincount(rl['state'], minlength=3))
+bal.close(); ctxl.close(); ba.close(); ctx.close()
