@@ -210,6 +210,11 @@ int nalo_ba_take_data(nalo_ba* ba, float* JpJdF_out /* nullable [n_res][8] */);
 int nalo_ba_accumulate_sc(nalo_ba* ba, int shiftPriorToZero, int useL, double* accD, double* accE, double* accEB, double* accHcc,
                           double* accbc, float* perPoint_out /* [n_pts][3] HdiF,bdSumF,idepth_hessian */);
 
+/* f2 (part): EnergyFunctional::resubstituteFPt (OptimizationBackend/EnergyFunctional.cpp:291-317) on the resident data of
+ * the last accumulate_top / take_data / accumulate_sc calls: step_out[p] = -(bdSumF - xc.Hcd - sum_r xAd[host*nf+target].JpJdF_r)
+ * * HdiF (0 for points without active residuals). xAd: [nf*nf][8], indexed hostIDX*nf + targetIDX as in the reference. */
+int nalo_ba_resubstitute(nalo_ba* ba, const float xc4[4], const float* xAd, int useL, float* step_out);
+
 /* ---- f1 (SURVEY.md §8 f, "next"): PointFrameResidual::linearize (FullSystem/Residuals.cpp:78-274) -----------------
  * Produces the residual records ON THE DEVICE, in place of the handle's records (same order as uploaded: bucket-sorted,
  * n_res must equal the uploaded problem's n_res for the accumulators that follow), so a BA iteration uploads 88 B per

@@ -515,6 +515,14 @@ class BA:
         return dict(state=st[:n], energy=en[:n], energy_outlier=eno[:n], center=None if ce is None else ce[:n], proj=None if pr is None else pr[:n],
                     rec=None if rec is None else rec[:n])
 
+    def resubstitute(self, xc, xAd, useL=False):
+        nP = self.prob["n_pts"]
+        xc = np.ascontiguousarray(xc, dtype=_f32)
+        xAd = np.ascontiguousarray(xAd, dtype=_f32)
+        step = np.zeros(max(nP, 1), dtype=_f32)
+        self.ctx._ck(self.L.nalo_ba_resubstitute(self.h_, _ptr(xc), _ptr(xAd), C.c_int(1 if useL else 0), _ptr(step)))
+        return step[:nP]
+
     def accumulate_sc(self, shiftPriorToZero=True, useL=False):
         nf, nP = self.prob["nf"], self.prob["n_pts"]
         accD = np.zeros((nf**3, 8, 8))

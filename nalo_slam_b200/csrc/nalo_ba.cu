@@ -64,6 +64,7 @@ struct nalo_ba {
   std::vector<int> hostBegin;    // [nf+1] into ptOrder
   bool haveA = false, haveL = false, haveJpJd = false;
   bool haveJpJdDev = false;      // d_jpjd is current for the uploaded records
+  bool haveSC = false;           // d_ppSC (HdiF, bdSumF) is current
   size_t partialFloats = 0, outDoubles = 0;
   int maxItems = 0;
 };
@@ -578,6 +579,41 @@ __global__ void sc_finalize_kernel(const float* __restrict__ partials, const int
   }
 }
 
+// f2 (part): EnergyFunctional::resubstituteFPt (OptimizationBackend/EnergyFunctional.cpp:291-317) — per-point
+// back-substitution with everything it needs already resident (JpJdF, the per-point sums of the accumulations, HdiF /
+// bdSumF of the Schur prologue). One thread per point, residuals in residualsAll order like the reference.
+__global__ void resubstitute_kernel(const float* __restrict__ rec, const float* __restrict__ JpJdF, const int* __restrict__ ptBegin,
+                                    const int* __restrict__ ptRes, const float* __restrict__ ppA, const float* __restrict__ ppL,
+                                    const float* __restrict__ ppSC, const float* __restrict__ xc, const float* __restrict__ xAd, int nf, int nPts,
+                                    float* __restrict__ step) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nPts) return;
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(ppSC) + p);  // HdiF, bdSum, H, ngood
+  if (sc.w == 0.f) { step[p] = 0.f; return; }
+  float b = sc.y;
+  float h[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) h[i] = __fadd_rn(ppA[(size_t)p * 6 + 2 + i], ppL ? ppL[(size_t)p * 6 + 2 + i] : 0.f);
+  b = __fsub_rn(b, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(xc[0], h[0]), __fmul_rn(xc[1], h[1])), __fmul_rn(xc[2], h[2])), __fmul_rn(xc[3], h[3])));
+  for (int k = ptBegin[p]; k < ptBegin[p + 1]; k++) {
+    const int ri = ptRes[k];
+    const uint32_t pk = __float_as_uint(__ldg(rec + (size_t)ri * REC + O_PACK));
+    if (!((pk >> 16) & 1)) continue;
+    const float* x = xAd + (size_t)((pk & 0xFF) * nf + ((pk >> 8) & 0xFF)) * 8;
+    const float4 j0 = __ldg(reinterpret_cast<const float4*>(JpJdF + (size_t)ri * 8)), j1 = __ldg(reinterpret_cast<const float4*>(JpJdF + (size_t)ri * 8) + 1);
+    float d = __fmul_rn(x[0], j0.x);
+    d = __fadd_rn(d, __fmul_rn(x[1], j0.y));
+    d = __fadd_rn(d, __fmul_rn(x[2], j0.z));
+    d = __fadd_rn(d, __fmul_rn(x[3], j0.w));
+    d = __fadd_rn(d, __fmul_rn(x[4], j1.x));
+    d = __fadd_rn(d, __fmul_rn(x[5], j1.y));
+    d = __fadd_rn(d, __fmul_rn(x[6], j1.z));
+    d = __fadd_rn(d, __fmul_rn(x[7], j1.w));
+    b = __fsub_rn(b, d);
+  }
+  step[p] = __fmul_rn(-b, sc.x);
+}
+
 // ---- f1: PointFrameResidual::linearize (src/FullSystem/Residuals.cpp:78-274) ------------------------------------------
 // One thread per residual, same operation order as the CPU oracle (un-contracted fp32), so records, states and energies
 // are bit-identical to it. Inputs are flat per-residual arrays (bucket-sorted like the records); the target image is the
@@ -862,7 +898,7 @@ int nalo_ba_upload(nalo_ba* ba, const NaloBAProblem* p) {
   if (!p->rec || !p->bucket_begin || !p->pt_begin || !p->pt_res || !p->adHTdeltaF || !p->cDeltaF) return NALO_E_ARG;
   NALO_CUDA(ctx, cudaSetDevice(ctx->device));
   ba->nf = p->nf; ba->nPts = p->n_pts; ba->nRes = p->n_res;
-  ba->haveA = ba->haveL = ba->haveJpJd = ba->haveJpJdDev = false;
+  ba->haveA = ba->haveL = ba->haveJpJd = ba->haveJpJdDev = ba->haveSC = false;
   cudaStream_t st = ctx->stream;
   const int nb = p->nf * p->nf;
   NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_rec, p->rec, sizeof(float) * REC * (size_t)p->n_res, cudaMemcpyHostToDevice, st));
@@ -1034,6 +1070,7 @@ int nalo_ba_accumulate_sc(nalo_ba* ba, int shiftPriorToZero, int useL, double* a
     sc_finalize_kernel<<<dim3(nf, (nU * 36 + 255) / 256), 256, 0, st>>>(ba->d_partials, ba->d_itemRange + 80, nf, dD, dE, dEB, dHost);
     NALO_CHECK_LAUNCH(ctx);
   }
+  ba->haveSC = true;
   // one D2H of the whole fp64 result block into pinned staging, then plain memcpy to the caller's arrays
   NALO_CUDA(ctx, cudaMemcpyAsync(ba->h_out, ba->d_out, sizeof(double) * totalD, cudaMemcpyDeviceToHost, st));
   std::vector<float> sc4;
@@ -1143,7 +1180,30 @@ int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, f
   }
   NALO_CUDA(ctx, cudaStreamSynchronize(st));
   // the records changed under the accumulators: per-point sums, JpJdF have to be recomputed
-  ba->haveA = ba->haveL = ba->haveJpJd = ba->haveJpJdDev = false;
+  ba->haveA = ba->haveL = ba->haveJpJd = ba->haveJpJdDev = ba->haveSC = false;
+  return NALO_OK;
+}
+
+int nalo_ba_resubstitute(nalo_ba* ba, const float xc4[4], const float* xAd, int useL, float* step_out) {
+  if (!ba || !xc4 || !xAd || !step_out) return NALO_E_ARG;
+  nalo_ctx* ctx = ba->ctx;
+  if (ba->nf == 0 || !ba->haveA || !ba->haveJpJd || !ba->haveSC)
+    return nalo_fail(ctx, NALO_E_STATE, "nalo_ba_resubstitute needs nalo_ba_accumulate_top(0), nalo_ba_take_data and nalo_ba_accumulate_sc first");
+  if (useL && !ba->haveL) return nalo_fail(ctx, NALO_E_STATE, "useL without a mode 1/2 accumulation");
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int nf = ba->nf;
+  float* d_x = reinterpret_cast<float*>(ba->d_out);  // the fp64 result staging is free between calls: 4 + nf*nf*8 floats
+  NALO_CUDA(ctx, cudaMemcpyAsync(d_x, xc4, sizeof(float) * 4, cudaMemcpyHostToDevice, st));
+  NALO_CUDA(ctx, cudaMemcpyAsync(d_x + 4, xAd, sizeof(float) * 8 * nf * nf, cudaMemcpyHostToDevice, st));
+  if (ba->nPts > 0) {
+    float* d_step = ba->d_contrib;  // per-residual scratch of the top pass, large enough for one float per point
+    resubstitute_kernel<<<(ba->nPts + 255) / 256, 256, 0, st>>>(ba->d_rec, ba->d_jpjd, ba->d_ptBegin, ba->d_ptRes, ba->d_ppA, useL ? ba->d_ppL : nullptr,
+                                                                 ba->d_ppSC, d_x, d_x + 4, nf, ba->nPts, d_step);
+    NALO_CHECK_LAUNCH(ctx);
+    NALO_CUDA(ctx, cudaMemcpyAsync(step_out, d_step, sizeof(float) * (size_t)ba->nPts, cudaMemcpyDeviceToHost, st));
+  }
+  NALO_CUDA(ctx, cudaStreamSynchronize(st));
   return NALO_OK;
 }
 

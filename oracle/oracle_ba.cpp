@@ -430,4 +430,33 @@ void oracle_ba_sc(int nThreads, int nf, int nPts, const float* rec, const float*
   }
 }
 
+// f2 (part): EnergyFunctional::resubstituteFPt (src/OptimizationBackend/EnergyFunctional.cpp:291-317): the per-point
+// back-substitution of the Schur complement. xAd is indexed hostIDX*nFrames + targetIDX (:311 — not the accumulators'
+// host + target*nFrames). perPointSC: [nPts][3] {HdiF, bdSumF, -} as written by oracle_ba_sc; Hcd = Hcd_accAF + Hcd_accLF.
+// Summation order fixed: 4-vector dot as ((x0 h0 + x1 h1) + x2 h2) + x3 h3, the 8-vector products left to right.
+void oracle_ba_resubstitute(int nf, int nPts, const float* rec, const float* JpJdF, const int* pt_begin, const int* pt_res,
+                            const float* HcdA, const float* HcdL, const float* perPointSC, const float* xc, const float* xAd, float* step) {
+  for (int p = 0; p < nPts; p++) {
+    int ngood = 0;
+    for (int k = pt_begin[p]; k < pt_begin[p + 1]; k++)
+      if ((reinterpret_cast<const uint32_t*>(rec)[(size_t)pt_res[k] * REC + O_PACK] >> 16) & 1) ngood++;
+    if (ngood == 0) { step[p] = 0.f; continue; }
+    float b = perPointSC[3 * (size_t)p + 1];
+    float h[4];
+    for (int i = 0; i < 4; i++) h[i] = HcdA[4 * (size_t)p + i] + (HcdL ? HcdL[4 * (size_t)p + i] : 0.f);
+    b -= ((xc[0] * h[0] + xc[1] * h[1]) + xc[2] * h[2]) + xc[3] * h[3];
+    for (int k = pt_begin[p]; k < pt_begin[p + 1]; k++) {
+      const int ri = pt_res[k];
+      const uint32_t pk = reinterpret_cast<const uint32_t*>(rec)[(size_t)ri * REC + O_PACK];
+      if (!((pk >> 16) & 1)) continue;
+      const float* x = xAd + (size_t)((pk & 0xFF) * nf + ((pk >> 8) & 0xFF)) * 8;
+      const float* j = JpJdF + (size_t)ri * 8;
+      float d = 0.f;
+      for (int i = 0; i < 8; i++) d += x[i] * j[i];
+      b -= d;
+    }
+    step[p] = -b * perPointSC[3 * (size_t)p];
+  }
+}
+
 }  // extern "C"

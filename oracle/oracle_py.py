@@ -408,3 +408,16 @@ def linearize(prob, dI_frames, rec_init=None, huberTH=9.0, outlierTHSumComponent
         _ptr(prob["state_in"]), _ptr(prob["energy_in"]), _ptr(rec), _ptr(state), _ptr(en), _ptr(eno), _ptr(center), _ptr(proj),
     )
     return dict(rec=rec, state=state, energy=en, energy_outlier=eno, center=center, proj=proj)
+
+
+def ba_resubstitute(prob, JpJdF, ppA, ppL, perPointSC, xc, xAd):
+    """EnergyFunctional::resubstituteFPt: per-point step = -(bdSumF - xc.Hcd - sum_r xAd[h*nf+t].JpJdF_r) * HdiF."""
+    nP = prob["n_pts"]
+    HcdA = np.ascontiguousarray(ppA[:, 2:6])
+    HcdL = None if ppL is None else np.ascontiguousarray(ppL[:, 2:6])
+    step = np.zeros(nP, dtype=_f32)
+    lib().oracle_ba_resubstitute(
+        C.c_int(prob["nf"]), C.c_int(nP), _ptr(prob["rec"]), _ptr(np.ascontiguousarray(JpJdF, dtype=_f32)), _ptr(prob["pt_begin"]), _ptr(prob["pt_res"]),
+        _ptr(HcdA), _ptr(HcdL), _ptr(np.ascontiguousarray(perPointSC, dtype=_f32)), _ptr(np.ascontiguousarray(xc, dtype=_f32)),
+        _ptr(np.ascontiguousarray(xAd, dtype=_f32)), _ptr(step))
+    return step

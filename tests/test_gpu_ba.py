@@ -70,6 +70,14 @@ def test_schur_complement(ba_ctx, oracle):
     for k in ("accE", "accEB", "accHcc", "accbc"):
         a, b = sg[k], so[k]
         assert np.all(np.abs(a - b) <= TOL * (np.abs(b) + 1e-3 * np.abs(b).max()) + 1e-30), k
+    # f2 (part): resubstituteFPt on the resident data
+    rng = np.random.default_rng(5)
+    xc = rng.normal(0, 1e-2, 4).astype(np.float32)
+    xAd = rng.normal(0, 1e-3, (nf * nf, 8)).astype(np.float32)
+    st_o = oracle.ba_resubstitute(prob, J_o, ppA_o, ppL_o, so["perPoint"], xc, xAd)
+    st_g = ba.resubstitute(xc, xAd, useL=True)
+    assert np.count_nonzero(st_o) > prob["n_pts"] // 2
+    assert np.all(np.abs(st_g - st_o) <= 2e-4 * (np.abs(st_o) + 1e-3 * np.abs(st_o).max()))
     ba.close()
 
 

@@ -120,3 +120,34 @@ def test_schur_matches_closed_form(oracle):
             accEB[ht] += hdi * bd * J[r1]
     for name, cf in (("accD", accD), ("accE", accE), ("accEB", accEB), ("accHcc", Hcc), ("accbc", bc)):
         assert np.allclose(out[name], cf, rtol=5e-4, atol=2e-5 * np.abs(cf).max()), name
+
+
+def test_resubstitute_closed_form(oracle):
+    """f2 (part) EnergyFunctional::resubstituteFPt (:291-317): step = -(bdSumF - xc.Hcd - sum_r xAd[h*nf+t].JpJdF_r) * HdiF,
+    recomputed in float64 with numpy."""
+    from nalo_slam_b200 import synth
+
+    prob = synth.make_ba_problem(nf=5, pts_per_frame=120, seed=8, lin_fraction=0.3)
+    nf, nP = prob["nf"], prob["n_pts"]
+    _, ppA, _ = oracle.ba_top(prob, mode=0)
+    _, ppL, _ = oracle.ba_top(prob, mode=1)
+    J = oracle.ba_take_data(prob)
+    sc = oracle.ba_sc(prob, J, ppA, ppL, shiftPriorToZero=True)
+    rng = np.random.default_rng(3)
+    xc = rng.normal(0, 1e-2, 4).astype(np.float32)
+    xAd = rng.normal(0, 1e-3, (nf * nf, 8)).astype(np.float32)
+    step = oracle.ba_resubstitute(prob, J, ppA, ppL, sc["perPoint"], xc, xAd)
+    pack = prob["rec"].view(np.uint32)[:, 73]
+    exp = np.zeros(nP)
+    for p in range(nP):
+        lst = prob["pt_res"][prob["pt_begin"][p] : prob["pt_begin"][p + 1]]
+        act = [r for r in lst if (pack[r] >> 16) & 1]
+        if not act:
+            continue
+        b = float(sc["perPoint"][p, 1]) - float(np.dot(xc.astype(np.float64), (ppA[p, 2:6].astype(np.float64) + ppL[p, 2:6])))
+        for r in act:
+            h, t = int(pack[r] & 0xFF), int((pack[r] >> 8) & 0xFF)
+            b -= float(np.dot(xAd[h * nf + t].astype(np.float64), J[r].astype(np.float64)))
+        exp[p] = -b * float(sc["perPoint"][p, 0])
+    assert np.count_nonzero(exp) > nP // 2
+    assert np.allclose(step, exp, rtol=1e-4, atol=1e-5 * np.abs(exp).max())
