@@ -65,6 +65,7 @@ typedef struct NaloTrackStats {
   int launches;         /* CUDA kernels launched by the call */
   int evals_per_level[NALO_TRACK_LEVELS]; /* evaluations per pyramid level (for the roofline's algorithmic bytes) */
   float kernel_ms;      /* device time of the tracking kernel (CUDA events on the context stream) */
+  float step_ms;        /* nalo_track_frame only: device time from before the pyramid kernel to the end of the tracking kernel */
 } NaloTrackStats;
 
 void nalo_default_params(NaloParams* p);
@@ -143,6 +144,13 @@ int nalo_calc_gs(nalo_ctx* ctx, int trk, int lvl, const double pose7[7], const d
 int nalo_track(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, double pose7_inout[7], double aff2_inout[2],
                int coarsestLvl, const double minResForAbort5[5], double lastRes5[5], double flow3[3], int* ok,
                NaloTrackStats* stats /* nullable */);
+
+/* The per-frame hot path of FullSystem::addActiveFrame in one call: makeImages of the new frame (FullSystem.cpp:1065) into
+ * `new_slot`, then trackNewestCoarse (:606). Exactly one of color_host / color_dev is given. The two launches are enqueued
+ * back to back (no host work in between); with nalo_set_profiling, stats->step_ms is the device time of the whole step. */
+int nalo_track_frame(nalo_ctx* ctx, int trk, int new_slot, const float* color_host, const float* color_dev, const float* B256,
+                     float exposure_new, double pose7_inout[7], double aff2_inout[2], int coarsestLvl, const double minResForAbort5[5],
+                     double lastRes5[5], double flow3[3], int* ok, NaloTrackStats* stats /* nullable */);
 
 /* ---- a11: FullSystem::trackNewCoarse (FullSystem.cpp:502-699) ------------------------------------------ */
 /* candidate list (:516-580) from camToWorld of sprelast, slast and the reference KF; returns count in *n_out (<=31) */

@@ -156,6 +156,21 @@ class CoarseTracker {
     newFrame = newFrameHessian;
     return ok != 0;
   }
+  // makeImages(color) of the new frame + trackNewestCoarse in one device submission (FullSystem::addActiveFrame's hot path,
+  // FullSystem.cpp:1065 + :606): the two launches go out back to back.
+  bool makeImagesAndTrack(FrameHessian* newFrameHessian, const float* color, const float* B256, SE3& lastToNew_out, AffLight& aff_g2l_out,
+                          int coarsestLvl, const Vec5& minResForAbort) {
+    double aff[2] = {aff_g2l_out.a, aff_g2l_out.b};
+    int ok = 0;
+    check(ctx.get(),
+          nalo_track_frame(ctx.get(), trk, newFrameHessian->slot, color, nullptr, B256, newFrameHessian->ab_exposure, lastToNew_out.data, aff,
+                           coarsestLvl, minResForAbort.data(), lastResiduals.data(), lastFlowIndicators.data(), &ok, &lastStats),
+          "nalo_track_frame");
+    aff_g2l_out.a = aff[0];
+    aff_g2l_out.b = aff[1];
+    newFrame = newFrameHessian;
+    return ok != 0;
+  }
   int pc_n(int lvl) const { int n = 0; nalo_get_ref_count(ctx.get(), trk, lvl, &n); return n; }
 
   Context& ctx;

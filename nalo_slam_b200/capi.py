@@ -43,11 +43,11 @@ class NaloParams(C.Structure):
 
 class NaloTrackStats(C.Structure):
     _fields_ = [("residuals", C.c_longlong), ("evals", C.c_int), ("iters", C.c_int), ("launches", C.c_int),
-                ("evals_per_level", C.c_int * 5), ("kernel_ms", C.c_float)]
+                ("evals_per_level", C.c_int * 5), ("kernel_ms", C.c_float), ("step_ms", C.c_float)]
 
     def as_dict(self):
         return dict(residuals=self.residuals, evals=self.evals, iters=self.iters, launches=self.launches,
-                    evals_per_level=list(self.evals_per_level), kernel_ms=float(self.kernel_ms))
+                    evals_per_level=list(self.evals_per_level), kernel_ms=float(self.kernel_ms), step_ms=float(self.step_ms))
 
 
 class NaloBAProblem(C.Structure):
@@ -330,6 +330,23 @@ class Context:
         ok = C.c_int(0)
         st = NaloTrackStats()
         self._ck(self.L.nalo_track(self.h_, C.c_int(trk), C.c_int(new_slot), C.c_float(exposure), _ptr(pose), _ptr(aff), C.c_int(coarsestLvl), _ptr(mr), _ptr(lr), _ptr(fl), C.byref(ok), C.byref(st)))
+        return bool(ok.value), pose, aff, lr, fl, st.as_dict()
+
+    def track_frame(self, trk, new_slot, pose7, aff2, color_host=None, color_dev_ptr=None, coarsestLvl=None, minRes=None, exposure=1.0, B256=None):
+        """nalo_track_frame: makeImages + trackNewestCoarse in one call (color_host: pinned/pageable float32 image, or a device pointer)."""
+        pose = np.array(pose7, dtype=np.float64)
+        aff = np.array(aff2, dtype=np.float64)
+        if coarsestLvl is None:
+            coarsestLvl = min(self.levels, 5) - 1
+        mr = np.full(5, np.nan) if minRes is None else np.ascontiguousarray(minRes, dtype=np.float64)
+        lr = np.zeros(5)
+        fl = np.zeros(3)
+        ok = C.c_int(0)
+        st = NaloTrackStats()
+        ch = None if color_host is None else np.ascontiguousarray(color_host, dtype=_f32).reshape(-1)
+        B = None if B256 is None else np.ascontiguousarray(B256, dtype=_f32)
+        self._ck(self.L.nalo_track_frame(self.h_, C.c_int(trk), C.c_int(new_slot), _ptr(ch), _P(color_dev_ptr) if color_dev_ptr else None, _ptr(B),
+                                         C.c_float(exposure), _ptr(pose), _ptr(aff), C.c_int(coarsestLvl), _ptr(mr), _ptr(lr), _ptr(fl), C.byref(ok), C.byref(st)))
         return bool(ok.value), pose, aff, lr, fl, st.as_dict()
 
     # ---- a11

@@ -137,7 +137,7 @@ struct nalo_ctx {
   int* d_selScratch = nullptr;
   size_t selScratchInts = 0;
   long long launches = 0;
-  cudaEvent_t evA = nullptr, evB = nullptr;
+  cudaEvent_t evA = nullptr, evB = nullptr, evS = nullptr;
   std::string err;
 };
 

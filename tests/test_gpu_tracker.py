@@ -188,3 +188,25 @@ def test_affine_modes(small_pair, gpu_ctx_small, oracle):
         assert dt < 1e-5 and dr < 1e-5, (mA, mB, dt, dr)
         assert np.allclose(aff_g, aff_o, atol=1e-2)
     ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)
+
+
+def test_track_frame_equals_make_images_plus_track(small_pair, gpu_ctx_small, oracle):
+    """nalo_track_frame (addActiveFrame's hot path in one call) == nalo_make_images + nalo_track, bit for bit, from a host
+    image and from a device image."""
+    import torch
+
+    P = small_pair
+    ctx = gpu_ctx_small
+    _setup(ctx, P, oracle)
+    p0 = synth.pose_identity()
+    ref = ctx.track(0, 1, p0, [0, 0])
+    ctx.make_images(1, P["ref"])  # scribble over the slot: track_frame must rebuild it
+    a = ctx.track_frame(0, 1, p0, [0, 0], color_host=P["new"])
+    dev = torch.from_numpy(np.ascontiguousarray(P["new"])).cuda()
+    ctx.make_images(1, P["ref"])
+    ctx.set_profiling(True)
+    b = ctx.track_frame(0, 1, p0, [0, 0], color_dev_ptr=dev.data_ptr())
+    ctx.set_profiling(False)
+    for r in (a, b):
+        assert r[0] == ref[0] and np.array_equal(r[1], ref[1]) and np.array_equal(r[2], ref[2]) and np.array_equal(r[3], ref[3], equal_nan=True)
+    assert b[5]["step_ms"] >= b[5]["kernel_ms"] > 0 and b[5]["launches"] == 2
