@@ -42,6 +42,8 @@ W, H, LEVELS = synth.KITTI_W, synth.KITTI_H, 5
 N_FRAMES = 8          # distinct new frames cycled through
 KEEP = 0.43           # fraction of level-0 pixels seeded (gradient-bearing), SURVEY.md §8(d) config 2
 METRIC = "dense-track residuals/s @1241x376 5-lvl"
+WORKLOAD = ("dense=1 coarse tracking, 1241x376, 5 levels, 1 hypothesis per frame: makeImages + trackNewestCoarse of F new frames per step "
+            "against one dense reference keyframe (F independent frames in flight, like the one-frame-per-core reference arm)")
 
 
 def log(*a):
@@ -168,8 +170,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "residuals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "dense=1 coarse tracking, 1241x376, 5 levels, 1 hypothesis, makeImages+trackNewestCoarse per frame",
-                   "pc_n": r["pc_n"], "frames_timed": r["frames"]},
+        "config": {"workload": WORKLOAD, "pc_n": r["pc_n"], "frames_timed": r["frames"], "frames_per_step_per_gpu": cores},
         "ms_per_frame": r["ms_per_frame"], "gn_iters_per_s": r["gn_iters_per_s"],
         "cpu_baseline": {"value": r["value"], "unit": "residuals/s", "cores": cores, "kind": "port",
                          "sample": f"{r['frames']} frames ({r['seconds']:.1f} s), one frame per core at a time, oracle -O3 -march=x86-64-v3"},
@@ -197,7 +198,8 @@ def run_b200(args, rank, world, local_rank):
     # Every rank aligns its own copy of the same synthetic sequence: per-GPU work is identical (the number of LM
     # iterations depends on the data), so the N-GPU figure isolates system effects from workload variance.
     sc, ref, news, gts = make_workload(seed=synth.DEFAULT_SEED)
-    ctx = capi.Context(W, H, LEVELS, device=local_rank, max_frames=3)
+    F = max(1, min(int(args.frames), 64))  # new frames per step (tracked concurrently against the same reference keyframe)
+    ctx = capi.Context(W, H, LEVELS, device=local_rank, max_frames=F + 2)
     ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)  # mode=1 of the reference preset (main_dso_pangolin.cpp:429-435)
     _, agref = ctx.make_images(0, ref, want_host=True)
     idw, ws = synth.dense_reference_maps(sc, agref[: W * H], KEEP)
@@ -211,52 +213,51 @@ def run_b200(args, rank, world, local_rank):
         a = capi.pinned_array((H, W), np.float32)
         a[...] = n
         pin_imgs.append(a)
-    ext = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
     p0 = synth.pose_identity()
     K, Wu = args.steps, args.warmup
-    results = np.zeros((K, 16))
+    slots = list(range(1, F + 1))
+    p0s, a0s = np.tile(p0, (F, 1)), np.zeros((F, 2))
 
-    # one step = FullSystem::addActiveFrame's hot path through ONE C-ABI call: makeImages + trackNewestCoarse
+    # One step = the per-frame hot path of FullSystem::addActiveFrame (makeImages + trackNewestCoarse) for F new frames
+    # through ONE C-ABI call; frame f of step i is image (i*F + f) mod N_FRAMES.
     def step_dev(i):
-        return ctx.track_frame(0, 1, p0, [0.0, 0.0], color_dev_ptr=dev_imgs[i % N_FRAMES].data_ptr())
+        return ctx.track_frames(0, slots, p0s, a0s, colors_dev_ptrs=[dev_imgs[(i * F + f) % N_FRAMES].data_ptr() for f in range(F)])
 
     def step_host(i):
-        return ctx.track_frame(0, 1, p0, [0.0, 0.0], color_host=pin_imgs[i % N_FRAMES])
+        return ctx.track_frames(0, slots, p0s, a0s, colors_host=[pin_imgs[(i * F + f) % N_FRAMES] for f in range(F)])
 
-    ctx.set_profiling(True)  # CUDA events around the tracking kernel (roofline.kernel_ms); off again for the e2e arm
+    ctx.set_profiling(True)  # CUDA events recorded by the library around the step (and around the tracking kernel)
     for i in range(Wu):
         ctx.flush_l2()
         step_dev(i)
     torch.cuda.synchronize()
     if dist:
-        warm = torch.zeros((K, 16), dtype=torch.float64, device="cuda")
+        warm = torch.zeros((K * F, 16), dtype=torch.float64, device="cuda")
         dist.all_gather([torch.empty_like(warm) for _ in range(world)], warm)  # NCCL warm-up (communicator setup), untimed
         torch.cuda.synchronize()
         dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ctx.kernel_launches()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     tot_res = tot_iters = tot_evals = 0
-    kern_ms, alg_bytes, lib_step_ms = [], [], []
+    kern_ms, alg_bytes, step_ms = [], [], []
+    results = np.zeros((K * F, 16))
     for i in range(K):
-        ctx.flush_l2()  # untimed: cold L2 for every step
-        with torch.cuda.stream(ext):
-            ev[i][0].record()
-        ok, pose, aff, lr, fl, st = step_dev(i)
-        with torch.cuda.stream(ext):
-            ev[i][1].record()
+        ctx.flush_l2()  # untimed: cold L2 for every step (the F pyramids of a step are 10 MB each on top of that)
+        r = step_dev(i)
+        st = r["stats"]
         tot_res += st["residuals"]
         tot_iters += st["iters"]
         tot_evals += st["evals"]
         kern_ms.append(st["kernel_ms"])
-        lib_step_ms.append(st["step_ms"])
+        step_ms.append(st["step_ms"])
         alg_bytes.append(algorithmic_bytes(st["evals_per_level"], pc_n))
-        results[i, 0] = ok
-        results[i, 1:8] = pose
-        results[i, 8:10] = aff
-        results[i, 10:15] = lr
+        results[i * F : (i + 1) * F, 0] = r["ok"]
+        results[i * F : (i + 1) * F, 1:8] = r["poses"]
+        results[i * F : (i + 1) * F, 8:10] = r["affs"]
+        results[i * F : (i + 1) * F, 10:15] = r["lastRes"]
     launches = ctx.kernel_launches() - launches0
+    frames_ok = int(results[:, 0].sum())
     # single tiny gather of the per-frame results (inside the timed region)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     res_dev = torch.from_numpy(results).cuda()
@@ -272,15 +273,12 @@ def run_b200(args, rank, world, local_rank):
     g1.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    # Step time = CUDA events recorded by the library on its launching stream immediately before the pyramid kernel and
-    # immediately after the tracking kernel (stream-ordered with the launches). The event pair recorded from Python
-    # around the call additionally contains the host latency of enqueueing it and is reported as a cross-check.
-    host_ev_ms = [a.elapsed_time(b) for a, b in ev]
-    step_ms = lib_step_ms
+    # Step time = CUDA events recorded by the library on its launching stream immediately before the first kernel of the
+    # step (the pyramid kernel) and immediately after the tracking kernel.
     total_ms = float(sum(step_ms)) + (g0.elapsed_time(g1) if dist else 0.0)
     if os.environ.get("NALO_BENCH_DEBUG"):
         log(f"[rank {rank}] steps ms: mean {np.mean(step_ms):.4f} min {np.min(step_ms):.4f} max {np.max(step_ms):.4f} p50 {np.median(step_ms):.4f}; "
-            f"kernel ms mean {np.mean(kern_ms):.4f}; gather ms {g0.elapsed_time(g1) if dist else 0.0:.4f}; evals {tot_evals / K:.1f}")
+            f"kernel ms mean {np.mean(kern_ms):.4f}; gather ms {g0.elapsed_time(g1) if dist else 0.0:.4f}; evals/frame {tot_evals / K / F:.1f}")
     if dist:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -291,7 +289,7 @@ def run_b200(args, rank, world, local_rank):
     else:
         job_res, job_iters, job_launches = float(tot_res), float(tot_iters), float(launches)
 
-    # ---- e2e arm: host image in, pose out, wall clock, through the C ABI
+    # ---- e2e arm: F host images in, F poses out, wall clock, through the C ABI (uploads pipelined against tracking)
     ctx.set_profiling(False)
     for i in range(min(Wu, 3)):
         step_host(i)
@@ -302,9 +300,9 @@ def run_b200(args, rank, world, local_rank):
         ctx.flush_l2()
         ctx.sync()
         t0 = time.perf_counter()
-        ok, pose, aff, lr, fl, st = step_host(i)
+        r = step_host(i)
         e2e_s += time.perf_counter() - t0
-        e2e_res += st["residuals"]
+        e2e_res += r["stats"]["residuals"]
     if dist:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -312,6 +310,29 @@ def run_b200(args, rank, world, local_rank):
         t = torch.tensor([float(e2e_res)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         e2e_res = float(t.item())
+
+    # ---- latency of ONE frame (the north-star "< 1 ms per frame" figure): same hot path, one frame per call
+    latency = None
+    if rank == 0:
+        ctx.set_profiling(True)
+        lat_step, lat_kern, lat_wall = [], [], []
+        nl = max(10, min(K, 50))
+        for i in range(3 + nl):
+            ctx.flush_l2()
+            ok_, _, _, _, _, st = ctx.track_frame(0, 1, p0, [0.0, 0.0], color_dev_ptr=dev_imgs[i % N_FRAMES].data_ptr())
+            if i >= 3:
+                lat_step.append(st["step_ms"])
+                lat_kern.append(st["kernel_ms"])
+        ctx.set_profiling(False)
+        for i in range(3 + nl):
+            ctx.flush_l2()
+            ctx.sync()
+            t0 = time.perf_counter()
+            ctx.track_frame(0, 1, p0, [0.0, 0.0], color_host=pin_imgs[i % N_FRAMES])
+            if i >= 3:
+                lat_wall.append(1e3 * (time.perf_counter() - t0))
+        latency = {"workload": "one frame per call (nalo_track_frame), all 148 SMs on it", "ms_per_frame_device": float(np.mean(lat_step)),
+                   "tracking_kernel_ms": float(np.mean(lat_kern)), "ms_per_frame_e2e_host_image": float(np.mean(lat_wall)), "frames": nl}
 
     peaks = {}
     try:
@@ -359,14 +380,14 @@ def run_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": job_res / (total_ms * 1e-3), "unit": "residuals/s", "n_gpus": world, "steps": K, "warmup": Wu,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "dense=1 coarse tracking, 1241x376, 5 levels, 1 hypothesis, makeImages+trackNewestCoarse per frame",
-                       "pc_n": pc_n, "seeded_px": int(ws.sum()), "l2": "flushed between steps (256 MiB memset, untimed)",
-                       "frames_per_step_per_gpu": 1, "init_pose": "identity"},
-            "ms_per_frame": total_ms / K, "ms_per_step_python_events": float(np.mean(host_ev_ms)),
-            "gn_iters_per_s": job_iters / (total_ms * 1e-3),
-            "residuals_per_frame": tot_res / K, "evals_per_frame": tot_evals / K,
-            "e2e": {"value": e2e_res / e2e_s, "unit": "residuals/s", "ms_per_frame": 1e3 * e2e_s / K,
-                    "h2d_bytes_per_step": int(W * H * 4 + 1200), "d2h_bytes_per_step": 256},
+            "config": {"workload": WORKLOAD, "pc_n": pc_n, "seeded_px": int(ws.sum()),
+                       "l2": "flushed between steps (256 MiB memset, untimed); the F pyramids of a step (10 MB each) exceed L2 as well",
+                       "frames_per_step_per_gpu": F, "init_pose": "identity", "frames_ok": frames_ok, "frames_total": K * F},
+            "ms_per_frame": total_ms / (K * F), "gn_iters_per_s": job_iters / (total_ms * 1e-3),
+            "residuals_per_frame": tot_res / (K * F), "evals_per_frame": tot_evals / (K * F),
+            "e2e": {"value": e2e_res / e2e_s, "unit": "residuals/s", "ms_per_frame": 1e3 * e2e_s / (K * F), "ms_per_step": 1e3 * e2e_s / K,
+                    "h2d_bytes_per_step": int(F * (W * H * 4) + F * 512), "d2h_bytes_per_step": int(F * 320)},
+            "latency": latency,
             "gpu_launches": int(job_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -395,6 +416,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--frames", type=int, default=64, help="new frames per step (tracked concurrently; 1..64)")
     ap.add_argument("--batch-pairs", type=int, default=592, help="frame pairs of the secondary batched-throughput figure (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -152,6 +152,14 @@ int nalo_track_frame(nalo_ctx* ctx, int trk, int new_slot, const float* color_ho
                      float exposure_new, double pose7_inout[7], double aff2_inout[2], int coarsestLvl, const double minResForAbort5[5],
                      double lastRes5[5], double flow3[3], int* ok, NaloTrackStats* stats /* nullable */);
 
+/* n NEW frames (n <= NALO_MAX_HYPOTHESES) tracked against the same reference in one submission: per frame makeImages into
+ * new_slots[i] (from colors_host[i], or colors_dev[i] when colors_dev is given), then ONE tracking launch for all of
+ * them. Per-frame results as nalo_track_frame (no abort thresholds). Throughput form of the per-frame hot path: a camera
+ * rig, several sequences, or re-localisation candidates. */
+int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const float* const* colors_host, const float* const* colors_dev,
+                      const float* B256, float exposure_new, double* poses7_inout, double* affs2_inout, int coarsestLvl, int* ok_out,
+                      double* lastRes5_out, NaloTrackStats* stats /* nullable */);
+
 /* ---- a11: FullSystem::trackNewCoarse (FullSystem.cpp:502-699) ------------------------------------------ */
 /* candidate list (:516-580) from camToWorld of sprelast, slast and the reference KF; returns count in *n_out (<=31) */
 int nalo_motion_candidates(const double sprelast_c2w[7], const double slast_c2w[7], const double lastF_c2w[7], int posesValid,

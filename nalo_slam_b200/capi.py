@@ -349,6 +349,27 @@ class Context:
                                          C.c_float(exposure), _ptr(pose), _ptr(aff), C.c_int(coarsestLvl), _ptr(mr), _ptr(lr), _ptr(fl), C.byref(ok), C.byref(st)))
         return bool(ok.value), pose, aff, lr, fl, st.as_dict()
 
+    def track_frames(self, trk, slots, poses7, affs2, colors_host=None, colors_dev_ptrs=None, coarsestLvl=None, exposure=1.0):
+        """nalo_track_frames: n new frames (host images or device pointers) against the same reference, one tracking launch."""
+        n = len(slots)
+        poses = np.ascontiguousarray(poses7, dtype=np.float64).reshape(n, 7).copy()
+        affs = np.ascontiguousarray(affs2, dtype=np.float64).reshape(n, 2).copy()
+        if coarsestLvl is None:
+            coarsestLvl = min(self.levels, 5) - 1
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        ok = np.zeros(n, dtype=np.int32)
+        lr = np.zeros((n, 5))
+        st = NaloTrackStats()
+        hp = dp = None
+        if colors_dev_ptrs is not None:
+            dp = (C.c_void_p * n)(*[int(p) for p in colors_dev_ptrs])
+        else:
+            keep = [np.ascontiguousarray(c, dtype=_f32).reshape(-1) for c in colors_host]
+            hp = (C.c_void_p * n)(*[k.ctypes.data for k in keep])
+        self._ck(self.L.nalo_track_frames(self.h_, C.c_int(trk), C.c_int(n), _ptr(sl), hp, dp, None, C.c_float(exposure), _ptr(poses), _ptr(affs),
+                                          C.c_int(coarsestLvl), _ptr(ok), _ptr(lr), C.byref(st)))
+        return dict(ok=ok, poses=poses, affs=affs, lastRes=lr, stats=st.as_dict())
+
     # ---- a11
     def track_multi(self, trk, new_slot, poses7, affs2, coarsestLvl=None, exposure=1.0):
         poses = np.ascontiguousarray(poses7, dtype=np.float64).copy()

@@ -91,6 +91,11 @@ struct nalo_ctx {
   int numSMs = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copyStream = nullptr;  // asynchronous export of the reference-layout host copies (nalo_make_images_async)
+  const void** d_frameTable = nullptr;  // pointer tables of multi-frame pyramid launches (4 regions, round-robin)
+  const void** h_frameTable = nullptr;  // pinned staging of the same
+  unsigned frameTableNext = 0;
+  float* d_colorMulti = nullptr;        // NALO_MAX_HYPOTHESES input images (nalo_track_frames from host images)
+  cudaEvent_t evUpload[2] = {nullptr, nullptr};
   float* d_exportStage = nullptr;     // its own staging buffer (d_stage is scratch of the main stream)
   cudaEvent_t exportDone = nullptr;   // last D2H out of d_exportStage
   bool exportBusy = false;
@@ -163,6 +168,7 @@ int nalo_fail(nalo_ctx* ctx, int code, const char* fmt, ...);
 // internal cross-file entry points
 int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float* B256_host, float* exportStage = nullptr, int exportLevels = 0);
 int nalo_images_to_host(nalo_ctx* ctx, int slot, float* dIp_host, float* absgrad_host);
+int nalo_images_run_multi(nalo_ctx* ctx, int n, const int* slots, const float* const* colors_dev, const float* B256_host, cudaStream_t stream);
 int nalo_depth_finish(nalo_ctx* ctx, int trk, int ref_slot);
 int nalo_track_init(nalo_ctx* ctx);
 void nalo_track_free(nalo_ctx* ctx);

@@ -183,9 +183,16 @@ __device__ __forceinline__ void fused_grad_store(const float* __restrict__ S, in
   }
 }
 
+// frameTable != nullptr: blockIdx.z selects a frame; frameTable[2z] = its input image, frameTable[2z+1] = its float4 pyramid
+// (many frames in ONE launch: nalo_track_frames).
 __global__ void __launch_bounds__(512) make_images_fused_kernel(const float* __restrict__ color, const float* __restrict__ B, int useB,
                                                                 float4* __restrict__ pix, const __grid_constant__ PyrLevels L,
-                                                                float* __restrict__ exportStage, int exportLevels) {
+                                                                float* __restrict__ exportStage, int exportLevels,
+                                                                const void* const* __restrict__ frameTable) {
+  if (frameTable != nullptr) {
+    color = static_cast<const float*>(frameTable[2 * blockIdx.z]);
+    pix = static_cast<float4*>(const_cast<void*>(frameTable[2 * blockIdx.z + 1]));
+  }
   __shared__ float s0[FR_H * FR_W];
   __shared__ float s1[(FR_H / 2) * (FR_W / 2)];
   __shared__ float s2[(FR_H / 4) * (FR_W / 4)];
@@ -313,7 +320,7 @@ int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float
   }
   if (ctx->levels <= 5) {
     dim3 fgrid((ctx->w0 + FT_W - 1) / FT_W, (ctx->h0 + FT_H - 1) / FT_H);
-    make_images_fused_kernel<<<fgrid, 512, 0, ctx->stream>>>(color_dev, ctx->d_B, useB, ctx->frames[slot].pix, L, exportStage, exportLevels);
+    make_images_fused_kernel<<<fgrid, 512, 0, ctx->stream>>>(color_dev, ctx->d_B, useB, ctx->frames[slot].pix, L, exportStage, exportLevels, nullptr);
     NALO_CHECK_LAUNCH(ctx);
     NALO_CUDA(ctx, cudaEventRecord(ctx->frames[slot].built, ctx->stream));
     ctx->frames[slot].valid = true;
@@ -340,6 +347,53 @@ int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float
   NALO_CUDA(ctx, cudaEventRecord(ctx->frames[slot].built, ctx->stream));
   ctx->frames[slot].valid = true;
   if (ctx->histFrameSlot == slot) ctx->histFrameSlot = -1;
+  return NALO_OK;
+}
+
+// Pyramids of n frames in ONE launch (levels <= 5): colors_dev[i] -> frame slot slots[i]. `stream` lets the caller place
+// the launch (nalo_track_frames pipelines uploads against tracking); the pointer table is staged in pinned memory.
+int nalo_images_run_multi(nalo_ctx* ctx, int n, const int* slots, const float* const* colors_dev, const float* B256_host, cudaStream_t stream) {
+  if (n < 1 || n > NALO_MAX_HYPOTHESES) return nalo_fail(ctx, NALO_E_ARG, "nalo_images_run_multi: n = %d", n);
+  if (ctx->levels > 5) {  // 6-level pyramids: frame by frame on the two-kernel path
+    for (int i = 0; i < n; i++) {
+      int rc = nalo_images_run(ctx, slots[i], colors_dev[i], B256_host, nullptr, 0);
+      if (rc != NALO_OK) return rc;
+    }
+    return NALO_OK;
+  }
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  PyrLevels L = make_levels(ctx);
+  int useB = 0;
+  if (B256_host) {
+    NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_B, B256_host, sizeof(float) * 256, cudaMemcpyHostToDevice, stream));
+    useB = 1;
+  }
+  if (!ctx->d_frameTable) {
+    NALO_CUDA(ctx, cudaMalloc(&ctx->d_frameTable, sizeof(void*) * 2 * NALO_MAX_HYPOTHESES * 4));
+    NALO_CUDA(ctx, cudaHostAlloc(&ctx->h_frameTable, sizeof(void*) * 2 * NALO_MAX_HYPOTHESES * 4, cudaHostAllocDefault));
+  }
+  // four table regions used round-robin, so a second call may be enqueued while the first one's copy is still in flight
+  const int region = (ctx->frameTableNext++) & 3;
+  const void** ht = ctx->h_frameTable + (size_t)region * 2 * NALO_MAX_HYPOTHESES;
+  const void** dt = ctx->d_frameTable + (size_t)region * 2 * NALO_MAX_HYPOTHESES;
+  for (int i = 0; i < n; i++) {
+    const int slot = slots[i];
+    if (slot < 0 || slot >= ctx->maxFrames) return nalo_fail(ctx, NALO_E_ARG, "frame slot %d out of range", slot);
+    if (ctx->frames[slot].hostPending) {
+      NALO_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->frames[slot].hostReady, 0));
+      ctx->frames[slot].hostPending = false;
+    }
+    ht[2 * i] = colors_dev[i];
+    ht[2 * i + 1] = ctx->frames[slot].pix;
+  }
+  NALO_CUDA(ctx, cudaMemcpyAsync(dt, ht, sizeof(void*) * 2 * n, cudaMemcpyHostToDevice, stream));
+  dim3 fgrid((ctx->w0 + FT_W - 1) / FT_W, (ctx->h0 + FT_H - 1) / FT_H, n);
+  make_images_fused_kernel<<<fgrid, 512, 0, stream>>>(nullptr, ctx->d_B, useB, nullptr, L, nullptr, 0, reinterpret_cast<const void* const*>(dt));
+  NALO_CHECK_LAUNCH(ctx);
+  for (int i = 0; i < n; i++) {
+    ctx->frames[slots[i]].valid = true;
+    if (ctx->histFrameSlot == slots[i]) ctx->histFrameSlot = -1;
+  }
   return NALO_OK;
 }
 

@@ -264,4 +264,107 @@ int nalo_winner_rule(int nHyp, const double* poses7, const double* affs2, const 
   return NALO_OK;
 }
 
+// Several NEW frames tracked against the same reference in one submission (e.g. a camera rig, several sequences, or
+// re-localisation candidates): per frame the pyramid is built into its own slot, then ONE launch of the persistent
+// tracking kernel aligns all of them (a group of CTAs per frame, dynamic queue). Same per-frame semantics as
+// nalo_track_frame; no abort thresholds. n <= NALO_MAX_HYPOTHESES.
+int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const float* const* colors_host, const float* const* colors_dev,
+                      const float* B256, float exposure_new, double* poses7, double* affs2, int coarsestLvl, int* ok_out, double* lastRes5_out,
+                      NaloTrackStats* stats) {
+  if (!ctx || trk < 0 || trk >= NALO_MAX_TRACKERS || !new_slots || !poses7 || !affs2 || (!colors_host && !colors_dev)) return NALO_E_ARG;
+  if (n < 1 || n > NALO_MAX_HYPOTHESES) return nalo_fail(ctx, NALO_E_ARG, "n %d out of [1,%d]", n, NALO_MAX_HYPOTHESES);
+  if (coarsestLvl < 0 || coarsestLvl >= NALO_TRACK_LEVELS || coarsestLvl >= ctx->levels) return NALO_E_ARG;
+  NaloTrackerState& T = ctx->trk[trk];
+  if (!T.haveK || !T.haveRef) return nalo_fail(ctx, NALO_E_STATE, "tracker %d has no reference", trk);
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const long long l0 = ctx->launches;
+  const bool timing = stats && ctx->profiling;
+  if (timing) NALO_CUDA(ctx, cudaEventRecord(ctx->evS, ctx->stream));
+  for (int i = 0; i < n; i++) {
+    const int slot = new_slots[i];
+    if (slot < 0 || slot >= ctx->maxFrames || slot == T.refSlot) return nalo_fail(ctx, NALO_E_ARG, "frame %d: bad slot %d", i, slot);
+    for (int k = 0; k < i; k++)
+      if (new_slots[k] == slot) return nalo_fail(ctx, NALO_E_ARG, "frame slot %d listed twice", slot);
+    if (!colors_dev && (!colors_host || !colors_host[i])) return NALO_E_ARG;
+  }
+  // problems of all frames (pointers into the frame slots do not depend on the pyramids being built yet)
+  for (int i = 0; i < n; i++) {
+    NaloTrackProblem* P = ctx->h_problems + i;
+    T.newSlot = new_slots[i];
+    T.newExposure = exposure_new;
+    ctx->frames[new_slots[i]].valid = true;
+    nalo_fill_problem(ctx, trk, P);
+    for (int k = 0; k < 7; k++) P->pose[k] = poses7[7 * i + k];
+    P->aff[0] = affs2[2 * i];
+    P->aff[1] = affs2[2 * i + 1];
+    P->coarsestLvl = coarsestLvl;
+    P->useAbort = 0;
+  }
+  NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_problems, ctx->h_problems, sizeof(NaloTrackProblem) * n, cudaMemcpyHostToDevice, ctx->stream));
+  // the frames' pyramids (10 MB each) exceed L2 from ~10 frames on: the evaluation then streams texels from HBM
+  const bool streamed = (size_t)n * ctx->totPix * sizeof(float4) > ((size_t)96 << 20);
+  const size_t n0 = (size_t)ctx->w0 * ctx->h0;
+  const float* srcs[NALO_MAX_HYPOTHESES];
+  // Host images: two halves. The upload of the second half (copy stream) overlaps pyramids + tracking of the first.
+  const int nParts = (!colors_dev && n >= 8) ? 2 : 1;
+  const int nA = (nParts == 2) ? (n + 1) / 2 : n;
+  if (!colors_dev) {
+    if (!ctx->d_colorMulti) {
+      NALO_CUDA(ctx, cudaMalloc(&ctx->d_colorMulti, sizeof(float) * n0 * NALO_MAX_HYPOTHESES));
+      NALO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evUpload[0], cudaEventDisableTiming));
+      NALO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evUpload[1], cudaEventDisableTiming));
+    }
+    // order the uploads after everything already enqueued on the main stream (previous users of the staging area)
+    NALO_CUDA(ctx, cudaEventRecord(ctx->evUpload[0], ctx->stream));
+    NALO_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evUpload[0], 0));
+    for (int part = 0; part < nParts; part++) {
+      const int lo = part ? nA : 0, hi = part ? n : nA;
+      for (int i = lo; i < hi; i++) {
+        NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_colorMulti + n0 * i, colors_host[i], sizeof(float) * n0, cudaMemcpyHostToDevice, ctx->copyStream));
+        srcs[i] = ctx->d_colorMulti + n0 * i;
+      }
+      NALO_CUDA(ctx, cudaEventRecord(ctx->evUpload[part], ctx->copyStream));
+    }
+  } else {
+    for (int i = 0; i < n; i++) srcs[i] = colors_dev[i];
+  }
+  for (int part = 0; part < nParts; part++) {
+    const int lo = part ? nA : 0, cnt = part ? n - nA : nA;
+    if (!colors_dev) NALO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evUpload[part], 0));
+    int rc = nalo_images_run_multi(ctx, cnt, new_slots + lo, srcs + lo, B256, ctx->stream);
+    if (rc != NALO_OK) return rc;
+    if (timing && part == 0) NALO_CUDA(ctx, cudaEventRecord(ctx->evA, ctx->stream));
+    int G = ctx->maxGroups / cnt;
+    if (G < 1) G = 1;
+    rc = nalo_track_launch(ctx, cnt, G, ctx->d_problems + lo, ctx->d_results + lo, streamed, /*helpAll=*/false);
+    if (rc != NALO_OK) return rc;
+  }
+  if (timing) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));
+  NALO_CUDA(ctx, cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(NaloTrackResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stats) memset(stats, 0, sizeof(*stats));
+  for (int i = 0; i < n; i++) {
+    const NaloTrackResult& R = ctx->h_results[i];
+    for (int k = 0; k < 7; k++) poses7[7 * i + k] = R.pose[k];
+    affs2[2 * i] = R.aff[0];
+    affs2[2 * i + 1] = R.aff[1];
+    if (ok_out) ok_out[i] = R.ok;
+    if (lastRes5_out) for (int k = 0; k < 5; k++) lastRes5_out[5 * i + k] = R.lastRes[k];
+    if (stats) {
+      stats->residuals += R.residuals;
+      stats->evals += R.evals;
+      stats->iters += R.iters;
+      for (int k = 0; k < NALO_TRACK_LEVELS; k++) stats->evals_per_level[k] += R.evalsLvl[k];
+    }
+  }
+  if (stats) {
+    stats->launches = (int)(ctx->launches - l0);
+    if (timing) {
+      NALO_CUDA(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->evA, ctx->evB));
+      NALO_CUDA(ctx, cudaEventElapsedTime(&stats->step_ms, ctx->evS, ctx->evB));
+    }
+  }
+  return NALO_OK;
+}
+
 }  // extern "C"

@@ -139,3 +139,43 @@ def test_batch_synth_pair_on_device(small_pair, gpu_ctx_small, oracle):
     dt, dr = synth.pose_distance(out["poses"][0], gt)
     assert out["ok"][0] == 1 and dt < 3e-3 and dr < 3e-4
     B.close()
+
+
+def test_track_frames_equals_single_frames(small_pair, gpu_ctx_small, oracle):
+    """nalo_track_frames: several NEW frames against one reference in one submission == nalo_track_frame one by one
+    (group size only changes the fp32 summation tree), from device images (one launch) and from host images (two
+    pipelined halves)."""
+    import torch
+
+    P = small_pair
+    w, h, L = P["w"], P["h"], P["L"]
+    ctx = capi.Context(w, h, L, device=0, max_frames=13)
+    ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)
+    try:
+        T, idw, ws = make_oracle_tracker(oracle, P)
+        ctx.make_images(0, P["ref"])
+        ctx.make_k(0, *P["scene"].K)
+        ctx.set_ref_dense(0, 0, idw, ws)
+        rng = np.random.default_rng(8)
+        news, gts = [], []
+        for i in range(12):
+            xi, aff = synth.random_motion(rng, 0.5)
+            gts.append(synth.se3_exp(xi))
+            news.append(synth.render_new(P["scene"], gts[-1], aff))
+        p0 = synth.pose_identity()
+        singles = [ctx.track_frame(0, 1, p0, [0, 0], color_host=news[i]) for i in range(12)]
+        slots = list(range(1, 13))
+        dev = [torch.from_numpy(np.ascontiguousarray(n)).cuda() for n in news]
+        outs = [ctx.track_frames(0, slots, np.tile(p0, (12, 1)), np.zeros((12, 2)), colors_dev_ptrs=[d.data_ptr() for d in dev]),
+                ctx.track_frames(0, slots, np.tile(p0, (12, 1)), np.zeros((12, 2)), colors_host=news),
+                ctx.track_frames(0, slots[:3], np.tile(p0, (3, 1)), np.zeros((3, 2)), colors_host=news[:3])]
+        for out in outs:
+            for i in range(len(out["ok"])):
+                assert out["ok"][i] == 1 and singles[i][0]
+                dt, dr = synth.pose_distance(out["poses"][i], singles[i][1])
+                assert dt < 1e-6 and dr < 1e-6, (i, dt, dr)
+                dt, dr = synth.pose_distance(out["poses"][i], gts[i])
+                assert dt < 3e-3 and dr < 3e-4
+        assert outs[0]["stats"]["launches"] == 2  # one pyramid launch for all frames + one tracking launch
+    finally:
+        ctx.close()
