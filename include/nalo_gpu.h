@@ -30,7 +30,7 @@ extern "C" {
 #define NALO_MAX_LEVELS 6     /* PYR_LEVELS, util/settings.h:52 */
 #define NALO_TRACK_LEVELS 5   /* trackNewestCoarse asserts coarsestLvl < 5, CoarseTracker.cpp:1083 */
 #define NALO_MAX_TRACKERS 2
-#define NALO_MAX_HYPOTHESES 64
+#define NALO_MAX_HYPOTHESES 160
 #define NALO_BA_RECORD_WORDS 76 /* one residual record = 304 bytes, layout below */
 #define NALO_BA_MAX_FRAMES 8
 

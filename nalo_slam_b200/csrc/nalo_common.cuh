@@ -89,13 +89,15 @@ struct nalo_ctx {
   int totPixDense = 0;  // unpadded (reference concatenation)
   int denseOff[NALO_MAX_LEVELS];
   int numSMs = 0;
+  size_t trackSmemMax = 0;  // dynamic shared memory track_kernel may use (opt-in limit minus its static part)
   cudaStream_t stream = nullptr;
   cudaStream_t copyStream = nullptr;  // asynchronous export of the reference-layout host copies (nalo_make_images_async)
   const void** d_frameTable = nullptr;  // pointer tables of multi-frame pyramid launches (4 regions, round-robin)
   const void** h_frameTable = nullptr;  // pinned staging of the same
   unsigned frameTableNext = 0;
   float* d_colorMulti = nullptr;        // NALO_MAX_HYPOTHESES input images (nalo_track_frames from host images)
-  cudaEvent_t evUpload[2] = {nullptr, nullptr};
+  static constexpr int kMaxUploadParts = 8;
+  cudaEvent_t evUpload[kMaxUploadParts + 1] = {};  // [0..7]: part uploaded; [8]: fork point on the main stream
   float* d_exportStage = nullptr;     // its own staging buffer (d_stage is scratch of the main stream)
   cudaEvent_t exportDone = nullptr;   // last D2H out of d_exportStage
   bool exportBusy = false;

@@ -134,7 +134,7 @@ int nalo_destroy(nalo_ctx* ctx) {
   cudaFree(ctx->d_exportStage);
   cudaFree(ctx->d_frameTable); cudaFree(ctx->d_colorMulti);
   if (ctx->h_frameTable) cudaFreeHost(ctx->h_frameTable);
-  for (int i = 0; i < 2; i++) if (ctx->evUpload[i]) cudaEventDestroy(ctx->evUpload[i]);
+  for (auto& e : ctx->evUpload) if (e) cudaEventDestroy(e);
   if (ctx->exportDone) cudaEventDestroy(ctx->exportDone);
   cudaFree(ctx->d_color); cudaFree(ctx->d_B); cudaFree(ctx->d_stage); cudaFree(ctx->d_mask); cudaFree(ctx->d_mask_all); cudaFree(ctx->d_ptlist); cudaFree(ctx->d_owner);
   cudaFree(ctx->d_scan); cudaFree(ctx->d_counts); cudaFree(ctx->d_flush);

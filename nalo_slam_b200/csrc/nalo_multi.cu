@@ -13,6 +13,8 @@
 // the small per-candidate records are gathered (NCCL, see bench.py / INTEGRATION.md) and rank 0 replays the rule.
 #include <cstdlib>
 
+#include <algorithm>
+
 #include "nalo_common.cuh"
 
 namespace {
@@ -305,20 +307,26 @@ int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const
   const bool streamed = (size_t)n * ctx->totPix * sizeof(float4) > ((size_t)96 << 20);
   const size_t n0 = (size_t)ctx->w0 * ctx->h0;
   const float* srcs[NALO_MAX_HYPOTHESES];
-  // Host images: two halves. The upload of the second half (copy stream) overlaps pyramids + tracking of the first.
-  const int nParts = (!colors_dev && n >= 8) ? 2 : 1;
-  const int nA = (nParts == 2) ? (n + 1) / 2 : n;
+  // Host images: the submission is cut into parts of ~37 frames (4 CTAs per frame on 148 SMs); the upload of part p+1
+  // (copy stream; a second DMA queue was measured slower) overlaps pyramids + tracking of part p. At 1241x376 the H2D copy of a frame (1.87 MB, ~40 us) costs
+  // more than tracking it (~30-40 us), so the call is PCIe-bound and finer parts only shorten the un-overlapped head/tail.
+  constexpr int kMaxParts = nalo_ctx::kMaxUploadParts;
+  static const char* envP = getenv("NALO_FRAMES_PART");  // measurement switch: frames per part
+  const int partTarget = (envP && atoi(envP) > 0) ? atoi(envP) : 37;
+  int nParts = 1;
+  if (!colors_dev && n >= 8) nParts = std::min(kMaxParts, std::max(1, (n + partTarget / 2) / partTarget));
+  if (nParts > n) nParts = n;
+  auto partLo = [&](int p) { return (int)((long long)n * p / nParts); };
   if (!colors_dev) {
     if (!ctx->d_colorMulti) {
       NALO_CUDA(ctx, cudaMalloc(&ctx->d_colorMulti, sizeof(float) * n0 * NALO_MAX_HYPOTHESES));
-      NALO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evUpload[0], cudaEventDisableTiming));
-      NALO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evUpload[1], cudaEventDisableTiming));
+      for (auto& e : ctx->evUpload) NALO_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     // order the uploads after everything already enqueued on the main stream (previous users of the staging area)
-    NALO_CUDA(ctx, cudaEventRecord(ctx->evUpload[0], ctx->stream));
-    NALO_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evUpload[0], 0));
+    NALO_CUDA(ctx, cudaEventRecord(ctx->evUpload[kMaxParts], ctx->stream));
+    NALO_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evUpload[kMaxParts], 0));
     for (int part = 0; part < nParts; part++) {
-      const int lo = part ? nA : 0, hi = part ? n : nA;
+      const int lo = partLo(part), hi = partLo(part + 1);
       for (int i = lo; i < hi; i++) {
         NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_colorMulti + n0 * i, colors_host[i], sizeof(float) * n0, cudaMemcpyHostToDevice, ctx->copyStream));
         srcs[i] = ctx->d_colorMulti + n0 * i;
@@ -329,14 +337,17 @@ int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const
     for (int i = 0; i < n; i++) srcs[i] = colors_dev[i];
   }
   for (int part = 0; part < nParts; part++) {
-    const int lo = part ? nA : 0, cnt = part ? n - nA : nA;
+    const int lo = partLo(part), cnt = partLo(part + 1) - lo;
     if (!colors_dev) NALO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evUpload[part], 0));
     int rc = nalo_images_run_multi(ctx, cnt, new_slots + lo, srcs + lo, B256, ctx->stream);
     if (rc != NALO_OK) return rc;
     if (timing && part == 0) NALO_CUDA(ctx, cudaEventRecord(ctx->evA, ctx->stream));
     int G = ctx->maxGroups / cnt;
     if (G < 1) G = 1;
-    rc = nalo_track_launch(ctx, cnt, G, ctx->d_problems + lo, ctx->d_results + lo, streamed, /*helpAll=*/false);
+    static const char* envG = getenv("NALO_FRAMES_G");        // measurement switches
+    static const char* envH = getenv("NALO_FRAMES_HELP");
+    if (envG && atoi(envG) > 0) G = atoi(envG);
+    rc = nalo_track_launch(ctx, cnt, G, ctx->d_problems + lo, ctx->d_results + lo, streamed, /*helpAll=*/envH && atoi(envH) > 0);
     if (rc != NALO_OK) return rc;
   }
   if (timing) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));

@@ -179,3 +179,39 @@ def test_track_frames_equals_single_frames(small_pair, gpu_ctx_small, oracle):
         assert outs[0]["stats"]["launches"] == 2  # one pyramid launch for all frames + one tracking launch
     finally:
         ctx.close()
+
+
+def test_track_frames_pipelined_parts(small_pair, gpu_ctx_small, oracle):
+    """nalo_track_frames from HOST images with enough frames (60) to be cut into two pipelined parts (upload of part 2
+    overlapping pyramids + tracking of part 1): every frame must match the one-by-one result."""
+    P = small_pair
+    w, h, L = P["w"], P["h"], P["L"]
+    n = 60
+    ctx = capi.Context(w, h, L, device=0, max_frames=n + 1)
+    ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)
+    try:
+        T, idw, ws = make_oracle_tracker(oracle, P)
+        ctx.make_images(0, P["ref"])
+        ctx.make_k(0, *P["scene"].K)
+        ctx.set_ref_dense(0, 0, idw, ws)
+        rng = np.random.default_rng(9)
+        news = []
+        for i in range(6):
+            xi, aff = synth.random_motion(rng, 0.5)
+            news.append(synth.render_new(P["scene"], synth.se3_exp(xi), aff))
+        p0 = synth.pose_identity()
+        singles = [ctx.track_frame(0, 1, p0, [0, 0], color_host=news[i]) for i in range(6)]
+        pins = []
+        for i in range(n):
+            a = capi.pinned_array((h, w), np.float32)
+            a[...] = news[i % 6]
+            pins.append(a)
+        for rep in range(2):  # second call reuses the staging area while nothing of the first is pending
+            out = ctx.track_frames(0, list(range(1, n + 1)), np.tile(p0, (n, 1)), np.zeros((n, 2)), colors_host=pins)
+            assert out["stats"]["launches"] == 4  # two parts x (pyramids + tracking)
+            for i in range(n):
+                assert out["ok"][i] == 1
+                dt, dr = synth.pose_distance(out["poses"][i], singles[i % 6][1])
+                assert dt < 1e-6 and dr < 1e-6, (i, dt, dr)
+    finally:
+        ctx.close()
