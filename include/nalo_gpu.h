@@ -265,6 +265,40 @@ typedef struct NaloLinInput {
 int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, float* energy, float* energy_with_outlier, float* center3,
                       float* projected16, float* rec_out);
 
+/* ---- f3 (SURVEY.md §8 f, "next"): CoarseInitializer::calcResAndGS (FullSystem/CoarseInitializer.cpp:336-608) --------
+ * The initializer's point set of ONE pyramid level (`Pnt`, CoarseInitializer.h:43-77) lives on the device between the
+ * calls of its Gauss-Newton loop (trackFrame :146-283: calcResAndGS -> 8x8 solve -> doStep -> calcResAndGS ...); the
+ * 8x8 solve, doStep / applyStep / optReg and the level propagation stay on the host in this round and exchange the
+ * per-point state through nalo_init_update_points / nalo_init_get_points.
+ * Frames are context frame slots built by nalo_make_images (firstFrame = ref_slot, newFrame = new_slot). */
+typedef struct NaloInitPoints {
+  int n;
+  const float* u;               /* Pnt::u, v  (x+0.1, y+0.1 as set by setFirst :831-832) */
+  const float* v;
+  const float* idepth_new;      /* Pnt::idepth_new */
+  const float* iR;              /* Pnt::iR */
+  const uint8_t* isGood;        /* Pnt::isGood */
+  const float* energy2;         /* [n][2] Pnt::energy */
+  const float* outlierTH;       /* Pnt::outlierTH */
+  const float* lastHessian_new; /* nullable: Pnt::lastHessian_new (kept for points that are not good in this call) */
+  const float* JbBuffer_new;    /* nullable [n][10]: previous JbBuffer_new (rows of !isGood points are never rewritten) */
+} NaloInitPoints;
+typedef struct nalo_init nalo_init;
+int nalo_init_create(nalo_ctx* ctx, int max_points, nalo_init** out);
+int nalo_init_destroy(nalo_init* in);
+int nalo_init_set_points(nalo_init* in, const NaloInitPoints* p);
+/* any of the four may be NULL (unchanged) */
+int nalo_init_update_points(nalo_init* in, const float* idepth_new, const float* iR, const uint8_t* isGood, const float* energy2);
+/* calcResAndGS(lvl, H_out, b_out, H_out_sc, b_out_sc, refToNew, refToNew_aff): K4 = fx[lvl], fy[lvl], cx[lvl], cy[lvl] of
+ * CoarseInitializer::makeK (:958-987); pose7 = refToNew (qx,qy,qz,qw,tx,ty,tz); aff2 = (a, b); alphaW, alphaK,
+ * couplingWeight as in the constructor (:92-95). H / Hsc row-major 8x8, res3 = {E.A, alphaEnergy, E.num}. The huber
+ * threshold comes from the context's NaloParams. Output pointers are nullable. */
+int nalo_init_calc_res_gs(nalo_init* in, int lvl, int ref_slot, int new_slot, const float K4[4], const double pose7[7], const double aff2[2],
+                          float alphaW, float alphaK, float couplingWeight, float* H64, float* b8, float* Hsc64, float* bsc8, float res3[3]);
+/* per-point results of the last call (all nullable): maxstep [n], isGood_new [n], energy_new [n][2], lastHessian_new [n],
+ * JbBuffer_new [n][10] */
+int nalo_init_get_points(nalo_init* in, float* maxstep, uint8_t* isGood_new, float* energy_new2, float* lastHessian_new, float* JbBuffer_new10);
+
 #ifdef __cplusplus
 }
 #endif

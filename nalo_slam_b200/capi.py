@@ -98,6 +98,12 @@ def load():
         L.nalo_host_free.argtypes = [_P]
         L.nalo_batch_results_dev.restype = _P
         L.nalo_batch_results_dev.argtypes = [_P]
+        L.nalo_init_create.argtypes = [_P, C.c_int, C.POINTER(_P)]
+        L.nalo_init_destroy.argtypes = [_P]
+        L.nalo_init_set_points.argtypes = [_P, _P]
+        L.nalo_init_update_points.argtypes = [_P, _P, _P, _P, _P]
+        L.nalo_init_calc_res_gs.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P]
+        L.nalo_init_get_points.argtypes = [_P, _P, _P, _P, _P, _P]
         _lib = L
     return _lib
 
@@ -480,6 +486,79 @@ class Batch:
 
     def results_dev_ptr(self) -> int:
         return int(self.L.nalo_batch_results_dev(self.h_) or 0)
+
+
+class NaloInitPoints(C.Structure):
+    _fields_ = [("n", C.c_int), ("u", _P), ("v", _P), ("idepth_new", _P), ("iR", _P), ("isGood", _P), ("energy2", _P),
+                ("outlierTH", _P), ("lastHessian_new", _P), ("JbBuffer_new", _P)]
+
+
+class Initializer:
+    """nalo_init: CoarseInitializer::calcResAndGS (CoarseInitializer.cpp:336-608) with the level's point set on the device."""
+
+    ALPHA_K, ALPHA_W, COUPLING = 2.5 * 2.5, 150.0 * 150.0, 1.0  # CoarseInitializer.cpp:92-95
+
+    def __init__(self, ctx: "Context", max_points: int):
+        self.ctx, self.L = ctx, ctx.L
+        h_ = _P()
+        ctx._ck(self.L.nalo_init_create(ctx.h_, C.c_int(max_points), C.byref(h_)))
+        self.h_ = h_
+        self.n = 0
+        ctx._children.add(self)
+
+    def close(self):
+        if getattr(self, "h_", None):
+            if getattr(self.ctx, "h_", None):
+                self.L.nalo_init_destroy(self.h_)
+            self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_points(self, pts: dict):
+        """pts: dict(u, v, idepth_new, iR, isGood (uint8), energy [n,2], outlierTH[, lastHessian_new, JbBuffer_new])."""
+        P = NaloInitPoints()
+        self.n = P.n = int(len(pts["u"]))
+        keep = []
+        for k, key, dt in (("u", "u", _f32), ("v", "v", _f32), ("idepth_new", "idepth_new", _f32), ("iR", "iR", _f32), ("isGood", "isGood", np.uint8),
+                           ("energy2", "energy", _f32), ("outlierTH", "outlierTH", _f32), ("lastHessian_new", "lastHessian_new", _f32),
+                           ("JbBuffer_new", "JbBuffer_new", _f32)):
+            a = pts.get(key)
+            if a is None:
+                setattr(P, k, None)
+            else:
+                a = np.ascontiguousarray(a, dtype=dt)
+                keep.append(a)
+                setattr(P, k, a.ctypes.data)
+        self.ctx._ck(self.L.nalo_init_set_points(self.h_, C.byref(P)))
+
+    def update_points(self, idepth_new=None, iR=None, isGood=None, energy=None):
+        c = lambda a, dt: None if a is None else np.ascontiguousarray(a, dtype=dt)
+        a, b, g, e = c(idepth_new, _f32), c(iR, _f32), c(isGood, np.uint8), c(energy, _f32)
+        self.ctx._ck(self.L.nalo_init_update_points(self.h_, _ptr(a), _ptr(b), _ptr(g), _ptr(e)))
+
+    def calc_res_gs(self, lvl, ref_slot, new_slot, K4, pose7, aff2, alphaW=None, alphaK=None, couplingWeight=None):
+        K4 = np.ascontiguousarray(K4, dtype=_f32)
+        pose = np.ascontiguousarray(pose7, dtype=np.float64)
+        aff = np.ascontiguousarray(aff2, dtype=np.float64)
+        H, b, Hsc, bsc, res = (np.zeros(64, dtype=_f32), np.zeros(8, dtype=_f32), np.zeros(64, dtype=_f32), np.zeros(8, dtype=_f32),
+                               np.zeros(3, dtype=_f32))
+        self.ctx._ck(self.L.nalo_init_calc_res_gs(
+            self.h_, C.c_int(lvl), C.c_int(ref_slot), C.c_int(new_slot), _ptr(K4), _ptr(pose), _ptr(aff),
+            C.c_float(self.ALPHA_W if alphaW is None else alphaW), C.c_float(self.ALPHA_K if alphaK is None else alphaK),
+            C.c_float(self.COUPLING if couplingWeight is None else couplingWeight), _ptr(H), _ptr(b), _ptr(Hsc), _ptr(bsc), _ptr(res)))
+        return dict(H=H.reshape(8, 8), b=b, Hsc=Hsc.reshape(8, 8), bsc=bsc, res=res)
+
+    def get_points(self):
+        n = max(self.n, 1)
+        ms, g, en, lh, jb = (np.zeros(n, dtype=_f32), np.zeros(n, dtype=np.uint8), np.zeros((n, 2), dtype=_f32), np.zeros(n, dtype=_f32),
+                             np.zeros((n, 10), dtype=_f32))
+        self.ctx._ck(self.L.nalo_init_get_points(self.h_, _ptr(ms), _ptr(g), _ptr(en), _ptr(lh), _ptr(jb)))
+        k = self.n
+        return dict(maxstep=ms[:k], isGood_new=g[:k], energy_new=en[:k], lastHessian_new=lh[:k], JbBuffer_new=jb[:k])
 
 
 class BA:

@@ -181,7 +181,8 @@ int nalo_track_multi(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, i
   if (nHyp > 8) G = ctx->maxGroups / ((nHyp + 2) / 3);  // ~three candidates per group, handed out through the dynamic queue
   if (envG > 0) G = envG;
   if (G < 1) G = 1;
-  rc = nalo_track_launch(ctx, nHyp, G, ctx->d_problems, ctx->d_results, /*streamed=*/false, /*helpAll=*/envHelp);
+  static const bool envStreamed = getenv("NALO_MULTI_STREAMED") != nullptr;
+  rc = nalo_track_launch(ctx, nHyp, G, ctx->d_problems, ctx->d_results, /*streamed=*/envStreamed, /*helpAll=*/envHelp);
   if (rc != NALO_OK) return rc;
   if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));
   NALO_CUDA(ctx, cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(NaloTrackResult) * nHyp, cudaMemcpyDeviceToHost, ctx->stream));

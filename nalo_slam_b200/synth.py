@@ -387,3 +387,42 @@ def make_lin_problem(scene: Scene, nf=4, pts_per_frame=500, seed=DEFAULT_SEED, b
                 pt4=np.array(pt4, dtype=np.float32).reshape(n, 4), color=np.array(color, dtype=np.float32).reshape(n, 8),
                 weights=np.array(weights, dtype=np.float32).reshape(n, 8), pack=np.array(pack, dtype=np.uint32),
                 point=np.array(point, dtype=np.int32), state_in=np.zeros(n, dtype=np.uint8), energy_in=np.zeros(n, dtype=np.float32))
+
+
+# ---------------------------------------------------------------- CoarseInitializer point sets
+def make_init_points(scene: Scene, lvl: int, step: int = 3, seed=DEFAULT_SEED, idepth_noise=0.05, bad_fraction=0.03, border=None):
+    """Synthetic `Pnt` set of one level as CoarseInitializer::setFirst lays it out (:824-858): integer pixels + 0.1 inside
+    the patternPadding border (here a regular grid every `step` px instead of the selector's picks), idepth_new = scaled
+    ground truth with noise, a few points already marked bad, outlierTH = patternNum * setting_outlierTH."""
+    rng = np.random.default_rng(seed + 17 * lvl)
+    wl, hl = scene.w >> lvl, scene.h >> lvl
+    pad = 2
+    lo = pad + 1 if border is None else border
+    xs = np.arange(lo, wl - pad - 2 if border is None else wl - border, step)
+    ys = np.arange(lo, hl - pad - 2 if border is None else hl - border, step)
+    xx, yy = np.meshgrid(xs, ys)
+    xx, yy = xx.ravel(), yy.ravel()
+    n = xx.size
+    s = float(1 << lvl)
+    idp = scene.idepth((xx + 0.5) * s - 0.5, (yy + 0.5) * s - 0.5)
+    idp = idp / np.mean(idp)  # the initializer works at unit mean inverse depth
+    idn = (idp * (1.0 + idepth_noise * rng.standard_normal(n))).astype(np.float32)
+    good = (rng.uniform(size=n) > bad_fraction).astype(np.uint8)
+    energy = np.stack([rng.uniform(0, 400, n), rng.uniform(0, 0.2, n)], axis=1).astype(np.float32)
+    return dict(u=(xx + 0.1).astype(np.float32), v=(yy + 0.1).astype(np.float32), idepth_new=idn,
+                iR=(idp * (1.0 + 0.02 * rng.standard_normal(n))).astype(np.float32), isGood=good, energy=energy,
+                outlierTH=np.full(n, 8 * 12.0 * 12.0, dtype=np.float32))
+
+
+def level_K(K, lvl):
+    """fx, fy, cx, cy of pyramid level lvl with CoarseInitializer::makeK's float arithmetic (:963-976)."""
+    fx, fy, cx, cy = (np.float32(k) for k in K)
+    fxl, fyl = fx, fy
+    for _ in range(lvl):
+        fxl = np.float32(np.float64(fxl) * 0.5)
+        fyl = np.float32(np.float64(fyl) * 0.5)
+    if lvl == 0:
+        return np.array([fx, fy, cx, cy], dtype=np.float32)
+    cxl = np.float32((np.float64(cx) + 0.5) / (1 << lvl) - 0.5)
+    cyl = np.float32((np.float64(cy) + 0.5) / (1 << lvl) - 0.5)
+    return np.array([fxl, fyl, cxl, cyl], dtype=np.float32)

@@ -421,3 +421,37 @@ def ba_resubstitute(prob, JpJdF, ppA, ppL, perPointSC, xc, xAd):
         _ptr(HcdA), _ptr(HcdL), _ptr(np.ascontiguousarray(perPointSC, dtype=_f32)), _ptr(np.ascontiguousarray(xc, dtype=_f32)),
         _ptr(np.ascontiguousarray(xAd, dtype=_f32)), _ptr(step))
     return step
+
+
+def init_calc_res_gs(dIp_ref_lvl, dIp_new_lvl, wl, hl, K4, pose7, aff2, pts, alphaW=150.0 * 150.0, alphaK=2.5 * 2.5, couplingWeight=1.0,
+                     huberTH=9.0, fast=False):
+    """CoarseInitializer::calcResAndGS on one level. dIp_*_lvl: the level's AoS {I,dx,dy} ([wl*hl,3] float32).
+    pts: dict(u, v, idepth_new, iR, isGood (uint8), energy [n,2], outlierTH[, lastHessian_new, JbBuffer_new]).
+    Returns dict(H, b, Hsc, bsc, res, maxstep, isGood_new, energy_new, lastHessian_new, JbBuffer_new)."""
+    n = int(len(pts["u"]))
+    f = lambda k: np.ascontiguousarray(pts[k], dtype=_f32)
+    ref = np.ascontiguousarray(dIp_ref_lvl, dtype=_f32)
+    new = np.ascontiguousarray(dIp_new_lvl, dtype=_f32)
+    K4 = np.ascontiguousarray(K4, dtype=_f32)
+    pose = np.ascontiguousarray(pose7, dtype=np.float64)
+    aff = np.ascontiguousarray(aff2, dtype=np.float64)
+    m = max(n, 1)
+    ms = np.zeros(m, dtype=_f32)
+    g = np.zeros(m, dtype=np.uint8)
+    en = np.zeros((m, 2), dtype=_f32)
+    lh = np.zeros(m, dtype=_f32) if pts.get("lastHessian_new") is None else np.ascontiguousarray(pts["lastHessian_new"], dtype=_f32).copy()
+    jb = np.zeros((m, 10), dtype=_f32) if pts.get("JbBuffer_new") is None else np.ascontiguousarray(pts["JbBuffer_new"], dtype=_f32).copy()
+    H, b, Hsc, bsc, res = np.zeros(64, dtype=_f32), np.zeros(8, dtype=_f32), np.zeros(64, dtype=_f32), np.zeros(8, dtype=_f32), np.zeros(3, dtype=_f32)
+    lib(fast).oracle_init_calc_res_gs(
+        C.c_int(wl), C.c_int(hl), _ptr(ref), _ptr(new), _ptr(K4), _ptr(pose), _ptr(aff), C.c_int(n), _ptr(f("u")), _ptr(f("v")),
+        _ptr(f("idepth_new")), _ptr(f("iR")), _ptr(np.ascontiguousarray(pts["isGood"], dtype=np.uint8)), _ptr(f("energy")), _ptr(f("outlierTH")),
+        C.c_float(alphaW), C.c_float(alphaK), C.c_float(couplingWeight), C.c_float(huberTH), _ptr(ms), _ptr(g), _ptr(en), _ptr(lh), _ptr(jb),
+        _ptr(H), _ptr(b), _ptr(Hsc), _ptr(bsc), _ptr(res))
+    return dict(H=H.reshape(8, 8), b=b, Hsc=Hsc.reshape(8, 8), bsc=bsc, res=res, maxstep=ms[:n], isGood_new=g[:n], energy_new=en[:n],
+                lastHessian_new=lh[:n], JbBuffer_new=jb[:n])
+
+
+def init_rki(K4, pose7):
+    RKi, t = np.zeros(9, dtype=_f32), np.zeros(3, dtype=_f32)
+    lib().oracle_init_rki(_ptr(np.ascontiguousarray(K4, dtype=_f32)), _ptr(np.ascontiguousarray(pose7, dtype=np.float64)), _ptr(RKi), _ptr(t))
+    return RKi.reshape(3, 3), t

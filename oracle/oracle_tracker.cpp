@@ -29,70 +29,11 @@
 #include <vector>
 
 #include "oracle_math.h"
+#include "oracle_acc9.h"
 
 namespace {
 
 constexpr int PYR = 6;
-
-// Accumulator9 — MatrixAccumulators.h:982-1345
-struct Acc9 {
-  alignas(16) float SSEData[4 * 45];
-  alignas(16) float SSEData1k[4 * 45];
-  alignas(16) float SSEData1m[4 * 45];
-  float numIn1, numIn1k, numIn1m;
-  size_t num;
-  float H[9][9];
-
-  void initialize() {
-    memset(H, 0, sizeof(H));
-    memset(SSEData, 0, sizeof(SSEData));
-    memset(SSEData1k, 0, sizeof(SSEData1k));
-    memset(SSEData1m, 0, sizeof(SSEData1m));
-    num = 0;
-    numIn1 = numIn1k = numIn1m = 0;
-  }
-  void shiftUp(bool force) {
-    if (numIn1 > 1000 || force) {
-      for (int i = 0; i < 45; i++)
-        _mm_store_ps(SSEData1k + 4 * i, _mm_add_ps(_mm_load_ps(SSEData + 4 * i), _mm_load_ps(SSEData1k + 4 * i)));
-      numIn1k += numIn1;
-      numIn1 = 0;
-      memset(SSEData, 0, sizeof(SSEData));
-    }
-    if (numIn1k > 1000 || force) {
-      for (int i = 0; i < 45; i++)
-        _mm_store_ps(SSEData1m + 4 * i, _mm_add_ps(_mm_load_ps(SSEData1k + 4 * i), _mm_load_ps(SSEData1m + 4 * i)));
-      numIn1m += numIn1k;
-      numIn1k = 0;
-      memset(SSEData1k, 0, sizeof(SSEData1k));
-    }
-  }
-  void finish() {
-    memset(H, 0, sizeof(H));
-    shiftUp(true);
-    int idx = 0;
-    for (int r = 0; r < 9; r++)
-      for (int c = r; c < 9; c++) {
-        float d = SSEData1m[idx + 0] + SSEData1m[idx + 1] + SSEData1m[idx + 2] + SSEData1m[idx + 3];
-        H[r][c] = H[c][r] = d;
-        idx += 4;
-      }
-  }
-  // updateSSE_eighted — MatrixAccumulators.h:1091-1166
-  void updateSSE_weighted(const __m128* J, const __m128 w) {
-    float* pt = SSEData;
-    for (int r = 0; r < 9; r++) {
-      __m128 Jw = _mm_mul_ps(J[r], w);
-      for (int c = r; c < 9; c++) {
-        _mm_store_ps(pt, _mm_add_ps(_mm_load_ps(pt), _mm_mul_ps(Jw, J[c])));
-        pt += 4;
-      }
-    }
-    num += 4;
-    numIn1++;
-    shiftUp(false);
-  }
-};
 
 // 16 zero floats of padding on both sides: the reference's level-0/1 dilation reads weightSums_bak[-1] and
 // weightSums_bak[w*h] (CoarseTracker.cpp:456-457 at i=w and i=w*h-w-1), i.e. one element outside the
@@ -140,7 +81,7 @@ struct OTracker {
   float setting_affineOptModeA = 1e12f;
   float setting_affineOptModeB = 1e8f;
 
-  Acc9 acc;
+  orc::Acc9 acc;
 
   // stats for the bench (not in the reference)
   long long statResiduals = 0;
@@ -390,7 +331,7 @@ void tracker_calc_res(OTracker* T, int lvl, const orc::SE3& refToNew, const doub
 
 // a7 — H_out 8x8 row-major double, b_out 8 double
 void tracker_calc_gs(OTracker* T, int lvl, double* H_out, double* b_out, const orc::SE3& /*refToNew*/, const double* aff_g2l) {
-  Acc9& acc = T->acc;
+  orc::Acc9& acc = T->acc;
   acc.initialize();
   __m128 fxl = _mm_set1_ps(T->fx[lvl]);
   __m128 fyl = _mm_set1_ps(T->fy[lvl]);
