@@ -185,7 +185,7 @@ __device__ __forceinline__ void fused_grad_store(const float* __restrict__ S, in
 
 // frameTable != nullptr: blockIdx.z selects a frame; frameTable[2z] = its input image, frameTable[2z+1] = its float4 pyramid
 // (many frames in ONE launch: nalo_track_frames).
-__global__ void __launch_bounds__(512) make_images_fused_kernel(const float* __restrict__ color, const float* __restrict__ B, int useB,
+__global__ void __launch_bounds__(512, 3) make_images_fused_kernel(const float* __restrict__ color, const float* __restrict__ B, int useB,
                                                                 float4* __restrict__ pix, const __grid_constant__ PyrLevels L,
                                                                 float* __restrict__ exportStage, int exportLevels,
                                                                 const void* const* __restrict__ frameTable) {
@@ -206,14 +206,19 @@ __global__ void __launch_bounds__(512) make_images_fused_kernel(const float* __r
   // All 12 loads of a thread are issued before the first store (one DRAM round trip, not twelve).
   {
     float v[12];
+    // 32-bit offsets from one base, validity as 3 column x 4 row predicates (the first version spent ~45 % of the kernel's
+    // issue slots on per-load bounds tests and 64-bit index arithmetic)
+    const int gx0 = rx0 + lane, gy0 = ry0 + wid;
+    const int off0 = gy0 * w0 + gx0;
+    bool xok[3], yok[4];
+#pragma unroll
+    for (int q = 0; q < 3; q++) xok[q] = (unsigned)(gx0 + 32 * q) < (unsigned)w0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) yok[r] = (unsigned)(gy0 + 16 * r) < (unsigned)h0;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-      const int gy = ry0 + wid + 16 * r;
 #pragma unroll
-      for (int q = 0; q < 3; q++) {
-        const int gx = rx0 + lane + 32 * q;
-        v[3 * r + q] = (gx >= 0 && gx < w0 && gy >= 0 && gy < h0) ? __ldg(color + (size_t)gy * w0 + gx) : 0.f;
-      }
+      for (int q = 0; q < 3; q++) v[3 * r + q] = (xok[q] && yok[r]) ? __ldg(color + (unsigned)(off0 + 16 * r * w0 + 32 * q)) : 0.f;
     }
 #pragma unroll
     for (int r = 0; r < 4; r++)

@@ -80,7 +80,7 @@ def cpu_time(fn, budget_s=3.0, min_reps=3):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--rows", default="a1,select,ref,eval,track,multi,batch,ba,lin")
+    ap.add_argument("--rows", default="a1,select,ref,eval,track,multi,batch,ba,lin,init")
     ap.add_argument("--batch-pairs", type=int, default=296)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "suite.json"))
@@ -395,6 +395,32 @@ def main():
             "per iteration: H2D 21 B/res (pt4, state, energy) + D2H 5 B/res (new state, energy), pageable, static point data resident; records stay on the device")
         bal.close()
         ctxl.close()
+
+    # ------------------------------------------------------------------ f3 CoarseInitializer::calcResAndGS
+    if "init" in rows_wanted:
+        ctx.make_images(0, ref)
+        ctx.make_images(1, news[0])
+        dref_o, _ = O.make_images(ref, W, H, L, fast=True)
+        dnew_o, _ = O.make_images(news[0], W, H, L, fast=True)
+        offs = np.cumsum([0] + [(W >> l) * (H >> l) for l in range(L)])
+        for lvl, step in ((0, 6), (1, 2), (2, 1)):  # ~0.03*w*h points at level 0 (setFirst :804-811), denser coarse levels
+            wl_, hl_ = W >> lvl, H >> lvl
+            K4 = synth.level_K(sc.K, lvl)
+            pts = synth.make_init_points(sc, lvl, step=step, bad_fraction=0.02)
+            n = len(pts["u"])
+            I = capi.Initializer(ctx, n)
+            I.set_points(pts)
+            pose = np.array(gts[0], dtype=np.float64)
+            pose[4:7] *= 2.0
+            d, wl, _ = T.run(lambda i: I.calc_res_gs(lvl, 0, 1, K4, pose, [0.01, 0.5]), reps=20)
+            c = None
+            if cpu:
+                c = cpu_time(lambda: O.init_calc_res_gs(dref_o[offs[lvl]:offs[lvl + 1]], dnew_o[offs[lvl]:offs[lvl + 1]], wl_, hl_, K4, pose, [0.01, 0.5],
+                                                        pts, fast=True), budget_s=2.0)[0]
+            # algorithmic bytes per point: 29 in (u,v,id,iR,good,energy,outlierTH) + 8 px x 8 texels x 16 B (L2-resident frames) ; out 61
+            add(f"f3 calcResAndGS lvl{lvl} npts={n}", d, wl, (29 + 8 * 8 * 16 + 61) * n, 8 * n, "residual", c, 1,
+                "two launches + 768 B readback; point state resident on the device")
+            I.close()
 
     doc = dict(peak_hbm_gbs=peak, peak_source="MEASURED_PEAKS.json" if peaks else "fallback", gpu=torch.cuda.get_device_name(0),
                host_cores=os.cpu_count(), pc_n=pc_n, rows=rows)
