@@ -69,3 +69,29 @@ def all_gather_records(local: np.ndarray, n_total: int, device=None) -> np.ndarr
     dist.all_gather(out, buf)
     parts = [out[r][: sizes[r]].cpu().numpy() for r in range(world)]
     return np.concatenate(parts, axis=0)
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ wrapper so torch can view a raw device pointer owned by the library."""
+
+    def __init__(self, ptr: int, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def all_gather_device_records(dev_ptr: int, n_local: int, n_total: int, device, width: int = 16) -> np.ndarray:
+    """all_gather of per-unit records that already sit in device memory (nalo_batch_results_dev: float64 [n_local][16]),
+    without the host round trip of all_gather_records: one device copy into the padded send buffer, one NCCL
+    all_gather_into_tensor over NVLink, one D2H of the gathered block."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    sizes = shard_sizes(n_total, world)
+    m = max(sizes)
+    buf = torch.zeros((m, width), dtype=torch.float64, device=device)
+    if n_local:
+        buf[:n_local] = torch.as_tensor(_DevArray(dev_ptr, (n_local, width)), device=device)
+    out = torch.empty((world * m, width), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, buf)
+    host = out.cpu().numpy().reshape(world, m, width)
+    return np.concatenate([host[r, : sizes[r]] for r in range(world)], axis=0)

@@ -148,8 +148,10 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         r = B.track(0, mine)
-        rec = sharding.pack_records(r)
-        full = gather(rec, total)
+        if dist:  # the packed per-pair records are gathered straight from device memory (NCCL over NVLink)
+            full = sharding.all_gather_device_records(B.results_dev_ptr(), mine, total, dev)
+        else:
+            full = sharding.pack_records(r)
         torch.cuda.synchronize()
         wall = 1e3 * (time.perf_counter() - t0)
         st = r["stats"]
