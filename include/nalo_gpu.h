@@ -299,6 +299,43 @@ int nalo_init_calc_res_gs(nalo_init* in, int lvl, int ref_slot, int new_slot, co
  * JbBuffer_new [n][10] */
 int nalo_init_get_points(nalo_init* in, float* maxstep, uint8_t* isGood_new, float* energy_new2, float* lastHessian_new, float* JbBuffer_new10);
 
+/* ---- f4 (SURVEY.md §8 f, "next"): ImmaturePoint (FullSystem/ImmaturePoint.cpp:32-66 constructor, :81-436 traceOn) ----
+ * The immature points of ONE host keyframe live on the device: the constructor's pattern colours / weights / gradient
+ * matrix / energy threshold and the depth-filter state that traceOn updates for every new frame
+ * (FullSystem::traceNewCoarse, FullSystem.cpp:700-740: one nalo_immature_trace per host keyframe and new frame). */
+typedef struct NaloTraceParams {   /* util/settings.cpp:99-100,146,165-174; huberTH comes from NaloParams */
+  float maxPixSearch;              /* setting_maxPixSearch = 0.027 */
+  float trace_stepsize;            /* 1.0 */
+  int trace_GNIterations;          /* 3 */
+  float trace_GNThreshold;         /* 0.1 */
+  float trace_extraSlackOnTH;      /* 1.2 */
+  float trace_slackInterval;       /* 1.5 */
+  float trace_minImprovementFactor;/* 2 */
+  int minTraceTestRadius;          /* 2 */
+  float outlierTH;                 /* setting_outlierTH = 12*12 */
+  float outlierTHSumComponent;     /* 50*50 */
+  float overallEnergyTHWeight;     /* 1 */
+} NaloTraceParams;
+void nalo_default_trace_params(NaloTraceParams* p);
+enum { NALO_IPS_GOOD = 0, NALO_IPS_OOB = 1, NALO_IPS_OUTLIER = 2, NALO_IPS_SKIPPED = 3, NALO_IPS_BADCONDITION = 4, NALO_IPS_UNINITIALIZED = 5 };
+typedef struct nalo_immature nalo_immature;
+int nalo_immature_create(nalo_ctx* ctx, int max_points, nalo_immature** out);
+int nalo_immature_destroy(nalo_immature* im);
+/* ImmaturePoint(u, v, host, ...) for n points of the frame in host_slot (u, v: integer pixel coordinates as floats, inside
+ * [2, w-3) x [2, h-3)); state := idepth_min 0, idepth_max NaN, quality 10000, status UNINITIALIZED. energyTH = NaN marks a
+ * point whose pattern touched a non-finite pixel (the reference deletes those). tp nullable = defaults. */
+int nalo_immature_init(nalo_immature* im, int host_slot, int n, const float* u, const float* v, const NaloTraceParams* tp);
+/* overwrite parts of the filter state (all nullable), e.g. after the host activated / dropped points */
+int nalo_immature_set_state(nalo_immature* im, const float* idepth_min, const float* idepth_max, const float* quality, const int* status);
+/* traceOn(frame, hostToFrame_KRKi, hostToFrame_Kt, hostToFrame_affine) for every point; KRKi row-major. counts6 (nullable)
+ * = number of points per ImmaturePointStatus after the call (the trace_good / trace_oob / ... counters of traceNewCoarse). */
+int nalo_immature_trace(nalo_immature* im, int frame_slot, const float KRKi9[9], const float Kt3[3], const float aff2[2], const NaloTraceParams* tp,
+                        int counts6[6]);
+/* read back (all nullable): idepth_min/max [n], quality [n], status [n], lastTraceUV [n][2], lastTracePixelInterval [n],
+ * color [n][8], weights [n][8], gradH [n][4] (row-major 2x2), energyTH [n] */
+int nalo_immature_get(nalo_immature* im, float* idepth_min, float* idepth_max, float* quality, int* status, float* lastTraceUV2,
+                      float* lastTracePixelInterval, float* color8, float* weights8, float* gradH4, float* energyTH);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,14 @@ def load():
         L.nalo_host_free.argtypes = [_P]
         L.nalo_batch_results_dev.restype = _P
         L.nalo_batch_results_dev.argtypes = [_P]
+        L.nalo_immature_create.argtypes = [_P, C.c_int, C.POINTER(_P)]
+        L.nalo_immature_destroy.argtypes = [_P]
+        L.nalo_immature_init.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P]
+        L.nalo_immature_set_state.argtypes = [_P, _P, _P, _P, _P]
+        L.nalo_immature_trace.argtypes = [_P, C.c_int, _P, _P, _P, _P, _P]
+        L.nalo_immature_get.argtypes = [_P] * 11
+        L.nalo_default_trace_params.argtypes = [_P]
+        L.nalo_default_trace_params.restype = None
         L.nalo_init_create.argtypes = [_P, C.c_int, C.POINTER(_P)]
         L.nalo_init_destroy.argtypes = [_P]
         L.nalo_init_set_points.argtypes = [_P, _P]
@@ -486,6 +494,65 @@ class Batch:
 
     def results_dev_ptr(self) -> int:
         return int(self.L.nalo_batch_results_dev(self.h_) or 0)
+
+
+class NaloTraceParams(C.Structure):
+    _fields_ = [("maxPixSearch", C.c_float), ("trace_stepsize", C.c_float), ("trace_GNIterations", C.c_int), ("trace_GNThreshold", C.c_float),
+                ("trace_extraSlackOnTH", C.c_float), ("trace_slackInterval", C.c_float), ("trace_minImprovementFactor", C.c_float),
+                ("minTraceTestRadius", C.c_int), ("outlierTH", C.c_float), ("outlierTHSumComponent", C.c_float), ("overallEnergyTHWeight", C.c_float)]
+
+
+class Immature:
+    """nalo_immature: the immature points of one host keyframe (ImmaturePoint constructor + traceOn) on the device."""
+
+    def __init__(self, ctx: "Context", max_points: int):
+        self.ctx, self.L = ctx, ctx.L
+        h_ = _P()
+        ctx._ck(self.L.nalo_immature_create(ctx.h_, C.c_int(max_points), C.byref(h_)))
+        self.h_ = h_
+        self.n = 0
+        ctx._children.add(self)
+
+    def close(self):
+        if getattr(self, "h_", None):
+            if getattr(self.ctx, "h_", None):
+                self.L.nalo_immature_destroy(self.h_)
+            self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self, host_slot, u, v, params=None):
+        u = np.ascontiguousarray(u, dtype=_f32)
+        v = np.ascontiguousarray(v, dtype=_f32)
+        self.n = len(u)
+        self.ctx._ck(self.L.nalo_immature_init(self.h_, C.c_int(host_slot), C.c_int(self.n), _ptr(u), _ptr(v), None if params is None else C.byref(params)))
+
+    def set_state(self, idepth_min=None, idepth_max=None, quality=None, status=None):
+        c = lambda a, dt: None if a is None else np.ascontiguousarray(a, dtype=dt)
+        a, b, q, s_ = c(idepth_min, _f32), c(idepth_max, _f32), c(quality, _f32), c(status, np.int32)
+        self.ctx._ck(self.L.nalo_immature_set_state(self.h_, _ptr(a), _ptr(b), _ptr(q), _ptr(s_)))
+
+    def trace(self, frame_slot, KRKi, Kt, aff, params=None):
+        K9 = np.ascontiguousarray(KRKi, dtype=_f32).reshape(-1)
+        t3 = np.ascontiguousarray(Kt, dtype=_f32)
+        a2 = np.ascontiguousarray(aff, dtype=_f32)
+        counts = np.zeros(6, dtype=np.int32)
+        self.ctx._ck(self.L.nalo_immature_trace(self.h_, C.c_int(frame_slot), _ptr(K9), _ptr(t3), _ptr(a2), None if params is None else C.byref(params),
+                                                _ptr(counts)))
+        return counts
+
+    def get(self):
+        n = max(self.n, 1)
+        d = dict(idepth_min=np.zeros(n, _f32), idepth_max=np.zeros(n, _f32), quality=np.zeros(n, _f32), status=np.zeros(n, np.int32),
+                 lastTraceUV=np.zeros((n, 2), _f32), lastTracePixelInterval=np.zeros(n, _f32), color=np.zeros((n, 8), _f32),
+                 weights=np.zeros((n, 8), _f32), gradH=np.zeros((n, 4), _f32), energyTH=np.zeros(n, _f32))
+        self.ctx._ck(self.L.nalo_immature_get(self.h_, *[_ptr(d[k]) for k in ("idepth_min", "idepth_max", "quality", "status", "lastTraceUV",
+                                                                             "lastTracePixelInterval", "color", "weights", "gradH", "energyTH")]))
+        return {k: a[: self.n] for k, a in d.items()}
 
 
 class NaloInitPoints(C.Structure):

@@ -426,3 +426,28 @@ def level_K(K, lvl):
     cxl = np.float32((np.float64(cx) + 0.5) / (1 << lvl) - 0.5)
     cyl = np.float32((np.float64(cy) + 0.5) / (1 << lvl) - 0.5)
     return np.array([fxl, fyl, cxl, cyl], dtype=np.float32)
+
+
+# ---------------------------------------------------------------- ImmaturePoint tracing
+def trace_geometry(K, pose7, aff=(0.0, 0.0)):
+    """hostToFrame_KRKi, hostToFrame_Kt, hostToFrame_affine as FullSystem::traceNewCoarse forms them (FullSystem.cpp:717-721)
+    for exposure 1 and a host with aff_g2l = 0: float K * float R * K^-1, K * float t, (exp(a), b)."""
+    fx, fy, cx, cy = K
+    Kf = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], dtype=np.float32)
+    Rf = quat_to_R(pose7[:4]).astype(np.float32)
+    tf = np.asarray(pose7[4:7], dtype=np.float32)
+    Kif = np.linalg.inv(Kf.astype(np.float64)).astype(np.float32)
+    KRKi = ((Kf @ Rf).astype(np.float32) @ Kif).astype(np.float32)
+    Kt = (Kf @ tf).astype(np.float32)
+    return KRKi, Kt, np.array([np.exp(aff[0]), aff[1]], dtype=np.float32)
+
+
+def immature_candidates(scene: Scene, step=7, border=8, seed=DEFAULT_SEED):
+    """Integer pixel positions on a jittered grid (stand-in for the selector's picks) + their ground-truth inverse depth."""
+    rng = np.random.default_rng(seed)
+    xs = np.arange(border, scene.w - border, step)
+    ys = np.arange(border, scene.h - border, step)
+    xx, yy = np.meshgrid(xs, ys)
+    xx = (xx + rng.integers(0, max(step - 1, 1), xx.shape)).ravel().clip(border, scene.w - border - 1)
+    yy = (yy + rng.integers(0, max(step - 1, 1), yy.shape)).ravel().clip(border, scene.h - border - 1)
+    return xx.astype(np.float32), yy.astype(np.float32), scene.idepth(xx, yy).astype(np.float32)

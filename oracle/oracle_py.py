@@ -455,3 +455,46 @@ def init_rki(K4, pose7):
     RKi, t = np.zeros(9, dtype=_f32), np.zeros(3, dtype=_f32)
     lib().oracle_init_rki(_ptr(np.ascontiguousarray(K4, dtype=_f32)), _ptr(np.ascontiguousarray(pose7, dtype=np.float64)), _ptr(RKi), _ptr(t))
     return RKi.reshape(3, 3), t
+
+
+class TraceSettings(C.Structure):
+    """Settings read by ImmaturePoint (settings.cpp:99-100,146,165-174 defaults)."""
+    _fields_ = [("maxPixSearch", C.c_float), ("stepsize", C.c_float), ("GNThreshold", C.c_float), ("extraSlackOnTH", C.c_float),
+                ("slackInterval", C.c_float), ("minImprovementFactor", C.c_float), ("huberTH", C.c_float), ("outlierTH", C.c_float),
+                ("outlierTHSumComponent", C.c_float), ("overallEnergyTHWeight", C.c_float), ("GNIterations", C.c_int),
+                ("minTraceTestRadius", C.c_int)]
+
+    @classmethod
+    def default(cls):
+        return cls(0.027, 1.0, 0.1, 1.2, 1.5, 2.0, 9.0, 12.0 * 12.0, 50.0 * 50.0, 1.0, 3, 2)
+
+
+IPS_GOOD, IPS_OOB, IPS_OUTLIER, IPS_SKIPPED, IPS_BADCONDITION, IPS_UNINITIALIZED = range(6)
+
+
+def immature_init(dI0, w, u, v, settings=None):
+    """ImmaturePoint constructor for the points (u, v) of one host frame. dI0: level-0 AoS {I,dx,dy} ([w*h,3])."""
+    S = settings or TraceSettings.default()
+    n = len(u)
+    u = np.ascontiguousarray(u, dtype=_f32)
+    v = np.ascontiguousarray(v, dtype=_f32)
+    color, weights, gradH, eth = np.zeros((n, 8), _f32), np.zeros((n, 8), _f32), np.zeros((n, 4), _f32), np.zeros(n, _f32)
+    lib().oracle_immature_init(C.c_int(w), _ptr(np.ascontiguousarray(dI0, dtype=_f32)), C.c_int(n), _ptr(u), _ptr(v), C.byref(S), _ptr(color),
+                               _ptr(weights), _ptr(gradH), _ptr(eth))
+    return dict(u=u, v=v, color=color, weights=weights, gradH=gradH, energyTH=eth, idepth_min=np.zeros(n, _f32),
+                idepth_max=np.full(n, np.nan, _f32), quality=np.full(n, 10000.0, _f32), status=np.full(n, IPS_UNINITIALIZED, np.int32),
+                lastTraceUV=np.zeros((n, 2), _f32), lastTracePixelInterval=np.zeros(n, _f32))
+
+
+def immature_trace(state, dI0_frame, w, h, KRKi, Kt, aff, settings=None):
+    """ImmaturePoint::traceOn for every point of `state` (dict from immature_init; updated IN PLACE and returned)."""
+    S = settings or TraceSettings.default()
+    n = len(state["u"])
+    K9 = np.ascontiguousarray(KRKi, dtype=_f32).reshape(-1)
+    t3 = np.ascontiguousarray(Kt, dtype=_f32)
+    a2 = np.ascontiguousarray(aff, dtype=_f32)
+    lib().oracle_immature_trace(C.c_int(w), C.c_int(h), _ptr(np.ascontiguousarray(dI0_frame, dtype=_f32)), C.c_int(n), _ptr(state["u"]), _ptr(state["v"]),
+                                _ptr(state["color"]), _ptr(state["weights"]), _ptr(state["gradH"]), _ptr(state["energyTH"]), _ptr(K9), _ptr(t3), _ptr(a2),
+                                C.byref(S), _ptr(state["idepth_min"]), _ptr(state["idepth_max"]), _ptr(state["quality"]), _ptr(state["status"]),
+                                _ptr(state["lastTraceUV"]), _ptr(state["lastTracePixelInterval"]))
+    return state
