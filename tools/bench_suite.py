@@ -80,7 +80,7 @@ def cpu_time(fn, budget_s=3.0, min_reps=3):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--rows", default="a1,select,ref,eval,track,multi,batch,ba,lin,init")
+    ap.add_argument("--rows", default="a1,select,ref,eval,track,multi,batch,ba,lin,init,trace")
     ap.add_argument("--batch-pairs", type=int, default=296)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "suite.json"))
@@ -420,6 +420,38 @@ def main():
             # algorithmic bytes per point: 29 in (u,v,id,iR,good,energy,outlierTH) + 8 px x 8 texels x 16 B (L2-resident frames) ; out 61
             add(f"f3 calcResAndGS lvl{lvl} npts={n}", d, wl, (29 + 8 * 8 * 16 + 61) * n, 8 * n, "residual", c, 1,
                 "two launches + 768 B readback; point state resident on the device")
+            I.close()
+
+    # ------------------------------------------------------------------ f4 ImmaturePoint constructor + traceOn
+    if "trace" in rows_wanted:
+        ctx.make_images(0, ref)
+        ctx.make_images(1, news[0])
+        dref_o, _ = O.make_images(ref, W, H, L, fast=True)
+        dnew_o, _ = O.make_images(news[0], W, H, L, fast=True)
+        for step in (15, 7):  # ~2 k points (one keyframe's immature points at preset 0) and ~9 k (a whole window's)
+            u, v, _idp = synth.immature_candidates(sc, step=step)
+            n = len(u)
+            I = capi.Immature(ctx, n)
+            pose = np.array(gts[0], dtype=np.float64)
+            pose[4:7] *= 3.0
+            KRKi, Kt, a2 = synth.trace_geometry(sc.K, pose, (0.0, 0.0))
+            d0, wl0, _ = T.run(lambda i: I.init(0, u, v), reps=10)
+            c0 = cpu_time(lambda: O.immature_init(dref_o[: W * H], W, u, v), budget_s=1.0)[0] if cpu else None
+            add(f"f4 ImmaturePoint ctor n={n}", d0, wl0, (8 + 8 * 4 * 16 + 88) * n, n, "point", c0, 1, "H2D of u, v inside")
+
+            def ftrace(i):
+                I.init(0, u, v)  # fresh filter state: every point does the full 34-step search
+                return I.trace(1, KRKi, Kt, a2)
+
+            d, wl, cnt = T.run(ftrace, reps=10)
+            c = None
+            if cpu:
+                def ctrace():
+                    so = O.immature_init(dref_o[: W * H], W, u, v)
+                    O.immature_trace(so, dnew_o[: W * H], W, H, KRKi, Kt, a2)
+                c = cpu_time(ctrace, budget_s=2.0)[0] - (c0 or 0.0)
+            add(f"f4 traceOn n={n} (first trace)", d - d0, wl - wl0, 0, n, "point", c, 1,
+                f"status counts {cnt.tolist()}; device time = (init + trace) - init; 24 B of counters read back")
             I.close()
 
     doc = dict(peak_hbm_gbs=peak, peak_source="MEASURED_PEAKS.json" if peaks else "fallback", gpu=torch.cuda.get_device_name(0),
