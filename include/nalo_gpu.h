@@ -325,6 +325,13 @@ int nalo_immature_destroy(nalo_immature* im);
  * [2, w-3) x [2, h-3)); state := idepth_min 0, idepth_max NaN, quality 10000, status UNINITIALIZED. energyTH = NaN marks a
  * point whose pattern touched a non-finite pixel (the reference deletes those). tp nullable = defaults. */
 int nalo_immature_init(nalo_immature* im, int host_slot, int n, const float* u, const float* v, const NaloTraceParams* tp);
+/* FullSystem::makeNewTraces after makeMaps (FullSystem.cpp:1677-1687): one ImmaturePoint per non-zero entry of the selection
+ * map that the last nalo_select_pixels / nalo_selector_select call left on the device for host_slot (pass map_out_host = NULL
+ * there to skip its 4*w*h-byte download), scanned in raster order over x in [3, w-4), y in [3, h-4) (patternPadding = 2);
+ * entries whose constructor ends with a non-finite energyTH are dropped as in the reference. *n_out = number of points;
+ * u_out / v_out / type_out (nullable, capacity max_points) = their pixel coordinates and map labels (my_type).
+ * NALO_E_STATE if the device map belongs to another frame, NALO_E_ARG if more than max_points entries qualify. */
+int nalo_immature_init_from_map(nalo_immature* im, int host_slot, const NaloTraceParams* tp, int* n_out, float* u_out, float* v_out, float* type_out);
 /* overwrite parts of the filter state (all nullable), e.g. after the host activated / dropped points */
 int nalo_immature_set_state(nalo_immature* im, const float* idepth_min, const float* idepth_max, const float* quality, const int* status);
 /* traceOn(frame, hostToFrame_KRKi, hostToFrame_Kt, hostToFrame_affine) for every point; KRKi row-major. counts6 (nullable)

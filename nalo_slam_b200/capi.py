@@ -102,6 +102,7 @@ def load():
         L.nalo_immature_destroy.argtypes = [_P]
         L.nalo_immature_init.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P]
         L.nalo_immature_set_state.argtypes = [_P, _P, _P, _P, _P]
+        L.nalo_immature_init_from_map.argtypes = [_P, C.c_int, _P, _P, _P, _P, _P]
         L.nalo_immature_trace.argtypes = [_P, C.c_int, _P, _P, _P, _P, _P]
         L.nalo_immature_get.argtypes = [_P] * 11
         L.nalo_default_trace_params.argtypes = [_P]
@@ -252,8 +253,9 @@ class Context:
         return dIp, ag
 
     # ---- a2-a4
-    def select_pixels(self, slot, density, currentPotential, recursionsLeft=1, thFactor=1.0):
-        m = np.zeros(self.w * self.h, dtype=_f32)
+    def select_pixels(self, slot, density, currentPotential, recursionsLeft=1, thFactor=1.0, want_map=True):
+        """PixelSelector::makeMaps. want_map=False leaves the map on the device (for Immature.init_from_map) and returns None for it."""
+        m = np.zeros(self.w * self.h, dtype=_f32) if want_map else None
         pot = C.c_int(currentPotential)
         n = C.c_int(0)
         self._ck(self.L.nalo_select_pixels(self.h_, C.c_int(slot), C.c_float(density), C.c_int(recursionsLeft), C.c_float(thFactor), C.byref(pot), _ptr(m), C.byref(n)))
@@ -511,6 +513,7 @@ class Immature:
         ctx._ck(self.L.nalo_immature_create(ctx.h_, C.c_int(max_points), C.byref(h_)))
         self.h_ = h_
         self.n = 0
+        self.max_points = max_points
         ctx._children.add(self)
 
     def close(self):
@@ -530,6 +533,18 @@ class Immature:
         v = np.ascontiguousarray(v, dtype=_f32)
         self.n = len(u)
         self.ctx._ck(self.L.nalo_immature_init(self.h_, C.c_int(host_slot), C.c_int(self.n), _ptr(u), _ptr(v), None if params is None else C.byref(params)))
+
+    def init_from_map(self, host_slot, params=None, want_lists=True):
+        """FullSystem::makeNewTraces on the selection map the last select_pixels call left on the device. Returns (n, u, v, type)."""
+        n = C.c_int(0)
+        cap = self.max_points
+        u, v, t = (np.zeros(cap, _f32), np.zeros(cap, _f32), np.zeros(cap, _f32)) if want_lists else (None, None, None)
+        self.ctx._ck(self.L.nalo_immature_init_from_map(self.h_, C.c_int(host_slot), None if params is None else C.byref(params), C.byref(n),
+                                                        _ptr(u), _ptr(v), _ptr(t)))
+        self.n = n.value
+        if not want_lists:
+            return self.n, None, None, None
+        return self.n, u[: self.n], v[: self.n], t[: self.n]
 
     def set_state(self, idepth_min=None, idepth_max=None, quality=None, status=None):
         c = lambda a, dt: None if a is None else np.ascontiguousarray(a, dtype=dt)

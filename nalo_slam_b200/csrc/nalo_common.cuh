@@ -141,6 +141,7 @@ struct nalo_ctx {
   int thsCap = 0;
   int histFrameSlot = -1;
   float* d_map = nullptr;
+  int mapSlot = -1;  // frame the selection map in d_map belongs to (-1: none)
   int* d_selScratch = nullptr;
   size_t selScratchInts = 0;
   long long launches = 0;

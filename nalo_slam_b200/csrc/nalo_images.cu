@@ -330,6 +330,7 @@ int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float
     NALO_CUDA(ctx, cudaEventRecord(ctx->frames[slot].built, ctx->stream));
     ctx->frames[slot].valid = true;
     if (ctx->histFrameSlot == slot) ctx->histFrameSlot = -1;
+    if (ctx->mapSlot == slot) ctx->mapSlot = -1;
     return NALO_OK;
   }
   // 6-level pyramids: two-kernel path (a level-5 pixel is coarser than the fused kernel's halo)
@@ -352,6 +353,7 @@ int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float
   NALO_CUDA(ctx, cudaEventRecord(ctx->frames[slot].built, ctx->stream));
   ctx->frames[slot].valid = true;
   if (ctx->histFrameSlot == slot) ctx->histFrameSlot = -1;
+  if (ctx->mapSlot == slot) ctx->mapSlot = -1;
   return NALO_OK;
 }
 
@@ -398,6 +400,7 @@ int nalo_images_run_multi(nalo_ctx* ctx, int n, const int* slots, const float* c
   for (int i = 0; i < n; i++) {
     ctx->frames[slots[i]].valid = true;
     if (ctx->histFrameSlot == slots[i]) ctx->histFrameSlot = -1;
+    if (ctx->mapSlot == slots[i]) ctx->mapSlot = -1;
   }
   return NALO_OK;
 }

@@ -5,12 +5,18 @@
 //
 // The immature points of one host keyframe live on the device (`nalo_immature`): pattern colours, weights, gradient
 // matrix, energy threshold from the constructor, and the depth-filter state (idepth interval, quality, status, last trace)
-// that traceOn updates for every new frame. One thread traces one point: projection of the idepth interval, the
-// conditioning test, the discrete epipolar search (<= 99 steps x 8 pattern pixels, energies kept in shared memory for the
-// second-best test), 3 Gauss-Newton refinement steps and the new interval. Every operation is a single fp32 op in the
-// reference's order (no contraction), so the whole per-point state is bit-identical to the CPU oracle. Points differ in
-// their number of search steps; the work is microseconds in total (a few thousand points per keyframe), so the kernel is
-// latency-, not throughput-minded: 64-thread CTAs spread the points over all SMs.
+// that traceOn updates for every new frame. Eight lanes trace one point (one lane per pattern pixel): projection of the
+// idepth interval, the conditioning test, the discrete epipolar search (<= 99 steps x 8 pattern pixels, energies kept in
+// shared memory for the second-best test), 3 Gauss-Newton refinement steps and the new interval. Every operation is a
+// single fp32 op in the reference's order (no contraction; the 8-term sums are replayed left to right from shuffled
+// terms), so the whole per-point state is bit-identical to the CPU oracle. Points differ in their number of search steps;
+// the work is microseconds in total (a few thousand points per keyframe), so the kernel is latency-, not
+// throughput-minded: a search step costs one round of bilinear loads instead of eight.
+//
+//   FullSystem::makeNewTraces      src/FullSystem/FullSystem.cpp:1655-1687   (map_row_count_kernel, map_compact_kernel)
+// builds the point list on the device from the selection map nalo_select_pixels left there (raster order, the reference's
+// border, points whose constructor yields a non-finite energyTH dropped), so neither the 1.87 MB map nor the coordinate
+// lists cross PCIe.
 #include <cstdlib>
 
 #include "nalo_common.cuh"
@@ -22,7 +28,9 @@ struct nalo_immature {
   float *d_u = nullptr, *d_v = nullptr, *d_color = nullptr, *d_weights = nullptr, *d_gradH = nullptr, *d_energyTH = nullptr;
   float *d_idMin = nullptr, *d_idMax = nullptr, *d_quality = nullptr, *d_uv = nullptr, *d_interval = nullptr;
   int* d_status = nullptr;
-  int* d_counts = nullptr;  // 6 status counters of the last trace
+  int* d_counts = nullptr;  // 6 status counters of the last trace; [6] number of points of a map-driven construction
+  float* d_type = nullptr;  // selection-map label (ImmaturePoint::my_type) of a map-driven construction
+  int* d_rowCount = nullptr;
 };
 
 namespace {
@@ -67,6 +75,7 @@ struct ImmSettings {
 struct ImmInitArgs {
   const float4* img;  // host frame, level 0
   int w, n;
+  const int* nDev;    // non-null: the number of points comes from the device (map-driven construction), n is the capacity
   const float *u, *v;
   float *color, *weights, *gradH, *energyTH, *idMin, *idMax, *quality, *uv, *interval;
   int* status;
@@ -75,7 +84,7 @@ struct ImmInitArgs {
 
 __global__ void __launch_bounds__(MT) immature_init_kernel(const __grid_constant__ ImmInitArgs a) {
   const int i = blockIdx.x * MT + threadIdx.x;
-  if (i >= a.n) return;
+  if (i >= (a.nDev ? min(*a.nDev, a.n) : a.n)) return;
   const float u = a.u[i], v = a.v[i];
   float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f;
   float* c = a.color + 8 * (size_t)i;
@@ -117,6 +126,76 @@ __global__ void __launch_bounds__(MT) immature_init_kernel(const __grid_constant
   a.interval[i] = 0.f;
 }
 
+// ---- FullSystem::makeNewTraces (FullSystem.cpp:1677-1687): point list from the selection map ----------------------------
+// x in [patternPadding+1, w-patternPadding-2), y likewise (patternPadding = 2, settings.h:237), raster order; a point whose
+// constructor would end with a non-finite energyTH (some pattern colour not finite) is deleted by the reference.
+__device__ __forceinline__ bool map_candidate(const float* __restrict__ map, const float4* __restrict__ img, int w, int h, int x, int y) {
+  if (x < 3 || x >= w - 4 || y < 3 || y >= h - 4) return false;
+  if (map[x + y * w] == 0.f) return false;
+  bool ok = true;
+#pragma unroll
+  for (int idx = 0; idx < 8; idx++) {  // ptc[0] of getInterpolatedElement33BiLin at an integer position
+    const float4* bp = img + ((x + kPat[idx][0]) + (y + kPat[idx][1]) * w);
+    const float tl = __ldg(bp).x, tr = __ldg(bp + 1).x, bl = __ldg(bp + w).x, br = __ldg(bp + w + 1).x;
+    const float leftInt = A_(M_(0.f, bl), M_(1.f, tl)), rightInt = A_(M_(0.f, br), M_(1.f, tr));
+    ok = ok && isfinite(A_(M_(0.f, rightInt), M_(1.f, leftInt)));
+  }
+  return ok;
+}
+
+__global__ void __launch_bounds__(256) map_row_count_kernel(const float* __restrict__ map, const float4* __restrict__ img, int w, int h,
+                                                            int* __restrict__ rowCount) {
+  const int y = blockIdx.x;
+  int c = 0;
+  for (int x0 = 0; x0 < w; x0 += 256) {
+    const int x = x0 + threadIdx.x;
+    c += __syncthreads_count(x < w && map_candidate(map, img, w, h, x, y));
+  }
+  if (threadIdx.x == 0) rowCount[y] = c;
+}
+
+__global__ void __launch_bounds__(256) map_compact_kernel(const float* __restrict__ map, const float4* __restrict__ img, int w, int h,
+                                                          const int* __restrict__ rowCount, int cap, float* __restrict__ u,
+                                                          float* __restrict__ v, float* __restrict__ type, int* __restrict__ nOut) {
+  __shared__ int sWarp[8];
+  __shared__ int sBase;
+  const int y = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int pre = 0;  // points of the rows above
+  for (int r = threadIdx.x; r < y; r += 256) pre += rowCount[r];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+  if (lane == 0) sWarp[wid] = pre;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < 8; k++) t += sWarp[k];
+    sBase = t;
+    if (y == h - 1) *nOut = t + rowCount[y];
+  }
+  __syncthreads();
+  for (int x0 = 0; x0 < w; x0 += 256) {
+    const int x = x0 + threadIdx.x;
+    const bool f = x < w && map_candidate(map, img, w, h, x, y);
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) sWarp[wid] = __popc(bal);
+    __syncthreads();
+    int ofs = sBase + __popc(bal & ((1u << lane) - 1u));
+    for (int k = 0; k < wid; k++) ofs += sWarp[k];
+    if (f && ofs < cap) {
+      u[ofs] = (float)x;
+      v[ofs] = (float)y;
+      type[ofs] = map[x + y * w];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int k = 0; k < 8; k++) t += sWarp[k];
+      sBase += t;
+    }
+    __syncthreads();
+  }
+}
+
 struct ImmTraceArgs {
   const float4* img;  // new frame, level 0
   int w, h, n;
@@ -128,12 +207,22 @@ struct ImmTraceArgs {
   ImmSettings S;
 };
 
-__global__ void __launch_bounds__(MT) immature_trace_kernel(const __grid_constant__ ImmTraceArgs a) {
-  __shared__ float sErr[100][MT];
+// One point per 8-lane group: lane `sub` owns pattern pixel `sub` (its bilinear lookups, residual, Huber weight); the
+// reference's left-to-right sums over the 8 pattern pixels are replayed in that order from shuffled terms, so every lane of
+// the group holds the bit-identical energy / H / b and takes the same branches. Everything outside the two pattern loops is
+// computed redundantly by the 8 lanes. Groups of one warp diverge freely (sub-warp shuffle masks).
+constexpr int TT = 128;     // threads per CTA
+constexpr int TP = TT / 8;  // points per CTA
+
+__global__ void __launch_bounds__(TT) immature_trace_kernel(const __grid_constant__ ImmTraceArgs a) {
+  __shared__ float sErr[TP][100];
   __shared__ int sCount[6];
   if (threadIdx.x < 6) sCount[threadIdx.x] = 0;
   __syncthreads();
-  const int p = blockIdx.x * MT + threadIdx.x;
+  const int lane = threadIdx.x & 31, sub = lane & 7, gsh = lane & 24;
+  const unsigned gmask = 0xFFu << gsh;
+  const int pl = threadIdx.x >> 3;
+  const int p = blockIdx.x * TP + pl;
   int st = -1;
   if (p < a.n) {
     st = a.status[p];
@@ -183,8 +272,8 @@ __global__ void __launch_bounds__(MT) immature_trace_kernel(const __grid_constan
         if (!(idMin < 0.f || (ptpMin[2] > 0.75f && ptpMin[2] < 1.5f))) { st = IPS_OOB; break; }
 
         float dx = M_(S.stepsize, S_(uMax, uMin)), dy = M_(S.stepsize, S_(vMax, vMin));
-        const float* G = a.gradH + 4 * (size_t)p;
-        const float G0 = G[0], G1 = G[1], G2 = G[2], G3 = G[3];
+        const float4 G = __ldg(reinterpret_cast<const float4*>(a.gradH) + p);
+        const float G0 = G.x, G1 = G.y, G2 = G.z, G3 = G.w;
         const float ea = A_(M_(A_(M_(dx, G0), M_(dy, G2)), dx), M_(A_(M_(dx, G1), M_(dy, G3)), dy));
         const float ndx = -dx;
         const float eb = A_(M_(A_(M_(dy, G0), M_(ndx, G2)), dy), M_(A_(M_(dy, G1), M_(ndx, G3)), ndx));
@@ -208,63 +297,75 @@ __global__ void __launch_bounds__(MT) immature_trace_kernel(const __grid_constan
         const float us = M_(uMin, 1000.f);
         const float randShift = S_(us, floorf(us));
         float ptx = S_(uMin, M_(randShift, dx)), pty = S_(vMin, M_(randShift, dy));
-        float rx[8], ry[8];
-#pragma unroll
-        for (int idx = 0; idx < 8; idx++) {
-          rx[idx] = A_(M_(a.KRKi[0], (float)kPat[idx][0]), M_(a.KRKi[1], (float)kPat[idx][1]));
-          ry[idx] = A_(M_(a.KRKi[3], (float)kPat[idx][0]), M_(a.KRKi[4], (float)kPat[idx][1]));
-        }
+        const float px = (float)kPat[sub][0], py = (float)kPat[sub][1];
+        const float rx = A_(M_(a.KRKi[0], px), M_(a.KRKi[1], py));  // rotatetPattern[sub]
+        const float ry = A_(M_(a.KRKi[3], px), M_(a.KRKi[4], py));
         if (!isfinite(dx) || !isfinite(dy)) { st = IPS_OOB; break; }
-        const float* col = a.color + 8 * (size_t)p;
-        const float* wts = a.weights + 8 * (size_t)p;
-        float tcol[8];  // (float)(aff0 * color + aff1)
-#pragma unroll
-        for (int idx = 0; idx < 8; idx++) tcol[idx] = A_(M_(a.aff[0], col[idx]), a.aff[1]);
+        const float tcol = A_(M_(a.aff[0], a.color[8 * (size_t)p + sub]), a.aff[1]);  // (float)(aff0 * color + aff1)
+        const float wt = a.weights[8 * (size_t)p + sub];
 
         float bestU = 0.f, bestV = 0.f, bestEnergy = 1e10f;
         int bestIdx = -1;
         if (numSteps >= 100) numSteps = 99;
+        float* err = sErr[pl];
         for (int i = 0; i < numSteps; i++) {
-          float energy = 0.f;
-#pragma unroll
-          for (int idx = 0; idx < 8; idx++) {
-            const float hit = interp31(a.img, A_(ptx, rx[idx]), A_(pty, ry[idx]), w);
-            if (!isfinite(hit)) { energy = A_(energy, 1e5f); continue; }
-            const float residual = S_(hit, tcol[idx]);
+          const float hit = interp31(a.img, A_(ptx, rx), A_(pty, ry), w);
+          float term = 1e5f;
+          if (isfinite(hit)) {
+            const float residual = S_(hit, tcol);
             const float ar = fabsf(residual);
             const float hw = ar < S.huberTH ? 1.f : D_(S.huberTH, ar);
-            energy = A_(energy, M_(M_(M_(hw, residual), residual), S_(2.f, hw)));
+            term = M_(M_(M_(hw, residual), residual), S_(2.f, hw));
           }
-          sErr[i][threadIdx.x] = energy;
+          float energy = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; k++) energy = A_(energy, __shfl_sync(gmask, term, k, 8));
+          if (sub == 0) err[i] = energy;
           if (energy < bestEnergy) { bestU = ptx; bestV = pty; bestEnergy = energy; bestIdx = i; }
           ptx = A_(ptx, dx);
           pty = A_(pty, dy);
         }
-        float secondBest = 1e10f;
-        for (int i = 0; i < numSteps; i++) {
-          const float e = sErr[i][threadIdx.x];
+        __syncwarp(gmask);
+        float secondBest = 1e10f;  // min over the eligible non-NaN energies (the reference's `e < secondBest` scan)
+        for (int i = sub; i < numSteps; i += 8) {
+          const float e = err[i];
           if ((i < bestIdx - S.minTraceTestRadius || i > bestIdx + S.minTraceTestRadius) && e < secondBest) secondBest = e;
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          const float other = __shfl_xor_sync(gmask, secondBest, o, 8);
+          if (other < secondBest) secondBest = other;
         }
         const float newQuality = D_(secondBest, bestEnergy);
         const float q = a.quality[p];
-        if (newQuality < q || numSteps > 10) a.quality[p] = newQuality;
+        __syncwarp(gmask);  // everyone has read quality[p] before lane 0 may overwrite it
+        if ((newQuality < q || numSteps > 10) && sub == 0) a.quality[p] = newQuality;
 
         float uBak = bestU, vBak = bestV, stepBack = 0.f;
         if (S.GNIterations > 0) bestEnergy = 1e5f;
         for (int it = 0; it < S.GNIterations; it++) {
+          float h0, h1, h2;
+          interp33(a.img, A_(bestU, rx), A_(bestV, ry), w, h0, h1, h2);
+          const bool fin = isfinite(h0);
+          const float residual = S_(h0, tcol);
+          const float dRes = A_(M_(dx, h1), M_(dy, h2));
+          const float ar = fabsf(residual);
+          const float hw = ar < S.huberTH ? 1.f : D_(S.huberTH, ar);
+          const float hT = M_(M_(hw, dRes), dRes);
+          const float bT = M_(M_(hw, residual), dRes);
+          const float eT = M_(M_(M_(M_(M_(wt, wt), hw), residual), residual), S_(2.f, hw));
+          const unsigned fm = __ballot_sync(gmask, fin) >> gsh;
           float H = 1.f, bb = 0.f, energy = 0.f;
 #pragma unroll
-          for (int idx = 0; idx < 8; idx++) {
-            float h0, h1, h2;
-            interp33(a.img, A_(bestU, rx[idx]), A_(bestV, ry[idx]), w, h0, h1, h2);
-            if (!isfinite(h0)) { energy = A_(energy, 1e5f); continue; }
-            const float residual = S_(h0, tcol[idx]);
-            const float dRes = A_(M_(dx, h1), M_(dy, h2));
-            const float ar = fabsf(residual);
-            const float hw = ar < S.huberTH ? 1.f : D_(S.huberTH, ar);
-            H = A_(H, M_(M_(hw, dRes), dRes));
-            bb = A_(bb, M_(M_(hw, residual), dRes));
-            energy = A_(energy, M_(M_(M_(M_(M_(wts[idx], wts[idx]), hw), residual), residual), S_(2.f, hw)));
+          for (int k = 0; k < 8; k++) {
+            const float hk = __shfl_sync(gmask, hT, k, 8), bk = __shfl_sync(gmask, bT, k, 8), ek = __shfl_sync(gmask, eT, k, 8);
+            if (fm & (1u << k)) {
+              H = A_(H, hk);
+              bb = A_(bb, bk);
+              energy = A_(energy, ek);
+            } else {
+              energy = A_(energy, 1e5f);
+            }
           }
           if (energy > bestEnergy) {
             stepBack = M_(stepBack, 0.5f);
@@ -299,20 +400,24 @@ __global__ void __launch_bounds__(MT) immature_trace_kernel(const __grid_constan
           nMax = D_(S_(M_(pr[2], hi), pr[1]), S_(a.Kt[1], M_(a.Kt[2], hi)));
         }
         if (nMin > nMax) { const float t = nMin; nMin = nMax; nMax = t; }
-        a.idMin[p] = nMin;  // (the reference assigns the members before the validity test below)
-        a.idMax[p] = nMax;
+        if (sub == 0) {  // (the reference assigns the members before the validity test below)
+          a.idMin[p] = nMin;
+          a.idMax[p] = nMax;
+        }
         if (!isfinite(nMin) || !isfinite(nMax) || (nMax < 0.f)) { st = IPS_OUTLIER; break; }
         interval = M_(2.f, errorInPixel);
         uvx = bestU;
         uvy = bestV;
         st = IPS_GOOD;
       } while (false);
-      a.status[p] = st;
-      a.uv[2 * p] = uvx;
-      a.uv[2 * p + 1] = uvy;
-      a.interval[p] = interval;
+      if (sub == 0) {
+        a.status[p] = st;
+        a.uv[2 * p] = uvx;
+        a.uv[2 * p + 1] = uvy;
+        a.interval[p] = interval;
+      }
     }
-    atomicAdd(&sCount[st], 1);
+    if (sub == 0) atomicAdd(&sCount[st], 1);
   }
   __syncthreads();
   if (threadIdx.x < 6 && sCount[threadIdx.x]) atomicAdd(&a.counts[threadIdx.x], sCount[threadIdx.x]);
@@ -354,7 +459,7 @@ int nalo_immature_destroy(nalo_immature* im) {
   cudaSetDevice(im->ctx->device);
   cudaFree(im->d_u); cudaFree(im->d_v); cudaFree(im->d_color); cudaFree(im->d_weights); cudaFree(im->d_gradH); cudaFree(im->d_energyTH);
   cudaFree(im->d_idMin); cudaFree(im->d_idMax); cudaFree(im->d_quality); cudaFree(im->d_uv); cudaFree(im->d_interval); cudaFree(im->d_status);
-  cudaFree(im->d_counts);
+  cudaFree(im->d_counts); cudaFree(im->d_type); cudaFree(im->d_rowCount);
   delete im;
   return NALO_OK;
 }
@@ -379,6 +484,8 @@ int nalo_immature_create(nalo_ctx* ctx, int max_points, nalo_immature** out) {
   MCK(cudaMalloc(&im->d_gradH, 16 * n)); MCK(cudaMalloc(&im->d_energyTH, 4 * n)); MCK(cudaMalloc(&im->d_idMin, 4 * n)); MCK(cudaMalloc(&im->d_idMax, 4 * n));
   MCK(cudaMalloc(&im->d_quality, 4 * n)); MCK(cudaMalloc(&im->d_uv, 8 * n)); MCK(cudaMalloc(&im->d_interval, 4 * n)); MCK(cudaMalloc(&im->d_status, 4 * n));
   MCK(cudaMalloc(&im->d_counts, sizeof(int) * 8));
+  MCK(cudaMalloc(&im->d_type, 4 * n));
+  MCK(cudaMalloc(&im->d_rowCount, sizeof(int) * (size_t)ctx->h0));
   MCK(cudaMemsetAsync(im->d_color, 0, 32 * n, ctx->stream));
   MCK(cudaMemsetAsync(im->d_weights, 0, 32 * n, ctx->stream));
 #undef MCK
@@ -404,13 +511,55 @@ int nalo_immature_init(nalo_immature* im, int host_slot, int n, const float* u, 
   NALO_CUDA(ctx, cudaMemcpyAsync(im->d_v, v, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
   ImmInitArgs a;
   a.img = ctx->frames[host_slot].pix + ctx->loff[0];
-  a.w = ctx->w0; a.n = n; a.u = im->d_u; a.v = im->d_v;
+  a.w = ctx->w0; a.n = n; a.nDev = nullptr; a.u = im->d_u; a.v = im->d_v;
   a.color = im->d_color; a.weights = im->d_weights; a.gradH = im->d_gradH; a.energyTH = im->d_energyTH; a.idMin = im->d_idMin; a.idMax = im->d_idMax;
   a.quality = im->d_quality; a.uv = im->d_uv; a.interval = im->d_interval; a.status = im->d_status;
   a.S = make_settings(ctx, tp);
   immature_init_kernel<<<(n + MT - 1) / MT, MT, 0, st>>>(a);
   NALO_CHECK_LAUNCH(ctx);
   NALO_CUDA(ctx, cudaStreamSynchronize(st));  // u, v may go away
+  return NALO_OK;
+}
+
+int nalo_immature_init_from_map(nalo_immature* im, int host_slot, const NaloTraceParams* tp, int* n_out, float* u_out, float* v_out, float* type_out) {
+  if (!im || !n_out) return NALO_E_ARG;
+  nalo_ctx* ctx = im->ctx;
+  if (host_slot < 0 || host_slot >= ctx->maxFrames || !ctx->frames[host_slot].valid)
+    return nalo_fail(ctx, NALO_E_STATE, "nalo_immature_init_from_map: frame slot %d not built", host_slot);
+  if (ctx->mapSlot != host_slot)
+    return nalo_fail(ctx, NALO_E_STATE, "nalo_immature_init_from_map: the selection map on the device belongs to slot %d, not %d (run nalo_select_pixels first)",
+                     ctx->mapSlot, host_slot);
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int w = ctx->w0, h = ctx->h0;
+  const float4* img = ctx->frames[host_slot].pix + ctx->loff[0];
+  im->n = 0;
+  im->hostSlot = host_slot;
+  map_row_count_kernel<<<h, 256, 0, st>>>(ctx->d_map, img, w, h, im->d_rowCount);
+  NALO_CHECK_LAUNCH(ctx);
+  map_compact_kernel<<<h, 256, 0, st>>>(ctx->d_map, img, w, h, im->d_rowCount, im->maxPts, im->d_u, im->d_v, im->d_type, im->d_counts + 6);
+  NALO_CHECK_LAUNCH(ctx);
+  ImmInitArgs a;
+  a.img = img;
+  a.w = w; a.n = im->maxPts; a.nDev = im->d_counts + 6; a.u = im->d_u; a.v = im->d_v;
+  a.color = im->d_color; a.weights = im->d_weights; a.gradH = im->d_gradH; a.energyTH = im->d_energyTH; a.idMin = im->d_idMin; a.idMax = im->d_idMax;
+  a.quality = im->d_quality; a.uv = im->d_uv; a.interval = im->d_interval; a.status = im->d_status;
+  a.S = make_settings(ctx, tp);
+  immature_init_kernel<<<(im->maxPts + MT - 1) / MT, MT, 0, st>>>(a);
+  NALO_CHECK_LAUNCH(ctx);
+  int* hn = ctx->h_counts + 56;
+  NALO_CUDA(ctx, cudaMemcpyAsync(hn, im->d_counts + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
+  NALO_CUDA(ctx, cudaStreamSynchronize(st));
+  const int n = *hn;
+  if (n > im->maxPts) return nalo_fail(ctx, NALO_E_ARG, "nalo_immature_init_from_map: %d points selected, capacity %d", n, im->maxPts);
+  im->n = n;
+  *n_out = n;
+  if (n > 0 && (u_out || v_out || type_out)) {
+    if (u_out) NALO_CUDA(ctx, cudaMemcpyAsync(u_out, im->d_u, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (v_out) NALO_CUDA(ctx, cudaMemcpyAsync(v_out, im->d_v, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (type_out) NALO_CUDA(ctx, cudaMemcpyAsync(type_out, im->d_type, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    NALO_CUDA(ctx, cudaStreamSynchronize(st));
+  }
   return NALO_OK;
 }
 
@@ -451,7 +600,7 @@ int nalo_immature_trace(nalo_immature* im, int frame_slot, const float KRKi9[9],
   a.counts = im->d_counts;
   a.S = make_settings(ctx, tp);
   NALO_CUDA(ctx, cudaMemsetAsync(im->d_counts, 0, sizeof(int) * 8, st));
-  immature_trace_kernel<<<(n + MT - 1) / MT, MT, 0, st>>>(a);
+  immature_trace_kernel<<<(n + TP - 1) / TP, TT, 0, st>>>(a);
   NALO_CHECK_LAUNCH(ctx);
   if (counts6) {
     NALO_CUDA(ctx, cudaMemcpyAsync(counts6, im->d_counts, sizeof(int) * 6, cudaMemcpyDeviceToHost, st));

@@ -504,6 +504,7 @@ int run_make_hists(nalo_ctx* ctx, int slot) {
 
 // select() into ctx->d_map; n3 = (n2,n3,n4) returned through pinned h_counts[32..34]
 int run_select(nalo_ctx* ctx, int slot, int pot, float thFactor, int n3[3]) {
+  ctx->mapSlot = slot;
   if (pot < 1) pot = 1;
   SelGeom g = make_geom(ctx, pot, thFactor);
   const int nB4 = g.nX4 * g.nY4;

@@ -98,6 +98,38 @@ void oracle_immature_init(int w, const float* dI, int n, const float* u, const f
   }
 }
 
+// FullSystem::makeNewTraces after makeMaps (FullSystem.cpp:1677-1687): raster scan of the selection map over
+// x in [patternPadding+1, w-patternPadding-2), y likewise (patternPadding = 2, util/settings.h), one ImmaturePoint per
+// non-zero entry, points whose constructor ends with a non-finite energyTH deleted. Outputs have capacity `cap` points;
+// returns the number of points kept (may exceed cap: then only the first cap are written).
+int oracle_make_new_traces(int w, int h, const float* dI, const float* map, int cap, const OracleTraceSettings* S, float* u, float* v,
+                           float* type, float* color, float* weights, float* gradH, float* energyTH) {
+  const int patternPadding = 2;
+  int n = 0;
+  for (int y = patternPadding + 1; y < h - patternPadding - 2; y++)
+    for (int x = patternPadding + 1; x < w - patternPadding - 2; x++) {
+      const int i = x + y * w;
+      if (map[i] == 0) continue;
+      const float fx = (float)x, fy = (float)y;
+      float c[8] = {0, 0, 0, 0, 0, 0, 0, 0}, wt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, g[4], e;
+      oracle_immature_init(w, dI, 1, &fx, &fy, S, c, wt, g, &e);
+      if (!std::isfinite(e)) continue;
+      if (n < cap) {
+        u[n] = fx;
+        v[n] = fy;
+        type[n] = map[i];
+        for (int k = 0; k < 8; k++) {
+          color[8 * (size_t)n + k] = c[k];
+          weights[8 * (size_t)n + k] = wt[k];
+        }
+        for (int k = 0; k < 4; k++) gradH[4 * (size_t)n + k] = g[k];
+        energyTH[n] = e;
+      }
+      n++;
+    }
+  return n;
+}
+
 // traceOn for n points of one host frame into `frame` (level-0 AoS {I,dx,dy}, size w x h).
 // In/out per point: idepth_min, idepth_max, quality, status, lastTraceUV [n][2], lastTracePixelInterval.
 void oracle_immature_trace(int w, int h, const float* dI, int n, const float* pu, const float* pv, const float* color, const float* weights,

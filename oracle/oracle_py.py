@@ -486,6 +486,23 @@ def immature_init(dI0, w, u, v, settings=None):
                 lastTraceUV=np.zeros((n, 2), _f32), lastTracePixelInterval=np.zeros(n, _f32))
 
 
+def make_new_traces(dI0, w, h, sel_map, cap=None, settings=None):
+    """FullSystem::makeNewTraces after makeMaps: the ImmaturePoints of a selection map (dict like immature_init + "type")."""
+    S = settings or TraceSettings.default()
+    sel_map = np.ascontiguousarray(sel_map, dtype=_f32).reshape(-1)
+    cap = int(cap if cap is not None else np.count_nonzero(sel_map) + 1)
+    u, v, t = np.zeros(cap, _f32), np.zeros(cap, _f32), np.zeros(cap, _f32)
+    color, weights, gradH, eth = np.zeros((cap, 8), _f32), np.zeros((cap, 8), _f32), np.zeros((cap, 4), _f32), np.zeros(cap, _f32)
+    f = lib().oracle_make_new_traces
+    f.restype = C.c_int
+    n = f(C.c_int(w), C.c_int(h), _ptr(np.ascontiguousarray(dI0, dtype=_f32)), _ptr(sel_map), C.c_int(cap), C.byref(S), _ptr(u), _ptr(v), _ptr(t),
+          _ptr(color), _ptr(weights), _ptr(gradH), _ptr(eth))
+    m = min(n, cap)
+    return n, dict(u=u[:m], v=v[:m], type=t[:m], color=color[:m], weights=weights[:m], gradH=gradH[:m], energyTH=eth[:m],
+                   idepth_min=np.zeros(m, _f32), idepth_max=np.full(m, np.nan, _f32), quality=np.full(m, 10000.0, _f32),
+                   status=np.full(m, IPS_UNINITIALIZED, np.int32), lastTraceUV=np.zeros((m, 2), _f32), lastTracePixelInterval=np.zeros(m, _f32))
+
+
 def immature_trace(state, dI0_frame, w, h, KRKi, Kt, aff, settings=None):
     """ImmaturePoint::traceOn for every point of `state` (dict from immature_init; updated IN PLACE and returned)."""
     S = settings or TraceSettings.default()

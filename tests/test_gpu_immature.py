@@ -92,3 +92,42 @@ def test_constructor_non_finite_and_errors(oracle):
         I.close()
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("w,h,L,density", [(320, 192, 4, 600), (1241, 376, 5, 4000)])
+def test_make_new_traces_from_device_map(oracle, w, h, L, density):
+    """FullSystem::makeNewTraces (FullSystem.cpp:1655-1687): makeMaps leaves the map on the device, the point list is built
+    there (raster order, reference window, non-finite constructors dropped) -- list, constructor state and the first trace
+    bit-exact vs the oracle chain fed with the oracle's map."""
+    sc, ref, news = _frames(oracle, w, h, L, seed=33, n_new=1)
+    ref = ref.copy()
+    ref[h // 2 : h // 2 + 3, w // 2 : w // 2 + 40] = np.nan  # some selected pixels sit next to non-finite ones
+    ctx = capi.Context(w, h, L, device=0, max_frames=2)
+    try:
+        dref, ag = ctx.make_images(0, ref, want_host=True)
+        n_sel, m_host, pot = ctx.select_pixels(0, density, 3)
+        n_sel2, none_map, pot2 = ctx.select_pixels(0, density, 3, want_map=False)
+        assert none_map is None and (n_sel2, pot2) == (n_sel, pot)
+        n_o, so = oracle.make_new_traces(dref[: w * h], w, h, m_host)
+        I = capi.Immature(ctx, n_o + 5)
+        n, u, v, t = I.init_from_map(0)
+        assert n == n_o and 0 < n <= n_sel
+        assert np.array_equal(u, so["u"]) and np.array_equal(v, so["v"]) and np.array_equal(t, so["type"])
+        _check(I.get(), so, CTOR + STATE)
+        gt, aff, img = news[0]
+        dnew, _ = ctx.make_images(1, img, want_host=True)
+        KRKi, Kt, a2 = synth.trace_geometry(sc.K, gt, aff)
+        oracle.immature_trace(so, dnew[: w * h], w, h, KRKi, Kt, a2)
+        counts = I.trace(1, KRKi, Kt, a2)
+        _check(I.get(), so, STATE)
+        assert np.array_equal(counts, np.bincount(so["status"], minlength=6))
+        small = capi.Immature(ctx, 16)
+        with pytest.raises(capi.NaloError):
+            small.init_from_map(0)  # over capacity
+        ctx.make_images(0, ref)     # rebuilding the frame invalidates the device map
+        with pytest.raises(capi.NaloError):
+            I.init_from_map(0)
+        small.close()
+        I.close()
+    finally:
+        ctx.close()

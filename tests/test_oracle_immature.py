@@ -109,3 +109,34 @@ def test_trace_oob_when_projection_leaves_the_image(scene_pair, oracle):
     KRKi[0, 2] += 400.0  # shifts every projection out of the image
     oracle.immature_trace(st, dnew, W, H, KRKi, Kt, a2)
     assert np.all(st["status"] == oracle.IPS_OOB) and np.all(st["lastTraceUV"] == -1) and np.all(st["lastTracePixelInterval"] == 0)
+
+
+def test_make_new_traces_kat(oracle):
+    """FullSystem::makeNewTraces (FullSystem.cpp:1677-1687): raster order, the reference's window [3, w-4) x [3, h-4), points with a
+    non-finite constructor dropped -- against an independent numpy selection + the per-point constructor."""
+    from nalo_slam_b200 import synth
+
+    w, h, L = 320, 192, 4
+    img = synth.render_ref(synth.make_scene(w, h, seed=5)).copy()
+    img[60:64, 100:104] = np.nan
+    d, _ = oracle.make_images(img, w, h, L)
+    rng = np.random.default_rng(0)
+    m = np.zeros(w * h, np.float32)
+    idx = rng.choice(w * h, 3000, replace=False)
+    m[idx] = rng.choice([1, 2, 4], 3000)
+    m[[3 + 3 * w, (w - 5) + (h - 5) * w, 2 + 50 * w, (w - 4) + 50 * w, 50 + 2 * w, 50 + (h - 4) * w, 101 + 61 * w]] = 1  # window corners in, just outside out, NaN out
+    n, st = oracle.make_new_traces(d[: w * h], w, h, m)
+    ys, xs = np.nonzero(m.reshape(h, w))  # raster order
+    keep = (xs >= 3) & (xs < w - 4) & (ys >= 3) & (ys < h - 4)
+    so = oracle.immature_init(d[: w * h], w, xs[keep].astype(np.float32), ys[keep].astype(np.float32))
+    fin = np.isfinite(so["energyTH"])
+    assert 0 < fin.sum() < keep.sum() < len(xs)
+    assert n == fin.sum() == len(st["u"])
+    assert np.array_equal(st["u"], xs[keep][fin]) and np.array_equal(st["v"], ys[keep][fin])
+    assert np.array_equal(st["type"], m.reshape(h, w)[ys[keep][fin], xs[keep][fin]])
+    assert (st["u"][0], st["v"][0]) == (3, 3) and (st["u"][-1], st["v"][-1]) == (w - 5, h - 5)
+    assert not np.any((st["u"] == 101) & (st["v"] == 61))
+    for k in ("color", "weights", "gradH", "energyTH"):
+        assert np.array_equal(st[k], so[k][fin]), k
+    n2, st2 = oracle.make_new_traces(d[: w * h], w, h, m, cap=10)  # over capacity: count still complete
+    assert n2 == n and len(st2["u"]) == 10 and np.array_equal(st2["u"], st["u"][:10])

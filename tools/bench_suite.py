@@ -400,7 +400,7 @@ def main():
     if "init" in rows_wanted:
         ctx.make_images(0, ref)
         ctx.make_images(1, news[0])
-        dref_o, _ = O.make_images(ref, W, H, L, fast=True)
+        dref_o, agref_o = O.make_images(ref, W, H, L, fast=True)
         dnew_o, _ = O.make_images(news[0], W, H, L, fast=True)
         offs = np.cumsum([0] + [(W >> l) * (H >> l) for l in range(L)])
         for lvl, step in ((0, 6), (1, 2), (2, 1)):  # ~0.03*w*h points at level 0 (setFirst :804-811), denser coarse levels
@@ -426,8 +426,30 @@ def main():
     if "trace" in rows_wanted:
         ctx.make_images(0, ref)
         ctx.make_images(1, news[0])
-        dref_o, _ = O.make_images(ref, W, H, L, fast=True)
+        dref_o, agref_o = O.make_images(ref, W, H, L, fast=True)
         dnew_o, _ = O.make_images(news[0], W, H, L, fast=True)
+        # FullSystem::makeNewTraces: makeMaps + one ImmaturePoint per selected pixel, the map staying on the device
+        Im = capi.Immature(ctx, 20000)
+        nmk = [0]
+
+        def fmk(i):
+            ctx.select_pixels(0, 4000.0, 3, want_map=False)
+            nmk[0] = Im.init_from_map(0)[0]
+
+        d, wl, _ = T.run(fmk, reps=10)
+        c = None
+        if cpu:
+            off = O.level_offsets(W, H, L)[0]
+
+            def cmk():
+                S = O.Selector(W, H, fast=True)
+                _n, m = S.make_maps(dref_o, agref_o, off, 4000.0)[:2]
+                O.make_new_traces(dref_o[: W * H], W, H, m)
+
+            c = cpu_time(cmk, budget_s=2.0)[0]
+        add(f"f4 makeNewTraces (makeMaps + point list + constructors) n={nmk[0]}", d, wl, int(12.3e6) + (8 * 4 * 16 + 100) * nmk[0], 1, "frame", c, 1,
+            "map stays on the device; D2H = 3 lists of n floats")
+        Im.close()
         for step in (15, 7):  # ~2 k points (one keyframe's immature points at preset 0) and ~9 k (a whole window's)
             u, v, _idp = synth.immature_candidates(sc, step=step)
             n = len(u)
