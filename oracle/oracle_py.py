@@ -410,6 +410,57 @@ def linearize(prob, dI_frames, rec_init=None, huberTH=9.0, outlierTHSumComponent
     return dict(rec=rec, state=state, energy=en, energy_outlier=eno, center=center, proj=proj)
 
 
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ba_stitch_top(nf, accH, adHost, adTarget, usePrior=False, cPrior=None, cDeltaF=None, framePrior=None, frameDeltaPrior=None):
+    """AccumulatedTopHessianSSE::stitchDoubleMT (non-MT branch): (H [N,N], b [N]), N = 4 + 8 nf."""
+    N = 4 + 8 * nf
+    H, b = np.zeros((N, N)), np.zeros(N)
+    cP = _d(cPrior if cPrior is not None else np.zeros(4))
+    cD = np.ascontiguousarray(cDeltaF if cDeltaF is not None else np.zeros(4), dtype=_f32)
+    fP = _d(framePrior if framePrior is not None else np.zeros((nf, 8)))
+    fD = _d(frameDeltaPrior if frameDeltaPrior is not None else np.zeros((nf, 8)))
+    lib().oracle_ba_stitch_top(C.c_int(nf), _ptr(_d(accH)), _ptr(_d(adHost)), _ptr(_d(adTarget)), C.c_int(1 if usePrior else 0), _ptr(cP), _ptr(cD),
+                               _ptr(fP), _ptr(fD), _ptr(H), _ptr(b))
+    return H, b
+
+
+def ba_stitch_sc(nf, accD, accE, accEB, accHcc, accbc, adHost, adTarget):
+    """AccumulatedSCHessianSSE::stitchDoubleMT (non-MT branch)."""
+    N = 4 + 8 * nf
+    H, b = np.zeros((N, N)), np.zeros(N)
+    lib().oracle_ba_stitch_sc(C.c_int(nf), _ptr(_d(accD)), _ptr(_d(accE)), _ptr(_d(accEB)), _ptr(_d(accHcc)), _ptr(_d(accbc)), _ptr(_d(adHost)),
+                              _ptr(_d(adTarget)), _ptr(H), _ptr(b))
+    return H, b
+
+
+def ldlt_solve_n(A, rhs):
+    """Eigen::LDLT<MatrixXd, Lower> compute + solve, run-time size."""
+    A = _d(A)
+    n = A.shape[0]
+    x = np.zeros(n)
+    lib().oracle_ldlt_solve_n(C.c_int(n), _ptr(A), _ptr(_d(rhs)), _ptr(x))
+    return x
+
+
+def ba_solve(nf, HA, bA, HL, bL, Hsc, bsc, HM, bM, delta, lam=1e-5):
+    """EnergyFunctional::solveSystemF, default solver mode: returns (lastHS, lastbS, x)."""
+    N = 4 + 8 * nf
+    lastHS, lastbS, x = np.zeros((N, N)), np.zeros(N), np.zeros(N)
+    lib().oracle_ba_solve(C.c_int(nf), _ptr(_d(HA)), _ptr(_d(bA)), _ptr(_d(HL)), _ptr(_d(bL)), _ptr(_d(Hsc)), _ptr(_d(bsc)), _ptr(_d(HM)), _ptr(_d(bM)),
+                          _ptr(_d(delta)), C.c_double(lam), _ptr(lastHS), _ptr(lastbS), _ptr(x))
+    return lastHS, lastbS, x
+
+
+def ba_xad(nf, x, adHost, adTarget):
+    """resubstituteF_MT prologue: (xc [4] f32, xAd [nf*nf, 8] f32 indexed host*nf + target)."""
+    xc, xAd = np.zeros(4, _f32), np.zeros((nf * nf, 8), _f32)
+    lib().oracle_ba_xad(C.c_int(nf), _ptr(_d(x)), _ptr(_d(adHost)), _ptr(_d(adTarget)), _ptr(xc), _ptr(xAd))
+    return xc, xAd
+
+
 def ba_resubstitute(prob, JpJdF, ppA, ppL, perPointSC, xc, xAd):
     """EnergyFunctional::resubstituteFPt: per-point step = -(bdSumF - xc.Hcd - sum_r xAd[h*nf+t].JpJdF_r) * HdiF."""
     nP = prob["n_pts"]
