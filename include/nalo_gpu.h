@@ -231,6 +231,31 @@ int nalo_ba_accumulate_sc(nalo_ba* ba, int shiftPriorToZero, int useL, double* a
  * * HdiF (0 for points without active residuals). xAd: [nf*nf][8], indexed hostIDX*nf + targetIDX as in the reference. */
 int nalo_ba_resubstitute(nalo_ba* ba, const float xc4[4], const float* xAd, int useL, float* step_out);
 
+/* f2: the fp64 tail of a BA iteration on the device, from the accumulator blocks the accumulate calls above left there:
+ * AccumulatedTopHessianSSE::stitchDoubleMT for the active (mode 0, usePrior = false) and the linearised (mode 1, usePrior = true;
+ * zero blocks if no mode-1/2 pass ran) set (AccumulatedTopHessian.cpp:241-303, .h:91-139), AccumulatedSCHessianSSE::stitchDoubleMT
+ * (AccumulatedSCHessian.cpp:78-148, .h:93-133), then EnergyFunctional::solveSystemF (EnergyFunctional.cpp:776-908) in the default
+ * solver mode (SOLVER_FIX_LAMBDA | SOLVER_ORTHOGONALIZE_X_LATER, util/settings.cpp:69: HFinal = HL + HM + HA with the diagonal
+ * times (1 + lambda) minus H_sc / (1 + lambda), bFinal = bL + (bM + HM delta) + bA - b_sc, Jacobi scaling 1/sqrt(diag + 10),
+ * Eigen's pivoted LDLT). N = 4 + 8 nf; matrices row-major. The nullspace orthogonalisation of x (iteration >= 2) stays with
+ * the caller: pass the orthogonalised x to nalo_ba_resubstitute, or keep the device's x with nalo_ba_resubstitute_x. */
+typedef struct NaloBASolveInput {
+  const double* adHost;            /* [nf*nf][8][8]  EnergyFunctional::adHost, index h + nf*t (EnergyFunctional.cpp:47-86) */
+  const double* adTarget;          /* [nf*nf][8][8] */
+  const double* cPrior;            /* [4]      EnergyFunctional::cPrior (nullable = 0) */
+  const double* frame_prior;       /* [nf][8]  EFFrame::prior (nullable = 0) */
+  const double* frame_delta_prior; /* [nf][8]  EFFrame::delta_prior (nullable = 0) */
+  const double* HM;                /* [N][N]   marginalisation prior (nullable = 0) */
+  const double* bM;                /* [N] */
+  const double* delta;             /* [N]      getStitchedDeltaF() */
+  double lambda;                   /* after solveSystemF's overrides: 1e-5 with SOLVER_FIX_LAMBDA */
+} NaloBASolveInput;
+/* x_out [N]; lastHS_out [N*N] / lastbS_out [N] = EnergyFunctional::lastHS / lastbS; stitched_out (parity hook) = HA [N*N], bA [N],
+ * HL, bL, H_sc, b_sc back to back. All outputs nullable. xc / xAd of resubstituteF_MT (:266-280) stay on the device. */
+int nalo_ba_solve(nalo_ba* ba, const NaloBASolveInput* in, double* x_out, double* lastHS_out, double* lastbS_out, double* stitched_out);
+/* resubstituteFPt with the x of the last nalo_ba_solve (nothing uploaded); xc4_out / xAd_out [nf*nf][8] nullable read-backs. */
+int nalo_ba_resubstitute_x(nalo_ba* ba, int useL, float* step_out, float* xc4_out, float* xAd_out);
+
 /* ---- f1 (SURVEY.md §8 f, "next"): PointFrameResidual::linearize (FullSystem/Residuals.cpp:78-274) -----------------
  * Produces the residual records ON THE DEVICE, in place of the handle's records (same order as uploaded: bucket-sorted,
  * n_res must equal the uploaded problem's n_res for the accumulators that follow), so a BA iteration uploads 88 B per

@@ -643,6 +643,11 @@ class Initializer:
         return dict(maxstep=ms[:k], isGood_new=g[:k], energy_new=en[:k], lastHessian_new=lh[:k], JbBuffer_new=jb[:k])
 
 
+class NaloBASolveInput(C.Structure):
+    _fields_ = [("adHost", _P), ("adTarget", _P), ("cPrior", _P), ("frame_prior", _P), ("frame_delta_prior", _P), ("HM", _P), ("bM", _P),
+                ("delta", _P), ("lam", C.c_double)]
+
+
 class BA:
     """nalo_ba: windowed-BA accumulators (AccumulatedTopHessianSSE / AccumulatedSCHessianSSE) on a flattened problem."""
 
@@ -721,6 +726,33 @@ class BA:
         step = np.zeros(max(nP, 1), dtype=_f32)
         self.ctx._ck(self.L.nalo_ba_resubstitute(self.h_, _ptr(xc), _ptr(xAd), C.c_int(1 if useL else 0), _ptr(step)))
         return step[:nP]
+
+    def solve(self, adHost, adTarget, cPrior=None, frame_prior=None, frame_delta_prior=None, HM=None, bM=None, delta=None, lam=1e-5,
+              want_stitched=False):
+        """f2: stitchDoubleMT (top A / L, Schur) + solveSystemF on the device. Returns dict(x, lastHS, lastbS[, HA, bA, HL, bL, Hsc, bsc])."""
+        nf = self.prob["nf"]
+        N = 4 + 8 * nf
+        d = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        keep = [d(adHost), d(adTarget), d(cPrior), d(frame_prior), d(frame_delta_prior), d(HM), d(bM), d(delta)]
+        inp = NaloBASolveInput(*[_ptr(a) for a in keep], C.c_double(lam))
+        x, lastHS, lastbS = np.zeros(N), np.zeros((N, N)), np.zeros(N)
+        st = np.zeros(3 * (N * N + N)) if want_stitched else None
+        self.ctx._ck(self.L.nalo_ba_solve(self.h_, C.byref(inp), _ptr(x), _ptr(lastHS), _ptr(lastbS), _ptr(st)))
+        out = dict(x=x, lastHS=lastHS, lastbS=lastbS)
+        if want_stitched:
+            o = 0
+            for k in ("HA", "bA", "HL", "bL", "Hsc", "bsc"):
+                n = N if k[0] == "b" else N * N
+                out[k] = st[o : o + n].reshape((N,) if k[0] == "b" else (N, N)).copy()
+                o += n
+        return out
+
+    def resubstitute_x(self, useL=False):
+        """resubstituteFPt with the device-resident x of the last solve(): (step, xc, xAd)."""
+        nf, nP = self.prob["nf"], self.prob["n_pts"]
+        step, xc, xAd = np.zeros(max(nP, 1), dtype=_f32), np.zeros(4, _f32), np.zeros((nf * nf, 8), _f32)
+        self.ctx._ck(self.L.nalo_ba_resubstitute_x(self.h_, C.c_int(1 if useL else 0), _ptr(step), _ptr(xc), _ptr(xAd)))
+        return step[:nP], xc, xAd
 
     def accumulate_sc(self, shiftPriorToZero=True, useL=False):
         nf, nP = self.prob["nf"], self.prob["n_pts"]

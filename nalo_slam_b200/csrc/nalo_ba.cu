@@ -65,6 +65,12 @@ struct nalo_ba {
   bool haveA = false, haveL = false, haveJpJd = false;
   bool haveJpJdDev = false;      // d_jpjd is current for the uploaded records
   bool haveSC = false;           // d_ppSC (HdiF, bdSumF) is current
+  bool haveX = false;            // d_xs (xc, xAd of the last nalo_ba_solve) is current
+  double* d_accA = nullptr;      // [64][169] stitched-input blocks of the last mode-0 top accumulation
+  double* d_accL = nullptr;      // [64][169] ... of the last mode-1/2 one
+  double* d_solve = nullptr;     // f2 workspace (inputs + stitched matrices + solution), see SolveLayout
+  double* h_solve = nullptr;     // pinned mirror
+  float* d_xs = nullptr;         // [4 + 64*8] xc, xAd
   size_t partialFloats = 0, outDoubles = 0;
   int maxItems = 0;
 };
@@ -579,6 +585,349 @@ __global__ void sc_finalize_kernel(const float* __restrict__ partials, const int
   }
 }
 
+// ---------------------------------------------------------------------------------------------- f2: stitch + solve
+// AccumulatedTopHessianSSE::stitchDoubleMT (AccumulatedTopHessian.cpp:241-303, .h:91-139), AccumulatedSCHessianSSE::
+// stitchDoubleMT (AccumulatedSCHessian.cpp:78-148, .h:93-133) and EnergyFunctional::solveSystemF (EnergyFunctional.cpp:776-908,
+// default solver mode) on the accumulator blocks the accumulate calls left on the device. The reference scatters every (h,t)
+// block into H; here every output block gathers its terms in a fixed order (deterministic, no atomics), fp64 throughout.
+constexpr int SV_MAXN = 4 + 8 * NALO_BA_MAX_FRAMES;  // 68
+struct SolveLayout {  // offsets in doubles into nalo_ba::d_solve
+  static constexpr int NN = SV_MAXN * SV_MAXN;
+  static constexpr int adH = 0, adT = adH + 64 * 64, cPrior = adT + 64 * 64, fPrior = cPrior + 4, fDelta = fPrior + 64, HM = fDelta + 64,
+                       bM = HM + NN, delta = bM + SV_MAXN, inEnd = delta + SV_MAXN;
+  static constexpr int HA = inEnd, bA = HA + NN, HL = bA + SV_MAXN, bL = HL + NN, HS = bL + SV_MAXN, bS = HS + NN, lastHS = bS + SV_MAXN,
+                       lastbS = lastHS + NN, x = lastbS + SV_MAXN, end = x + SV_MAXN;
+};
+
+struct StitchArgs {
+  int nf, haveL;
+  const double *accA, *accL, *accD, *accE, *accEB, *hostHcc;
+  const float* cDeltaF;
+  double* W;  // SolveLayout workspace
+};
+
+constexpr int ST_GROUPS = 16;  // 64-thread groups per CTA of stitch_kernel
+// one frame-frame block (a, b) of HA, HL and Hsc per CTA: ST_GROUPS groups of 64 threads share the list of A * D * B^T terms
+__device__ void stitch_frame_block(const StitchArgs& S, int a, int b) {
+  __shared__ int4 sDesc[2 * (2 + 2 * NALO_BA_MAX_FRAMES) + NALO_BA_MAX_FRAMES * NALO_BA_MAX_FRAMES + 3 * NALO_BA_MAX_FRAMES];
+  __shared__ int sQ;
+  __shared__ double sT[ST_GROUPS][64];
+  __shared__ double sPart[ST_GROUPS][3][64];
+  const int nf = S.nf, nf2 = nf * nf;
+  const int g = threadIdx.x >> 6, t64 = threadIdx.x & 63, r = t64 >> 3, c = t64 & 7;
+  if (threadIdx.x == 0) {
+    // descriptor: x = A (block index, +256: adTarget), y = B likewise, z = D (set << 16 | index), w = target matrix | transposed << 4
+    int q = 0;
+    const int T = 256;
+    for (int set = 0; set < 2; set++) {
+      if (set == 1 && !S.haveL) continue;
+      const int ab = a + nf * b, ba_ = b + nf * a;
+      sDesc[q++] = make_int4(ab, ab + T, (set << 16) | ab, set);  // adH_ab Hpp adT_ab^T
+      if (a != b) sDesc[q++] = make_int4(ba_, ba_ + T, (set << 16) | ba_, set | 16);  // (adH_ba Hpp adT_ba^T)^T
+      else {
+        for (int t = 0; t < nf; t++) sDesc[q++] = make_int4(a + nf * t, a + nf * t, (set << 16) | (a + nf * t), set);
+        for (int h = 0; h < nf; h++) sDesc[q++] = make_int4(h + nf * a + T, h + nf * a + T, (set << 16) | (h + nf * a), set);
+      }
+    }
+    if (a == b)
+      for (int j = 0; j < nf; j++)
+        for (int k = 0; k < nf; k++) sDesc[q++] = make_int4(a + nf * j, a + nf * k, (2 << 16) | ((a + nf * j) + k * nf2), 2);
+    for (int i = 0; i < nf; i++) sDesc[q++] = make_int4(i + nf * a + T, i + nf * b + T, (2 << 16) | ((i + nf * a) + b * nf2), 2);
+    for (int k = 0; k < nf; k++) sDesc[q++] = make_int4(b + nf * a + T, b + nf * k, (2 << 16) | ((b + nf * a) + k * nf2), 2);
+    for (int j = 0; j < nf; j++) sDesc[q++] = make_int4(a + nf * j, a + nf * b + T, (2 << 16) | ((a + nf * j) + b * nf2), 2);
+    sQ = q;
+  }
+  __syncthreads();
+  const int Q = sQ;
+  const double* adH = S.W + SolveLayout::adH;
+  const double* adT = S.W + SolveLayout::adT;
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int q0 = 0; q0 < Q; q0 += ST_GROUPS) {
+    const int q = q0 + g;
+    int4 d = make_int4(0, 0, 0, 0);
+    if (q < Q) {
+      d = sDesc[q];
+      const double* B = ((d.y & 256) ? adT : adH) + (size_t)(d.y & 255) * 64;
+      const int set = d.z >> 16, idx = d.z & 0xFFFF;
+      double t = 0.0;  // thread (m = r, col = c): (D B^T)[m][col]
+      if (set == 2) {
+        const double* D = S.accD + (size_t)idx * 64;
+#pragma unroll
+        for (int n = 0; n < 8; n++) t += D[8 * r + n] * B[8 * c + n];
+      } else {
+        const double* D = (set == 0 ? S.accA : S.accL) + (size_t)idx * 169 + 4 * 13 + 4;
+#pragma unroll
+        for (int n = 0; n < 8; n++) t += D[13 * r + n] * B[8 * c + n];
+      }
+      sT[g][t64] = t;
+    }
+    __syncthreads();
+    if (q < Q) {
+      const double* A = ((d.x & 256) ? adT : adH) + (size_t)(d.x & 255) * 64;
+      const int rr = (d.w & 16) ? c : r, cc = (d.w & 16) ? r : c;
+      double s = 0.0;
+#pragma unroll
+      for (int m = 0; m < 8; m++) s += A[8 * rr + m] * sT[g][8 * m + cc];
+      acc[d.w & 3] += s;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) sPart[g][k][t64] = acc[k];
+  __syncthreads();
+  if (g == 0) {
+    const int N = 4 + 8 * nf;
+    const size_t e = (size_t)(4 + 8 * a + r) * N + 4 + 8 * b + c;
+    double v[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      v[k] = sPart[0][k][t64];
+#pragma unroll
+      for (int gg = 1; gg < ST_GROUPS; gg++) v[k] += sPart[gg][k][t64];
+    }
+    if (a == b && r == c) v[1] += S.W[SolveLayout::fPrior + 8 * a + r];  // usePrior (L only), AccumulatedTopHessian.cpp:296
+    S.W[SolveLayout::HA + e] = v[0];
+    S.W[SolveLayout::HL + e] = v[1];
+    S.W[SolveLayout::HS + e] = v[2];
+  }
+}
+
+__global__ void __launch_bounds__(64 * ST_GROUPS) stitch_kernel(const __grid_constant__ StitchArgs S) {
+  const int nf = S.nf, nb = nf * nf, N = 4 + 8 * nf;
+  const int blk = blockIdx.x;
+  if (blk < nb) {
+    stitch_frame_block(S, blk % nf, blk / nf);
+    return;
+  }
+  const double* adH = S.W + SolveLayout::adH;
+  const double* adT = S.W + SolveLayout::adT;
+  const int set = threadIdx.x / 40, e = threadIdx.x % 40;
+  if (set > 2) return;
+  double* Hout = S.W + (set == 0 ? SolveLayout::HA : set == 1 ? SolveLayout::HL : SolveLayout::HS);
+  double* bout = S.W + (set == 0 ? SolveLayout::bA : set == 1 ? SolveLayout::bL : SolveLayout::bS);
+  const bool live = !(set == 1 && !S.haveL);
+  const double* acc = set == 0 ? S.accA : S.accL;
+  if (blk < nb + nf) {  // H[a, calib] (8x4), b[a] (8)
+    const int a = blk - nb;
+    const int r = e < 32 ? e >> 2 : e - 32, c = e < 32 ? (e & 3) : 0;
+    auto pc = [&](int k, int m) -> double {  // Hpc(m, c) / bp(m) of block k
+      if (set == 2) return e < 32 ? S.accE[(size_t)k * 32 + 4 * m + c] : S.accEB[(size_t)k * 8 + m];
+      return acc[(size_t)k * 169 + (4 + m) * 13 + (e < 32 ? c : 12)];
+    };
+    double s = 0.0;
+    if (live) {
+      for (int t = 0; t < nf; t++) {
+        const int k = a + nf * t;
+        double p = 0.0;
+#pragma unroll
+        for (int m = 0; m < 8; m++) p += adH[(size_t)k * 64 + 8 * r + m] * pc(k, m);
+        s += p;
+      }
+      for (int h = 0; h < nf; h++) {
+        const int k = h + nf * a;
+        double p = 0.0;
+#pragma unroll
+        for (int m = 0; m < 8; m++) p += adT[(size_t)k * 64 + 8 * r + m] * pc(k, m);
+        s += p;
+      }
+    }
+    if (e < 32) {
+      Hout[(size_t)(4 + 8 * a + r) * N + c] = s;
+      Hout[(size_t)c * N + 4 + 8 * a + r] = s;
+    } else {
+      if (set == 1) s += S.W[SolveLayout::fPrior + 8 * a + r] * S.W[SolveLayout::fDelta + 8 * a + r];
+      bout[4 + 8 * a + r] = s;
+    }
+  } else if (e < 20) {  // H[calib, calib], b[calib]
+    const int r = e < 16 ? e >> 2 : e - 16, c = e < 16 ? (e & 3) : 12;
+    double s = 0.0;
+    if (set == 2) {
+      for (int h = 0; h < nf; h++) s += S.hostHcc[(size_t)h * 20 + e];
+    } else if (live) {
+      for (int k = 0; k < nb; k++) s += acc[(size_t)k * 169 + r * 13 + c];
+    }
+    if (e < 16) {
+      if (set == 1 && r == c) s += S.W[SolveLayout::cPrior + r];
+      Hout[(size_t)r * N + c] = s;
+    } else {
+      if (set == 1) s += S.W[SolveLayout::cPrior + r] * (double)S.cDeltaF[r];
+      bout[r] = s;
+    }
+  }
+}
+
+// solveSystemF :797-890 + the xc / xAd prologue of resubstituteF_MT (:263-281) in one CTA. Eigen's LDLT (diagonal pivoting
+// on the not-yet-updated diagonal, lower, unblocked, left-looking) with one thread per matrix row.
+__global__ void __launch_bounds__(512) solve_kernel(double* __restrict__ W, int nf, double lambda, float* __restrict__ xs) {
+  constexpr int LD = SV_MAXN + 1, NT = 512;
+  __shared__ double m[SV_MAXN * LD];
+  __shared__ double sv[SV_MAXN], d[SV_MAXN], temp[SV_MAXN], bF[SV_MAXN];
+  __shared__ double colb[2][SV_MAXN];
+  __shared__ double rkb[2];
+  __shared__ int perm[SV_MAXN];
+  const int N = 4 + 8 * nf, tid = threadIdx.x;
+  const double *HA = W + SolveLayout::HA, *HL = W + SolveLayout::HL, *HS = W + SolveLayout::HS, *HM = W + SolveLayout::HM;
+  const double f = 1.0f / (1 + lambda);
+  // bFinal_top, the damped diagonal and the Jacobi scaling first: the pivot order depends on nothing else
+  if (tid < N) {
+    double s = 0.0;
+    for (int j = 0; j < N; j++) s += HM[(size_t)tid * N + j] * W[SolveLayout::delta + j];
+    const double bMtop = W[SolveLayout::bM + tid] + s;
+    const double v = ((W[SolveLayout::bL + tid] + bMtop) + W[SolveLayout::bA + tid]) - W[SolveLayout::bS + tid];
+    bF[tid] = v;
+    W[SolveLayout::lastbS + tid] = v;
+    const size_t e = (size_t)tid * N + tid;
+    const double hd = __dsub_rn(__dmul_rn((HL[e] + HM[e]) + HA[e], 1 + lambda), __dmul_rn(HS[e], f));
+    const double s1 = 1.0 / sqrt(hd + 10.0);
+    sv[tid] = s1;
+    temp[tid] = fabs((s1 * hd) * s1);
+    perm[tid] = tid;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    // Eigen's LDLT<Lower> (diagonal pivoting, unblocked, left-looking) never updates the trailing diagonal, so its whole pivot
+    // sequence -- first largest |diagonal| of the trailing corner at every step -- follows from the initial diagonal and the
+    // swaps. Warp 0 replays it (values in registers: lane owns positions lane, lane+32, lane+64) while the other warps fill the
+    // matrix. Non-negative doubles order like their bit patterns: two 32-bit warp-max reductions + one min over the positions.
+    unsigned long long key[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const int i = tid + 32 * c;
+      const double v = i < N ? temp[i] : 0.0;
+      key[c] = (v != v) ? 1ull : (unsigned long long)__double_as_longlong(v) + 2ull;  // 0: out of range, 1: NaN (never wins over a number)
+      if (i >= N) key[c] = 0ull;
+    }
+    for (int k = 0; k < N; k++) {
+      unsigned long long best = 0ull;
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+        if (tid + 32 * c >= k && key[c] > best) best = key[c];
+      const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32));
+      const unsigned lo = __reduce_max_sync(0xffffffffu, ((unsigned)(best >> 32) == hi) ? (unsigned)best : 0u);
+      const unsigned long long win = ((unsigned long long)hi << 32) | lo;
+      unsigned pos = 0x7fffffffu;
+#pragma unroll
+      for (int c = 2; c >= 0; c--)
+        if (tid + 32 * c >= k && key[c] == win) pos = tid + 32 * c;
+      int idx = (int)__reduce_min_sync(0xffffffffu, pos);
+      // the key of position k (a NaN there keeps k: nothing compares greater than it in the scan)
+      const int kc = k >> 5, kl = k & 31;
+      const unsigned long long mine = kc == 0 ? key[0] : kc == 1 ? key[1] : key[2];
+      const unsigned long long keyK = __shfl_sync(0xffffffffu, mine, kl);
+      if (keyK == 1ull || win == 0ull) idx = k;
+      if (idx != k) {
+        if (tid == (idx & 31)) {  // old value of position k moves to idx
+          if ((idx >> 5) == 0) key[0] = keyK; else if ((idx >> 5) == 1) key[1] = keyK; else key[2] = keyK;
+        }
+        if (tid == 0) { const int t0 = perm[k]; perm[k] = perm[idx]; perm[idx] = t0; }
+      }
+      __syncwarp();
+    }
+  } else {
+    // HFinal_top = HL + HM + HA (:851), lastHS (:854), diagonal * (1 + lambda) (:857), - H_sc / (1 + lambda) (:858), Jacobi scaling
+    for (int e = tid - 32; e < N * N; e += NT - 32) {
+      const int i = e / N, j = e - i * N;
+      double hf = (HL[e] + HM[e]) + HA[e];
+      const double hs = HS[e];
+      W[SolveLayout::lastHS + e] = hf - hs;
+      if (i == j) hf = __dmul_rn(hf, 1 + lambda);
+      hf = __dsub_rn(hf, __dmul_rn(hs, f));
+      m[i * LD + j] = (sv[i] * hf) * sv[j];
+    }
+  }
+  __syncthreads();
+  // permuted lower triangle (read the way Eigen's lower-only swaps leave it) -> registers -> back into m; permuted right-hand
+  // side; column 0 into the column buffer. The factorisation then runs right-looking without pivoting -- the same L and D up
+  // to summation order -- one CTA barrier per column, the forward substitution riding along as an extra column.
+  // (An all-zero diagonal needs no special case: nothing is eliminated and D^-1 maps everything to 0, like Eigen's solve.)
+  constexpr int PER = (SV_MAXN * (SV_MAXN + 1) / 2 + NT - 1) / NT;
+  int ta[PER], tb[PER];  // this thread's lower-triangle elements e = tid + c * NT -> (a, b), b <= a
+  {
+    double v[PER];
+    const int nLow = N * (N + 1) / 2;
+#pragma unroll
+    for (int c = 0; c < PER; c++) {
+      const int e = tid + c * NT;
+      int a = (int)((__fsqrt_rn(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+      while (a * (a + 1) / 2 > e) a--;
+      while ((a + 1) * (a + 2) / 2 <= e) a++;
+      ta[c] = a;
+      tb[c] = e - a * (a + 1) / 2;
+      v[c] = 0.0;
+      if (e < nLow) {
+        const int pi = perm[ta[c]], pj = perm[tb[c]];
+        v[c] = m[max(pi, pj) * LD + min(pi, pj)];
+      }
+    }
+    const double rhs = tid < N ? sv[perm[tid]] * bF[perm[tid]] : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < PER; c++) {
+      const int e = tid + c * NT;
+      if (e < nLow) {
+        m[ta[c] * LD + tb[c]] = v[c];
+        if (tb[c] == 0) colb[0][ta[c]] = v[c];
+        if (e == 0) rkb[0] = fabs(v[c]) > 0.0 ? 1.0 / v[c] : 0.0;
+      }
+    }
+    if (tid < N) d[tid] = rhs;
+    __syncthreads();
+  }
+  for (int k = 0; k < N; k++) {
+    const double* col = colb[k & 1];
+    double* coln = colb[(k + 1) & 1];
+    const double rk = rkb[k & 1];  // 1 / pivot; 0 for a zero pivot: Eigen leaves the (all-zero) column unscaled, nothing is eliminated
+    if (rk != 0.0 && tid > k && tid < N) {
+      const double li = col[tid] * rk;
+      m[tid * LD + k] = li;
+      d[tid] -= li * d[k];  // forward substitution L y = P b
+    }
+    const int rs = N - k - 1, nT = rs * (rs + 1) / 2;  // trailing lower triangle, rows / columns k+1 .. N-1
+#pragma unroll
+    for (int c = 0; c < PER; c++) {
+      const int e = tid + c * NT;
+      if (e < nT) {
+        const int i = k + 1 + ta[c], jj = k + 1 + tb[c];
+        const double nv = m[i * LD + jj] - (col[i] * rk) * col[jj];
+        m[i * LD + jj] = nv;
+        if (tb[c] == 0) {
+          coln[i] = nv;
+          if (e == 0) rkb[(k + 1) & 1] = fabs(nv) > 0.0 ? 1.0 / nv : 0.0;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // D^-1, then L^T z = y by columns on the first three warps (named barrier), then x = S P^T z
+  if (tid < 96) {
+    if (tid < N) {
+      const double dii = m[tid * LD + tid];
+      d[tid] = (fabs(dii) > 2.2250738585072014e-308) ? d[tid] / dii : 0.0;
+    }
+    asm volatile("bar.sync 1, 96;" ::: "memory");
+    for (int jn = N - 1; jn >= 1; jn--) {
+      if (tid < jn) d[tid] -= m[jn * LD + tid] * d[jn];
+      asm volatile("bar.sync 1, 96;" ::: "memory");
+    }
+    if (tid < N) temp[perm[tid]] = sv[perm[tid]] * d[tid];
+  }
+  __syncthreads();
+  if (tid < N) W[SolveLayout::x + tid] = temp[tid];
+  // ---- xc, xAd[h * nf + t] = xF_h^T adHostF[h + nf t] + xF_t^T adTargetF[h + nf t]   (fp32, EnergyFunctional.cpp:266-280)
+  if (tid < 4) xs[tid] = (float)temp[tid];
+  for (int o = tid; o < nf * nf * 8; o += blockDim.x) {
+    const int j = o & 7, ht = o >> 3, h = ht / nf, t = ht % nf;
+    const double* AH = W + SolveLayout::adH + (size_t)(h + nf * t) * 64;
+    const double* AT = W + SolveLayout::adT + (size_t)(h + nf * t) * 64;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s1 = __fadd_rn(s1, __fmul_rn((float)temp[4 + 8 * h + i], (float)AH[8 * i + j]));
+#pragma unroll
+    for (int i = 0; i < 8; i++) s2 = __fadd_rn(s2, __fmul_rn((float)temp[4 + 8 * t + i], (float)AT[8 * i + j]));
+    xs[4 + o] = __fadd_rn(s1, s2);
+  }
+}
+
 // f2 (part): EnergyFunctional::resubstituteFPt (OptimizationBackend/EnergyFunctional.cpp:291-317) — per-point
 // back-substitution with everything it needs already resident (JpJdF, the per-point sums of the accumulations, HdiF /
 // bdSumF of the Schur prologue). One thread per point, residuals in residualsAll order like the reference.
@@ -868,6 +1217,11 @@ int nalo_ba_create(nalo_ctx* ctx, int max_res, int max_pts, nalo_ba** out) {
   ACK(cudaMalloc(&ba->d_out, sizeof(double) * ba->outDoubles));
   ACK(cudaHostAlloc(&ba->h_out, sizeof(double) * ba->outDoubles, cudaHostAllocDefault));
   ACK(cudaMalloc(&ba->d_counter, sizeof(int) * 4));
+  ACK(cudaMalloc(&ba->d_accA, sizeof(double) * 64 * 169));
+  ACK(cudaMalloc(&ba->d_accL, sizeof(double) * 64 * 169));
+  ACK(cudaMalloc(&ba->d_solve, sizeof(double) * SolveLayout::end));
+  ACK(cudaHostAlloc(&ba->h_solve, sizeof(double) * SolveLayout::end, cudaHostAllocDefault));
+  ACK(cudaMalloc(&ba->d_xs, sizeof(float) * (4 + 64 * 8)));
   ACK(cudaMalloc(&ba->d_itemRange, sizeof(int) * 160));  // [0,80): bucket ranges of the top items, [80,160): host ranges of the Schur items
   ACK(cudaFuncSetAttribute(top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TOP_STAGE_RECS * REC * 4 + 64));
 #undef ACK
@@ -883,6 +1237,7 @@ int nalo_ba_destroy(nalo_ba* ba) {
   cudaFree(ba->d_deltaF); cudaFree(ba->d_priorF); cudaFree(ba->d_adHT); cudaFree(ba->d_cDelta); cudaFree(ba->d_ppA); cudaFree(ba->d_ppL);
   cudaFree(ba->d_ppSC); cudaFree(ba->d_ptHost); cudaFree(ba->d_ptOrder); cudaFree(ba->d_items); cudaFree(ba->d_partials); cudaFree(ba->d_out);
   cudaFree(ba->d_counter); cudaFree(ba->d_itemRange);
+  cudaFree(ba->d_accA); cudaFree(ba->d_accL); cudaFree(ba->d_solve); cudaFree(ba->d_xs); if (ba->h_solve) cudaFreeHost(ba->h_solve);
   cudaFree(ba->d_linPt4); cudaFree(ba->d_linColor); cudaFree(ba->d_linWeights); cudaFree(ba->d_linEnergyIn); cudaFree(ba->d_linPairs);
   cudaFree(ba->d_linPack); cudaFree(ba->d_linPoint); cudaFree(ba->d_linStateIn); cudaFree(ba->d_linState); cudaFree(ba->d_linEnergy);
   cudaFree(ba->d_linEnergyOut); cudaFree(ba->d_linCenter); cudaFree(ba->d_linProj);
@@ -898,7 +1253,7 @@ int nalo_ba_upload(nalo_ba* ba, const NaloBAProblem* p) {
   if (!p->rec || !p->bucket_begin || !p->pt_begin || !p->pt_res || !p->adHTdeltaF || !p->cDeltaF) return NALO_E_ARG;
   NALO_CUDA(ctx, cudaSetDevice(ctx->device));
   ba->nf = p->nf; ba->nPts = p->n_pts; ba->nRes = p->n_res;
-  ba->haveA = ba->haveL = ba->haveJpJd = ba->haveJpJdDev = ba->haveSC = false;
+  ba->haveA = ba->haveL = ba->haveJpJd = ba->haveJpJdDev = ba->haveSC = ba->haveX = false;
   cudaStream_t st = ctx->stream;
   const int nb = p->nf * p->nf;
   NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_rec, p->rec, sizeof(float) * REC * (size_t)p->n_res, cudaMemcpyHostToDevice, st));
@@ -998,12 +1353,14 @@ int nalo_ba_accumulate_top(nalo_ba* ba, int mode, double* H_out, float* perPoint
     NALO_CHECK_LAUNCH(ctx);
     ba->haveJpJdDev = true;
   }
-  top_finalize_kernel<<<nb, 768, 0, st>>>(ba->d_partials, ba->d_itemRange, nb, ba->d_out);
+  double* dAcc = (mode == 0) ? ba->d_accA : ba->d_accL;  // kept for nalo_ba_solve (d_out is reused by the Schur pass)
+  top_finalize_kernel<<<nb, 768, 0, st>>>(ba->d_partials, ba->d_itemRange, nb, dAcc);
   NALO_CHECK_LAUNCH(ctx);
   if (ba->nPts > 0) {
     point_sum_kernel<<<(ba->nPts + 255) / 256, 256, 0, st>>>(ba->d_contrib, ba->d_ptBegin, ba->d_ptRes, ba->nPts, pp);
     NALO_CHECK_LAUNCH(ctx);
   }
+  ba->haveX = false;
   if (mode == 2) {  // marginalisation also clears the active-set sums (AccumulatedTopHessian.cpp:152-157)
     NALO_CUDA(ctx, cudaMemsetAsync(ba->d_ppA, 0, sizeof(float) * 6 * (size_t)ba->nPts, st));
     ba->haveA = true;
@@ -1012,7 +1369,7 @@ int nalo_ba_accumulate_top(nalo_ba* ba, int mode, double* H_out, float* perPoint
   // small results go through pinned staging (a D2H copy into pageable memory would be staged by the driver anyway)
   double* hH = ba->h_out;
   int* hN = reinterpret_cast<int*>(ba->h_out + 169 * 64);
-  if (H_out) NALO_CUDA(ctx, cudaMemcpyAsync(hH, ba->d_out, sizeof(double) * 169 * nb, cudaMemcpyDeviceToHost, st));
+  if (H_out) NALO_CUDA(ctx, cudaMemcpyAsync(hH, dAcc, sizeof(double) * 169 * nb, cudaMemcpyDeviceToHost, st));
   if (perPoint_out && ba->nPts > 0)
     NALO_CUDA(ctx, cudaMemcpyAsync(perPoint_out, pp, sizeof(float) * 6 * (size_t)ba->nPts, cudaMemcpyDeviceToHost, st));
   NALO_CUDA(ctx, cudaMemcpyAsync(hN, ba->d_counter, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1180,7 +1537,7 @@ int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, f
   }
   NALO_CUDA(ctx, cudaStreamSynchronize(st));
   // the records changed under the accumulators: per-point sums, JpJdF have to be recomputed
-  ba->haveA = ba->haveL = ba->haveJpJd = ba->haveJpJdDev = ba->haveSC = false;
+  ba->haveA = ba->haveL = ba->haveJpJd = ba->haveJpJdDev = ba->haveSC = ba->haveX = false;
   return NALO_OK;
 }
 
@@ -1193,7 +1550,8 @@ int nalo_ba_resubstitute(nalo_ba* ba, const float xc4[4], const float* xAd, int 
   NALO_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const int nf = ba->nf;
-  float* d_x = reinterpret_cast<float*>(ba->d_out);  // the fp64 result staging is free between calls: 4 + nf*nf*8 floats
+  float* d_x = ba->d_xs;
+  ba->haveX = false;  // overwritten by the caller's x
   NALO_CUDA(ctx, cudaMemcpyAsync(d_x, xc4, sizeof(float) * 4, cudaMemcpyHostToDevice, st));
   NALO_CUDA(ctx, cudaMemcpyAsync(d_x + 4, xAd, sizeof(float) * 8 * nf * nf, cudaMemcpyHostToDevice, st));
   if (ba->nPts > 0) {
@@ -1203,6 +1561,82 @@ int nalo_ba_resubstitute(nalo_ba* ba, const float xc4[4], const float* xAd, int 
     NALO_CHECK_LAUNCH(ctx);
     NALO_CUDA(ctx, cudaMemcpyAsync(step_out, d_step, sizeof(float) * (size_t)ba->nPts, cudaMemcpyDeviceToHost, st));
   }
+  NALO_CUDA(ctx, cudaStreamSynchronize(st));
+  return NALO_OK;
+}
+
+int nalo_ba_solve(nalo_ba* ba, const NaloBASolveInput* in, double* x_out, double* lastHS_out, double* lastbS_out, double* stitched_out) {
+  if (!ba || !in || !in->adHost || !in->adTarget) return NALO_E_ARG;
+  nalo_ctx* ctx = ba->ctx;
+  if (ba->nf == 0 || !ba->haveA || !ba->haveSC)
+    return nalo_fail(ctx, NALO_E_STATE, "nalo_ba_solve needs nalo_ba_accumulate_top(0) and nalo_ba_accumulate_sc first");
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int nf = ba->nf, nb = nf * nf, N = 4 + 8 * nf;
+  using SL = SolveLayout;
+  double* h = ba->h_solve;
+  memset(h, 0, sizeof(double) * SL::inEnd);
+  memcpy(h + SL::adH, in->adHost, sizeof(double) * 64 * nb);
+  memcpy(h + SL::adT, in->adTarget, sizeof(double) * 64 * nb);
+  if (in->cPrior) memcpy(h + SL::cPrior, in->cPrior, sizeof(double) * 4);
+  if (in->frame_prior) memcpy(h + SL::fPrior, in->frame_prior, sizeof(double) * 8 * nf);
+  if (in->frame_delta_prior) memcpy(h + SL::fDelta, in->frame_delta_prior, sizeof(double) * 8 * nf);
+  if (in->HM) memcpy(h + SL::HM, in->HM, sizeof(double) * N * N);
+  if (in->bM) memcpy(h + SL::bM, in->bM, sizeof(double) * N);
+  if (in->delta) memcpy(h + SL::delta, in->delta, sizeof(double) * N);
+  NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_solve, h, sizeof(double) * SL::inEnd, cudaMemcpyHostToDevice, st));
+  StitchArgs S;
+  S.nf = nf; S.haveL = ba->haveL ? 1 : 0;
+  S.accA = ba->d_accA; S.accL = ba->d_accL;
+  S.accD = ba->d_out;                                  // layout of nalo_ba_accumulate_sc
+  S.accE = S.accD + (size_t)nf * nf * nf * 64;
+  S.accEB = S.accE + (size_t)nf * nf * 32;
+  S.hostHcc = S.accEB + (size_t)nf * nf * 8;
+  S.cDeltaF = ba->d_cDelta;
+  S.W = ba->d_solve;
+  stitch_kernel<<<nb + nf + 1, 64 * ST_GROUPS, 0, st>>>(S);
+  NALO_CHECK_LAUNCH(ctx);
+  solve_kernel<<<1, 512, 0, st>>>(ba->d_solve, nf, in->lambda, ba->d_xs);
+  NALO_CHECK_LAUNCH(ctx);
+  ba->haveX = true;
+  // outputs: [HA .. x] is one contiguous block
+  const bool wantAll = stitched_out || lastHS_out || lastbS_out;
+  const int lo = wantAll ? SL::HA : SL::x;
+  NALO_CUDA(ctx, cudaMemcpyAsync(h + lo, ba->d_solve + lo, sizeof(double) * (SL::end - lo), cudaMemcpyDeviceToHost, st));
+  NALO_CUDA(ctx, cudaStreamSynchronize(st));
+  if (x_out) memcpy(x_out, h + SL::x, sizeof(double) * N);
+  if (lastHS_out) memcpy(lastHS_out, h + SL::lastHS, sizeof(double) * N * N);
+  if (lastbS_out) memcpy(lastbS_out, h + SL::lastbS, sizeof(double) * N);
+  if (stitched_out) {  // parity hook: HA, bA, HL, bL, Hsc, bsc back to back
+    double* o = stitched_out;
+    const int src[6] = {SL::HA, SL::bA, SL::HL, SL::bL, SL::HS, SL::bS};
+    for (int k = 0; k < 6; k++) {
+      const size_t cnt = (k & 1) ? (size_t)N : (size_t)N * N;
+      memcpy(o, h + src[k], sizeof(double) * cnt);
+      o += cnt;
+    }
+  }
+  return NALO_OK;
+}
+
+int nalo_ba_resubstitute_x(nalo_ba* ba, int useL, float* step_out, float* xc4_out, float* xAd_out) {
+  if (!ba || !step_out) return NALO_E_ARG;
+  nalo_ctx* ctx = ba->ctx;
+  if (ba->nf == 0 || !ba->haveX || !ba->haveA || !ba->haveJpJd || !ba->haveSC)
+    return nalo_fail(ctx, NALO_E_STATE, "nalo_ba_resubstitute_x needs nalo_ba_solve (after accumulate_top(0), take_data, accumulate_sc) first");
+  if (useL && !ba->haveL) return nalo_fail(ctx, NALO_E_STATE, "useL without a mode 1/2 accumulation");
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int nf = ba->nf;
+  if (ba->nPts > 0) {
+    float* d_step = ba->d_contrib;
+    resubstitute_kernel<<<(ba->nPts + 255) / 256, 256, 0, st>>>(ba->d_rec, ba->d_jpjd, ba->d_ptBegin, ba->d_ptRes, ba->d_ppA, useL ? ba->d_ppL : nullptr,
+                                                                 ba->d_ppSC, ba->d_xs, ba->d_xs + 4, nf, ba->nPts, d_step);
+    NALO_CHECK_LAUNCH(ctx);
+    NALO_CUDA(ctx, cudaMemcpyAsync(step_out, d_step, sizeof(float) * (size_t)ba->nPts, cudaMemcpyDeviceToHost, st));
+  }
+  if (xc4_out) NALO_CUDA(ctx, cudaMemcpyAsync(xc4_out, ba->d_xs, sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
+  if (xAd_out) NALO_CUDA(ctx, cudaMemcpyAsync(xAd_out, ba->d_xs + 4, sizeof(float) * 8 * nf * nf, cudaMemcpyDeviceToHost, st));
   NALO_CUDA(ctx, cudaStreamSynchronize(st));
   return NALO_OK;
 }

@@ -371,6 +371,31 @@ def main():
                 _, ppL, _ = O.ba_top(prob, mode=1, nThreads=6, fast=True)
                 c = cpu_time(lambda: O.ba_sc(prob, J, ppA, ppL, True, nThreads=6, fast=True), budget_s=2.0)[0]
             add(f"a10 AccumulatedSCHessian nres={nres}", d, wl, 40 * nres + 32 * npts, nres, "residual", c, 6)
+            # f2: stitch (top A, top L, Schur) + solveSystemF + x-driven resubstitution, all on resident data
+            nf_ = prob["nf"]
+            N_ = 4 + 8 * nf_
+            rngw = np.random.default_rng(5)
+            aw = rngw.normal(size=(N_, N_ + 4))
+            Wn = dict(adHost=-np.eye(8)[None] + 0.2 * rngw.normal(size=(nf_ * nf_, 8, 8)), adTarget=np.eye(8)[None] + 0.2 * rngw.normal(size=(nf_ * nf_, 8, 8)),
+                      cPrior=np.full(4, 5e9), frame_prior=rngw.uniform(0, 1e3, (nf_, 8)), frame_delta_prior=rngw.normal(0, 1e-3, (nf_, 8)),
+                      HM=10.0 * (aw @ aw.T), bM=rngw.normal(size=N_), delta=rngw.normal(0, 1e-3, N_))
+            ba.take_data()
+            sg = ba.accumulate_sc(True, True)
+            HAa, _, _ = ba.accumulate_top(0)
+            HLa, _, _ = ba.accumulate_top(1)
+            d, wl, _ = T.run(lambda i: ba.solve(**Wn), reps=10)
+            c = None
+            if cpu:
+                def csolve():
+                    a1 = O.ba_stitch_top(nf_, HAa, Wn["adHost"], Wn["adTarget"])
+                    a2 = O.ba_stitch_top(nf_, HLa, Wn["adHost"], Wn["adTarget"], True, Wn["cPrior"], prob["cDeltaF"], Wn["frame_prior"], Wn["frame_delta_prior"])
+                    a3 = O.ba_stitch_sc(nf_, sg["accD"], sg["accE"], sg["accEB"], sg["accHcc"], sg["accbc"], Wn["adHost"], Wn["adTarget"])
+                    O.ba_solve(nf_, a1[0], a1[1], a2[0], a2[1], a3[0], a3[1], Wn["HM"], Wn["bM"], Wn["delta"], 1e-5)
+                c = cpu_time(csolve, budget_s=1.0)[0]
+            add(f"f2 stitch + solveSystemF nf={nf_} (N={N_}) nres={nres}", d, wl, 8 * (2 * 49 * 169 + 343 * 64 + 3 * N_ * N_), 1, "system", c, 1,
+                "two launches; H2D of adjoints/priors/HM (108 KB), D2H of x, lastHS, lastbS")
+            d, wl, _ = T.run(lambda i: ba.resubstitute_x(True), reps=10)
+            add(f"f2 resubstituteFPt (device x) npts={npts}", d, wl, 40 * nres + 44 * npts, npts, "point", None, None, "D2H of the steps inside")
             ba.close()
 
     # ------------------------------------------------------------------ f1 linearize
