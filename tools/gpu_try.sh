@@ -1,3 +1,8 @@
-python -m pytest tests/test_gpu_solve.py tests/test_gpu_ba.py -x -q 2>&1 | tail -5
-python tools/bench_suite.py --rows ba --out gpurun_out/suite_f2.json 2>&1 | grep "f2" | cut -c1-250
-python tools/prof_solve.py > /dev/null && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_solve.csv python tools/prof_solve.py > gpurun_out/ncu_solve.log 2>&1
+./tools/probes/div_probe 8 2>&1 | tail -6
+python -m pytest tests/test_gpu_tracker.py tests/test_gpu_multi_batch.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -4
+python bench.py --steps 20 --warmup 3 > gpurun_out/b_rcp.json 2> gpurun_out/b_rcp.err
+python - <<P
+import json
+d=json.loads(open('gpurun_out/b_rcp.json').read().strip().splitlines()[-1])
+print('value %.2f G'%(d['value']/1e9), 'e2e %.2f G'%(d['e2e']['value']/1e9), 'frac', round(d['roofline']['frac'],4), 'kernel_ms', round(d['roofline']['kernel_ms'],3), 'batched frac', round(d['batched']['roofline']['frac'],4), 'batched ms', round(d['batched']['kernel_ms'],2))
+P
