@@ -12,7 +12,9 @@
 #include "../../include/nalo_gpu.h"
 
 #define NALO_NPART 52        // words of one block partial: 45 H/b/rr + E + flowT + flowRT + 4 ints
+#ifndef NALO_TRACK_THREADS
 #define NALO_TRACK_THREADS 512
+#endif
 #define NALO_PIX_ALIGN 32    // level offsets (in pixels) are multiples of this => 512-byte aligned float4 rows
 
 struct NaloLevelGeom {
