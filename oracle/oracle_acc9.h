@@ -2,6 +2,8 @@
 // Restatement of the reference's SSE accumulators used by the tracker and the initializer:
 //   Accumulator9   src/OptimizationBackend/MatrixAccumulators.h:982-1345
 //   Accumulator11  src/OptimizationBackend/MatrixAccumulators.h:91-175
+// PINNED: bit-identical to the reference's own MatrixAccumulators.h compiled by `make ref` (oracle/_ref, ref_harness.cpp)
+// on seeded inputs across all three shift-up tiers — tests/test_ref_pin.py, fixture tests/golden/ref_pin.npz.
 #pragma once
 #include <emmintrin.h>
 
@@ -136,6 +138,13 @@ struct Acc11 {
   void updateSingle(float val) {
     SSEData[0] += val;
     num++;
+    numIn1++;
+    shiftUp(false);
+  }
+  // updateSSE — MatrixAccumulators.h:123-130
+  void updateSSE(const __m128 val) {
+    _mm_store_ps(SSEData, _mm_add_ps(_mm_load_ps(SSEData), val));
+    num += 4;
     numIn1++;
     shiftUp(false);
   }

@@ -13,7 +13,9 @@
 // a CSR point -> residual list that preserves `p->residualsAll` order, so the loop order (points in
 // allPoints order, residuals in residualsAll order) and therefore the fp32 summation order of one
 // reference worker thread (tid 0, EnergyFunctional.cpp:208-214 non-MT branch) is reproduced exactly.
-// Parity unpinned by the reference (no tests upstream); pinned by closed-form KATs in tests/test_oracle_ba.py.
+// Parity: the accumulator classes (AccApprox / AccXX / AccX) are pinned bit for bit to the reference's own
+// MatrixAccumulators.h compiled by `make ref` (tests/test_ref_pin.py); addPoint / stitch logic is unpinned by the
+// reference (no tests upstream) and pinned by closed-form KATs in tests/test_oracle_ba.py.
 #include <xmmintrin.h>
 
 #include <atomic>
@@ -459,4 +461,48 @@ void oracle_ba_resubstitute(int nf, int nPts, const float* rec, const float* JpJ
   }
 }
 
+// ---- pin hooks (tests/test_ref_pin.py): the accumulator restatements above driven element by element, so they can be
+// compared with the reference's own MatrixAccumulators.h compiled by `make ref` (oracle/ref_harness.cpp, same signatures).
+void oracle_pin_accapprox(int n, const float* x4, const float* x6, const float* y4, const float* y6, const float* abc,
+                          const float* TR, const float* BRv, float* H169, double* num) {
+  AccApprox acc;
+  acc.initialize();
+  for (int i = 0; i < n; i++) {
+    acc.update(x4 + 4 * i, x6 + 6 * i, y4 + 4 * i, y6 + 6 * i, abc[3 * i], abc[3 * i + 1], abc[3 * i + 2]);
+    const float* t = TR + 6 * i;
+    acc.updateTopRight(x4 + 4 * i, x6 + 6 * i, y4 + 4 * i, y6 + 6 * i, t[0], t[1], t[2], t[3], t[4], t[5]);
+    const float* b = BRv + 6 * i;
+    acc.updateBotRight(b[0], b[1], b[2], b[3], b[4], b[5]);
+  }
+  acc.finish();
+  for (int r = 0; r < 13; r++)
+    for (int c = 0; c < 13; c++) H169[r * 13 + c] = acc.H[r][c];
+  *num = (double)acc.num;
+}
+void oracle_pin_accxx_8_4(int n, const float* L, const float* R, const float* w, float* A32, double* num) {
+  AccXX<8, 4> acc;
+  acc.initialize();
+  for (int i = 0; i < n; i++) acc.update(L + 8 * i, R + 4 * i, w[i]);
+  acc.finish();
+  for (int r = 0; r < 8; r++)
+    for (int c = 0; c < 4; c++) A32[r * 4 + c] = acc.A1m[r][c];
+  *num = (double)acc.num;
+}
+void oracle_pin_accxx_8_8(int n, const float* L, const float* R, const float* w, float* A64, double* num) {
+  AccXX<8, 8> acc;
+  acc.initialize();
+  for (int i = 0; i < n; i++) acc.update(L + 8 * i, R + 8 * i, w[i]);
+  acc.finish();
+  for (int r = 0; r < 8; r++)
+    for (int c = 0; c < 8; c++) A64[r * 8 + c] = acc.A1m[r][c];
+  *num = (double)acc.num;
+}
+void oracle_pin_accx_8(int n, const float* L, const float* w, float* A8, double* num) {
+  AccX<8> acc;
+  acc.initialize();
+  for (int i = 0; i < n; i++) acc.update(L + 8 * i, w[i]);
+  acc.finish();
+  for (int r = 0; r < 8; r++) A8[r] = acc.A1m[r];
+  *num = (double)acc.num;
+}
 }  // extern "C"

@@ -306,4 +306,15 @@ void oracle_immature_trace(int w, int h, const float* dI, int n, const float* pu
   }
 }
 
+// ---- pin hooks (tests/test_ref_pin.py): the interpolation restatements above vs. the reference's util/globalFuncs.h
+// compiled by `make ref`. mat3 is the reference's Eigen::Vector3f image ({I, dx, dy} per pixel), xy n pairs.
+void oracle_pin_interp33(const float* mat3, int width, int n, const float* xy, float* out3) {
+  for (int i = 0; i < n; i++) interp33(mat3, xy[2 * i], xy[2 * i + 1], width, out3 + 3 * i);
+}
+void oracle_pin_interp31(const float* mat3, int width, int n, const float* xy, float* out) {
+  for (int i = 0; i < n; i++) out[i] = interp31(mat3, xy[2 * i], xy[2 * i + 1], width);
+}
+void oracle_pin_interp33bilin(const float* mat3, int width, int n, const float* xy, float* out3) {
+  for (int i = 0; i < n; i++) interp33BiLin(mat3, xy[2 * i], xy[2 * i + 1], width, out3 + 3 * i);
+}
 }  // extern "C"

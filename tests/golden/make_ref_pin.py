@@ -1,0 +1,26 @@
+"""Regenerates tests/golden/ref_pin.npz from the REFERENCE'S OWN code: oracle/_ref/libnalo_ref.so, built by
+`make -C oracle ref` from /root/reference/src (MatrixAccumulators.h, globalFuncs.h, settings.cpp compiled unmodified
+against the stand-in third-party headers in oracle/ref_standin/). Run in the build container (needs /root/reference):
+    python tests/golden/make_ref_pin.py
+The fixture keeps the reference's outputs available where /root/reference and the compiled library are absent."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ref_pin_cases as R  # noqa: E402
+
+subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref"])
+L = C.CDLL(R.REF_LIB)
+out = R.run_cases(L, "ref_pin_")
+settings, pattern = R.ref_settings(L)
+out["settings"] = np.array([settings[k] for k in R.SETTINGS_NAMES], np.float64)
+out["pattern"] = pattern
+for i, a in enumerate(R.ref_global_calib(L)):
+    out[f"global_calib/{i}"] = a
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_pin.npz"), **out)
+print("wrote ref_pin.npz:", len(out), "arrays")

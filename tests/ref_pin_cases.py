@@ -1,0 +1,123 @@
+"""Shared by tests/test_ref_pin.py and tests/golden/make_ref_pin.py: seeded inputs for the accumulator / interpolation
+pin cases and one runner that drives either the oracle's restatement (`oracle_pin_*` in oracle/liboracle.so) or the
+reference's own code (`ref_pin_*` in oracle/_ref/libnalo_ref.so, built by `make -C oracle ref` from /root/reference/src).
+TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libnalo_ref.so")
+_P = C.c_void_p
+
+
+def _p(a):
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_P)
+
+
+def _f32(rng, shape, scale=1.0):
+    return np.ascontiguousarray((rng.standard_normal(shape) * scale).astype(np.float32))
+
+
+# numbers of updates: below the first shift-up (<= 1000), across it, and across the second (> 1000 * 1001)
+SIZES = {"tiny": 7, "tier1k": 2503, "tier1m": 1_003_017}
+
+
+def run_cases(L, prefix, sizes=("tiny", "tier1k", "tier1m")):
+    """-> dict name -> ndarray, every output of every case (float32 payloads; `num` counters as float64)."""
+    out = {}
+    num = C.c_double()
+    for sname in sizes:
+        n = SIZES[sname]
+        rng = np.random.default_rng(20261018 + n)
+        # Jacobian rows with the magnitudes calcGSSSE sees (idepth*grad, rotations, affine, residual), Huber-like weights
+        scale9 = np.array([0.8, 0.8, 0.5, 30, 30, 20, 90, 1, 6], np.float32)
+        J = np.ascontiguousarray(_f32(rng, (n, 9, 4)) * scale9[None, :, None])
+        w = np.ascontiguousarray(rng.uniform(0.2, 1.0, (n, 4)).astype(np.float32))
+        H = np.zeros(81, np.float32)
+        getattr(L, prefix + "acc9_sse_weighted")(n, _p(J), _p(w), _p(H), C.byref(num))
+        out[f"acc9_sse_weighted/{sname}"] = H.copy()
+        out[f"acc9_sse_weighted/{sname}/num"] = np.float64(num.value)
+        getattr(L, prefix + "acc9_sse")(n, _p(J), _p(H), C.byref(num))
+        out[f"acc9_sse/{sname}"] = H.copy()
+        J1 = np.ascontiguousarray(J[:, :, 0])
+        w1 = np.ascontiguousarray(w[:, 0])
+        getattr(L, prefix + "acc9_single_weighted")(n, _p(J1), _p(w1), _p(H), C.byref(num))
+        out[f"acc9_single_weighted/{sname}"] = H.copy()
+        out[f"acc9_single_weighted/{sname}/num"] = np.float64(num.value)
+        v = np.ascontiguousarray(np.abs(_f32(rng, (n,), 40.0)))
+        v4 = np.ascontiguousarray(np.abs(_f32(rng, (n // 3 + 1, 4), 40.0)))
+        A = np.zeros(1, np.float32)
+        getattr(L, prefix + "acc11")(n, _p(v), n // 3 + 1, _p(v4), _p(A), C.byref(num))
+        out[f"acc11/{sname}"] = A.copy()
+        out[f"acc11/{sname}/num"] = np.float64(num.value)
+        # AccumulatorApprox: x/y = the two Jacobian rows of a residual, (a, b, c) = its 2x2 gradient outer product
+        x4, y4 = _f32(rng, (n, 4), 3.0), _f32(rng, (n, 4), 3.0)
+        x6, y6 = _f32(rng, (n, 6), 20.0), _f32(rng, (n, 6), 20.0)
+        abc = np.ascontiguousarray(np.abs(_f32(rng, (n, 3), 50.0)))
+        TR, BR = _f32(rng, (n, 6), 10.0), _f32(rng, (n, 6), 100.0)
+        H13 = np.zeros(169, np.float32)
+        getattr(L, prefix + "accapprox")(n, _p(x4), _p(x6), _p(y4), _p(y6), _p(abc), _p(TR), _p(BR), _p(H13), C.byref(num))
+        out[f"accapprox/{sname}"] = H13.copy()
+        out[f"accapprox/{sname}/num"] = np.float64(num.value)
+        if sname != "tier1m":  # Eigen-expression accumulators (stand-in arithmetic): two tiers are enough
+            Lv, R4, R8 = _f32(rng, (n, 8), 5.0), _f32(rng, (n, 4), 5.0), _f32(rng, (n, 8), 5.0)
+            ww = np.ascontiguousarray(rng.uniform(1e-3, 1.0, (n,)).astype(np.float32))
+            A32, A64, A8 = np.zeros(32, np.float32), np.zeros(64, np.float32), np.zeros(8, np.float32)
+            getattr(L, prefix + "accxx_8_4")(n, _p(Lv), _p(R4), _p(ww), _p(A32), C.byref(num))
+            getattr(L, prefix + "accxx_8_8")(n, _p(Lv), _p(R8), _p(ww), _p(A64), C.byref(num))
+            getattr(L, prefix + "accx_8")(n, _p(Lv), _p(ww), _p(A8), C.byref(num))
+            out[f"accxx_8_4/{sname}"], out[f"accxx_8_8/{sname}"], out[f"accx_8/{sname}"] = A32.copy(), A64.copy(), A8.copy()
+    # interpolation on an {I, dx, dy} image, sample points anywhere inside [1, w-2] x [1, h-2] incl. exact integers
+    rng = np.random.default_rng(77)
+    w_, h_, n = 97, 61, 4000
+    img = np.ascontiguousarray(_f32(rng, (h_ * w_, 3), 60.0))
+    xy = np.empty((n, 2), np.float32)
+    xy[:, 0] = rng.uniform(1, w_ - 2, n)
+    xy[:, 1] = rng.uniform(1, h_ - 2, n)
+    xy[:50] = np.floor(xy[:50])
+    xy = np.ascontiguousarray(xy)
+    o3, o1 = np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
+    getattr(L, prefix + "interp33")(_p(img), w_, n, _p(xy), _p(o3))
+    out["interp33"] = o3.copy()
+    getattr(L, prefix + "interp31")(_p(img), w_, n, _p(xy), _p(o1))
+    out["interp31"] = o1.copy()
+    getattr(L, prefix + "interp33bilin")(_p(img), w_, n, _p(xy), _p(o3))
+    out["interp33bilin"] = o3.copy()
+    return out
+
+
+SETTINGS_NAMES = [
+    "huberTH", "coarseCutoffTH", "affineOptModeA", "affineOptModeB", "minGradHistCut", "minGradHistAdd", "gradDownweightPerLevel",
+    "selectDirectionDistribution", "outlierTH", "outlierTHSumComponent", "overallEnergyTHWeight", "maxPixSearch", "trace_stepsize",
+    "trace_GNIterations", "trace_GNThreshold", "trace_extraSlackOnTH", "trace_slackInterval", "trace_minImprovementFactor",
+    "minTraceTestRadius", "minTraceQuality", "idepthFixPrior", "initialTransPrior", "solverMode", "solverModeDelta",
+    "desiredImmatureDensity", "desiredPointDensity", "margWeightFac", "maxShiftWeightT", "maxShiftWeightRT", "kfGlobalWeight",
+    "maxAffineWeight", "pyrLevelsUsed", "PYR_LEVELS", "patternNum", "patternPadding", "SOLVER_FIX_LAMBDA", "SOLVER_ORTHOGONALIZE_X_LATER",
+]
+
+
+def ref_settings(L):
+    buf = np.zeros(64, np.float64)
+    L.ref_pin_settings.restype = C.c_int
+    n = L.ref_pin_settings(_p(buf), 64)
+    assert n == len(SETTINGS_NAMES)
+    pat = np.zeros(16, np.int32)
+    L.ref_pin_pattern(_p(pat))
+    return dict(zip(SETTINGS_NAMES, buf[:n].tolist())), pat.reshape(8, 2)
+
+
+CALIB_CASES = [(1248, 384, 718.856, 718.856, 607.1928, 185.2157), (640, 480, 525.0, 525.25, 319.5, 239.5), (1280, 1024, 1100.0, 1098.5, 645.3, 510.7)]
+
+
+def ref_global_calib(L):
+    """util/globalCalib.cpp setGlobalCalib -> list of [levels][10] arrays (w, h, fx, fy, cx, cy, fxi, fyi, cxi, cyi)."""
+    L.ref_pin_global_calib.restype = C.c_int
+    res = []
+    for (w, h, fx, fy, cx, cy) in CALIB_CASES:
+        out = np.zeros((8, 10), np.float32)
+        n = L.ref_pin_global_calib(w, h, C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(out))
+        res.append(out[:n].copy())
+    return res

@@ -1,0 +1,131 @@
+"""Pins the oracle to the REFERENCE'S OWN code where that can be compiled here.
+
+oracle/_ref/libnalo_ref.so is built by `make -C oracle ref` from the reference sources where they lie under
+/root/reference/src — OptimizationBackend/MatrixAccumulators.h (Accumulator9 / 11 / Approx / XX / X), util/globalFuncs.h
+(getInterpolatedElement33 / 31 / 33BiLin) and util/settings.cpp — against minimal stand-ins for the absent third-party
+headers (oracle/ref_standin/). tests/golden/ref_pin.npz holds that library's outputs on seeded inputs
+(tests/golden/make_ref_pin.py), so the pin also holds where neither /root/reference nor the library exists.
+
+Checked here, all BIT-EXACT:
+  * the oracle's accumulator / interpolation restatements == the fixture (always);
+  * the compiled reference == the fixture and == the oracle (when the library is present);
+  * the product's default settings (C ABI, host-only calls) and the oracle's == util/settings.cpp's values.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import ref_pin_cases as R
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_pin.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return dict(np.load(GOLD))
+
+
+@pytest.fixture(scope="module")
+def oracle_out(oracle):
+    return R.run_cases(oracle.lib(), "oracle_pin_")
+
+
+def _same_bits(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.dtype == np.float32:
+        return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    return np.array_equal(a, b)
+
+
+def test_oracle_matches_reference_fixture(oracle_out, gold):
+    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith("global_calib")]
+    assert len(keys) >= 30
+    for k in keys:
+        assert k in oracle_out, k
+        assert _same_bits(oracle_out[k], gold[k]), f"oracle restatement differs from the reference's output: {k}"
+    # the three tiers really exercised the 1k / 1m shift-ups: counts are exact
+    assert gold["acc9_sse_weighted/tier1m/num"] == 4 * R.SIZES["tier1m"]
+    assert gold["accapprox/tier1k/num"] == R.SIZES["tier1k"]
+
+
+@pytest.mark.skipif(not os.path.exists(R.REF_LIB), reason="oracle/_ref/libnalo_ref.so not built (needs /root/reference)")
+def test_compiled_reference_matches_fixture_and_oracle(oracle_out, gold):
+    L = C.CDLL(R.REF_LIB)
+    ref = R.run_cases(L, "ref_pin_")
+    for k, v in ref.items():
+        assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
+        assert _same_bits(v, oracle_out[k]), f"oracle != compiled reference: {k}"
+    settings, pattern = R.ref_settings(L)
+    assert np.array_equal(np.array([settings[k] for k in R.SETTINGS_NAMES]), gold["settings"])
+    assert np.array_equal(pattern, gold["pattern"])
+    for i, a in enumerate(R.ref_global_calib(L)):
+        assert _same_bits(a, gold[f"global_calib/{i}"]), f"fixture is stale: global_calib/{i}"
+
+
+def test_fixture_is_the_weighted_gram_sum(gold):
+    """Sanity of the fixture itself: the 4 M-residual Accumulator9 entry is sum(w * J0 * J0) of the seeded inputs."""
+    n = R.SIZES["tier1m"]
+    rng = np.random.default_rng(20261018 + n)
+    scale9 = np.array([0.8, 0.8, 0.5, 30, 30, 20, 90, 1, 6], np.float32)
+    J = rng.standard_normal((n, 9, 4)).astype(np.float32) * scale9[None, :, None]
+    w = rng.uniform(0.2, 1.0, (n, 4)).astype(np.float32)
+    exact00 = np.sum((J[:, 0, :].astype(np.float64) * w) * J[:, 0, :])
+    assert abs(float(gold["acc9_sse_weighted/tier1m"][0]) - exact00) / exact00 < 1e-5
+
+
+def test_make_k_matches_set_global_calib(gold, oracle):
+    """CoarseTracker::makeK (oracle restatement) vs the reference's setGlobalCalib (same per-level formulas): level
+    sizes and forward intrinsics bit-exact; inverse intrinsics to 1e-6 (Eigen's 3x3 inverse is stand-in arithmetic)."""
+    for i, (w, h, fx, fy, cx, cy) in enumerate(R.CALIB_CASES):
+        g = gold[f"global_calib/{i}"]
+        levels = g.shape[0]
+        assert levels == {0: 5, 1: 4, 2: 6}[i]  # setGlobalCalib's level rule (both sides even, > 5000 px, <= PYR_LEVELS)
+        T = oracle.Tracker(w, h, levels)
+        T.makeK(fx, fy, cx, cy)
+        K = T.get_K()
+        for l in range(levels):
+            assert (int(g[l, 0]), int(g[l, 1])) == (w >> l, h >> l)
+            assert _same_bits(K[l, :4], g[l, 2:6]), (i, l)
+            Ki = K[l, 4:].reshape(3, 3)
+            assert np.allclose([Ki[0, 0], Ki[1, 1], Ki[0, 2], Ki[1, 2]], g[l, 6:10], rtol=1e-6, atol=0)
+
+
+def test_settings_match_reference(gold, oracle):
+    s = dict(zip(R.SETTINGS_NAMES, gold["settings"].tolist()))
+    from nalo_slam_b200 import capi
+
+    p = capi.default_params()  # host-only C-ABI call: no GPU needed
+    for name in ("huberTH", "coarseCutoffTH", "affineOptModeA", "affineOptModeB", "minGradHistCut", "minGradHistAdd",
+                 "gradDownweightPerLevel", "selectDirectionDistribution"):
+        assert float(getattr(p, name)) == s[name], name
+    t = capi.NaloTraceParams()
+    capi.load().nalo_default_trace_params(C.byref(t))
+    for name in ("maxPixSearch", "trace_stepsize", "trace_GNIterations", "trace_GNThreshold", "trace_extraSlackOnTH",
+                 "trace_slackInterval", "trace_minImprovementFactor", "minTraceTestRadius", "outlierTH", "outlierTHSumComponent",
+                 "overallEnergyTHWeight"):
+        assert float(getattr(t, name)) == s[name], name
+    assert s["PYR_LEVELS"] == 6 and s["patternNum"] == 8
+    assert s["solverMode"] == s["SOLVER_FIX_LAMBDA"] + s["SOLVER_ORTHOGONALIZE_X_LATER"]  # the mode f2 restates
+    # the 8-pixel residual pattern used by f1 / f3 / f4 (settings.h patternP = staticPattern[8])
+    assert gold["pattern"].tolist() == [[0, -2], [-1, -1], [1, -1], [-2, 0], [0, 0], [2, 0], [-1, 1], [0, 2]]
+
+
+@pytest.mark.gpu
+def test_gpu_make_k_matches_set_global_calib(gold):
+    """The product's makeK (C ABI) against the reference's setGlobalCalib outputs in the fixture: forward intrinsics
+    bit-exact per level."""
+    from nalo_slam_b200 import capi
+
+    for i, (w, h, fx, fy, cx, cy) in enumerate(R.CALIB_CASES):
+        g = gold[f"global_calib/{i}"]
+        levels = g.shape[0]
+        ctx = capi.Context(w, h, levels, device=0, max_frames=1)
+        ctx.make_k(0, fx, fy, cx, cy)
+        K = ctx.get_k(0)
+        for l in range(levels):
+            assert _same_bits(K[l, :4], g[l, 2:6]), (i, l)
+            Ki = K[l, 4:].reshape(3, 3)
+            assert np.allclose([Ki[0, 0], Ki[1, 1], Ki[0, 2], Ki[1, 2]], g[l, 6:10], rtol=1e-6, atol=0)
+        ctx.close()
