@@ -14,7 +14,8 @@ carries ms_per_frame and gn_iters_per_s (the other two figures BASELINE.json's m
           recorded by the library right before the pyramid kernel and right after the tracking kernel), L2 flushed
           between steps.
   e2e   : same step through the C ABI with the F images in pinned HOST memory (H2D inside the timed region, poses
-          read back to the host), wall clock.
+          read back to the host), wall clock; streaming form (nalo_track_frames_submit / _wait, two submissions in
+          flight), with the blocking one-call-per-step figure beside it (`sync_call`).
   roofline : tracking kernel, algorithmic bytes sum_l evals_l*(16 N_l + 12 w_l h_l) / device time of the kernel.
   cpu_baseline : the CPU oracle (restatement of the reference; the reference itself cannot be compiled here) on
           1 host core, bounded sample, rank 0 at N=1 only.
@@ -203,7 +204,7 @@ def run_b200(args, rank, world, local_rank):
     # iterations depends on the data), so the N-GPU figure isolates system effects from workload variance.
     sc, ref, news, gts = make_workload(seed=synth.DEFAULT_SEED)
     F = max(1, min(int(args.frames), 160))  # new frames per step (tracked concurrently against the same reference keyframe)
-    ctx = capi.Context(W, H, LEVELS, device=local_rank, max_frames=F + 2)
+    ctx = capi.Context(W, H, LEVELS, device=local_rank, max_frames=2 * F + 2)  # two submissions of F frames in flight (e2e arm)
     ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)  # mode=1 of the reference preset (main_dso_pangolin.cpp:429-435)
     _, agref = ctx.make_images(0, ref, want_host=True)
     idw, ws = synth.dense_reference_maps(sc, agref[: W * H], KEEP)
@@ -295,20 +296,44 @@ def run_b200(args, rank, world, local_rank):
     else:
         job_res, job_iters, job_launches = float(tot_res), float(tot_iters), float(launches)
 
-    # ---- e2e arm: F host images in, F poses out, wall clock, through the C ABI (uploads pipelined against tracking)
+    # ---- e2e arm: F host images in, F poses out, wall clock, through the C ABI.
+    # (a) the synchronous call, one step at a time (uploads pipelined against tracking inside the call);
+    # (b) the streaming form a rig at frame rate uses: nalo_track_frames_submit / _wait with two submissions in flight, so
+    #     the host images of step i+1 cross PCIe while step i is tracked. Every step still uploads its F images and reads
+    #     its F results back; the timed region is the K steps from the first submit to the last wait. (b) is `e2e`.
     ctx.set_profiling(False)
     for i in range(min(Wu, 3)):
         step_host(i)
     if dist:
         dist.barrier()
-    e2e_s, e2e_res = 0.0, 0
+    sync_s, sync_res = 0.0, 0
     for i in range(K):
         ctx.flush_l2()
         ctx.sync()
         t0 = time.perf_counter()
         r = step_host(i)
-        e2e_s += time.perf_counter() - t0
-        e2e_res += r["stats"]["residuals"]
+        sync_s += time.perf_counter() - t0
+        sync_res += r["stats"]["residuals"]
+    slots2 = [slots, list(range(F + 1, 2 * F + 1))]
+
+    def submit_host(i):
+        ctx.flush_l2()  # stream-ordered between the tracking of step i-1 and the pyramids of step i (inside the timed region)
+        return ctx.track_frames_submit(0, slots2[i & 1], p0s, a0s, colors_host=[pin_imgs[(i * F + f) % NB] for f in range(F)])
+
+    for rep in range(2):  # rep 0: warm-up (allocates the second staging set)
+        ctx.sync()
+        if dist and rep == 1:
+            dist.barrier()
+        n_steps = K if rep == 1 else min(Wu, 3) + 1
+        e2e_res, prev = 0, None
+        t0 = time.perf_counter()
+        for i in range(n_steps):
+            t = submit_host(i)
+            if prev is not None:
+                e2e_res += ctx.track_frames_wait(prev)["stats"]["residuals"]
+            prev = t
+        e2e_res += ctx.track_frames_wait(prev)["stats"]["residuals"]
+        e2e_s = time.perf_counter() - t0
     if dist:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -392,7 +417,10 @@ def run_b200(args, rank, world, local_rank):
             "ms_per_frame": total_ms / (K * F), "gn_iters_per_s": job_iters / (total_ms * 1e-3),
             "residuals_per_frame": tot_res / (K * F), "evals_per_frame": tot_evals / (K * F),
             "e2e": {"value": e2e_res / e2e_s, "unit": "residuals/s", "ms_per_frame": 1e3 * e2e_s / (K * F), "ms_per_step": 1e3 * e2e_s / K,
-                    "h2d_bytes_per_step": int(F * (W * H * 4) + F * 512), "d2h_bytes_per_step": int(F * 320)},
+                    "h2d_bytes_per_step": int(F * (W * H * 4) + F * 512), "d2h_bytes_per_step": int(F * 320),
+                    "mode": "nalo_track_frames_submit/_wait, two submissions of F frames in flight; wall clock over the K steps",
+                    "sync_call": {"value": sync_res / sync_s, "ms_per_step": 1e3 * sync_s / K,
+                                  "mode": "nalo_track_frames, one blocking call per step, per-call wall time summed"}},
             "latency": latency,
             "gpu_launches": int(job_launches),
             "clocks": clocks,

@@ -160,6 +160,18 @@ int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const
                       const float* B256, float exposure_new, double* poses7_inout, double* affs2_inout, int coarsestLvl, int* ok_out,
                       double* lastRes5_out, NaloTrackStats* stats /* nullable */);
 
+/* The same in two halves, for callers that stream submissions (a rig at frame rate): _submit enqueues uploads, pyramids,
+ * tracking and the result copy and returns at once with a ticket; _wait blocks until that submission's results are on the
+ * host. Two submissions may be in flight (two staging sets): the host images of submission k+1 cross PCIe while
+ * submission k is tracked, which is what bounds this PCIe-limited path. The frame slots of two submissions in flight must
+ * be disjoint; colors_host images must stay valid (and should be pinned) until the matching _wait returns. Errors:
+ * NALO_E_STATE for a third submission, an unknown ticket, or nalo_track_frames while a submission is in flight. */
+int nalo_track_frames_submit(nalo_ctx* ctx, int trk, int n, const int* new_slots, const float* const* colors_host,
+                             const float* const* colors_dev, const float* B256, float exposure_new, const double* poses7,
+                             const double* affs2, int coarsestLvl, unsigned* ticket_out);
+int nalo_track_frames_wait(nalo_ctx* ctx, unsigned ticket, double* poses7_out, double* affs2_out, int* ok_out, double* lastRes5_out,
+                           NaloTrackStats* stats /* nullable; no timings */);
+
 /* ---- a11: FullSystem::trackNewCoarse (FullSystem.cpp:502-699) ------------------------------------------ */
 /* candidate list (:516-580) from camToWorld of sprelast, slast and the reference KF; returns count in *n_out (<=31) */
 int nalo_motion_candidates(const double sprelast_c2w[7], const double slast_c2w[7], const double lastF_c2w[7], int posesValid,

@@ -386,6 +386,40 @@ class Context:
                                           C.c_int(coarsestLvl), _ptr(ok), _ptr(lr), C.byref(st)))
         return dict(ok=ok, poses=poses, affs=affs, lastRes=lr, stats=st.as_dict())
 
+    def track_frames_submit(self, trk, slots, poses7, affs2, colors_host=None, colors_dev_ptrs=None, coarsestLvl=None, exposure=1.0):
+        """nalo_track_frames_submit: enqueue one submission and return its ticket (two may be in flight). The host images
+        are kept referenced until track_frames_wait returns."""
+        n = len(slots)
+        poses = np.ascontiguousarray(poses7, dtype=np.float64).reshape(n, 7)
+        affs = np.ascontiguousarray(affs2, dtype=np.float64).reshape(n, 2)
+        if coarsestLvl is None:
+            coarsestLvl = min(self.levels, 5) - 1
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        hp = dp = keep = None
+        if colors_dev_ptrs is not None:
+            dp = (C.c_void_p * n)(*[int(p) for p in colors_dev_ptrs])
+        else:
+            keep = [np.ascontiguousarray(c, dtype=_f32).reshape(-1) for c in colors_host]
+            hp = (C.c_void_p * n)(*[k.ctypes.data for k in keep])
+        ticket = C.c_uint(0)
+        self._ck(self.L.nalo_track_frames_submit(self.h_, C.c_int(trk), C.c_int(n), _ptr(sl), hp, dp, None, C.c_float(exposure), _ptr(poses),
+                                                 _ptr(affs), C.c_int(coarsestLvl), C.byref(ticket)))
+        if not hasattr(self, "_frames_keep"):
+            self._frames_keep = {}
+        self._frames_keep[ticket.value] = (keep, n)
+        return ticket.value
+
+    def track_frames_wait(self, ticket):
+        """nalo_track_frames_wait: block until the submission's results are on the host."""
+        keep = getattr(self, "_frames_keep", {}).pop(ticket, None)
+        n = keep[1] if keep else 160  # NALO_MAX_HYPOTHESES
+        poses, affs = np.zeros((n, 7)), np.zeros((n, 2))
+        ok = np.zeros(n, dtype=np.int32)
+        lr = np.zeros((n, 5))
+        st = NaloTrackStats()
+        self._ck(self.L.nalo_track_frames_wait(self.h_, C.c_uint(ticket), _ptr(poses), _ptr(affs), _ptr(ok), _ptr(lr), C.byref(st)))
+        return dict(ok=ok, poses=poses, affs=affs, lastRes=lr, stats=st.as_dict())
+
     # ---- a11
     def track_multi(self, trk, new_slot, poses7, affs2, coarsestLvl=None, exposure=1.0):
         poses = np.ascontiguousarray(poses7, dtype=np.float64).copy()

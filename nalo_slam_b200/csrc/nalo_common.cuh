@@ -94,12 +94,29 @@ struct nalo_ctx {
   size_t trackSmemMax = 0;  // dynamic shared memory track_kernel may use (opt-in limit minus its static part)
   cudaStream_t stream = nullptr;
   cudaStream_t copyStream = nullptr;  // asynchronous export of the reference-layout host copies (nalo_make_images_async)
-  const void** d_frameTable = nullptr;  // pointer tables of multi-frame pyramid launches (4 regions, round-robin)
+  const void** d_frameTable = nullptr;  // pointer tables of multi-frame pyramid launches (kFrameTableRegions regions, round-robin)
   const void** h_frameTable = nullptr;  // pinned staging of the same
   unsigned frameTableNext = 0;
-  float* d_colorMulti = nullptr;        // NALO_MAX_HYPOTHESES input images (nalo_track_frames from host images)
   static constexpr int kMaxUploadParts = 8;
-  cudaEvent_t evUpload[kMaxUploadParts + 1] = {};  // [0..7]: part uploaded; [8]: fork point on the main stream
+  static constexpr int kFrameTableRegions = 4 * kMaxUploadParts;  // >= the pyramid launches of two submissions in flight
+  // Two complete staging sets of nalo_track_frames (submit / wait): while submission k is tracked, the host images of
+  // submission k+1 are already crossing PCIe into the other set.
+  struct FramesBuf {
+    float* d_color = nullptr;              // NALO_MAX_HYPOTHESES input images
+    NaloTrackProblem* h_prob = nullptr;    // pinned
+    NaloTrackProblem* d_prob = nullptr;
+    NaloTrackResult* h_res = nullptr;      // pinned
+    NaloTrackResult* d_res = nullptr;
+    cudaEvent_t evUpload[kMaxUploadParts] = {};  // part uploaded (copy stream)
+    cudaEvent_t evDone = nullptr;                // results of the submission are in h_res (main stream)
+    int n = 0;
+    int slots[NALO_MAX_HYPOTHESES] = {};   // frame slots of the submission
+    bool pending = false;   // submitted, not yet waited for
+    bool timing = false;
+    long long launches0 = 0;
+    unsigned ticket = 0;
+  } fb[2];
+  unsigned framesTicketNext = 1;
   float* d_exportStage = nullptr;     // its own staging buffer (d_stage is scratch of the main stream)
   cudaEvent_t exportDone = nullptr;   // last D2H out of d_exportStage
   bool exportBusy = false;

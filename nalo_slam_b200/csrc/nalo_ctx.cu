@@ -132,9 +132,15 @@ int nalo_destroy(nalo_ctx* ctx) {
   for (auto& f : ctx->frames) { if (f.built) cudaEventDestroy(f.built); if (f.hostReady) cudaEventDestroy(f.hostReady); }
   if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
   cudaFree(ctx->d_exportStage);
-  cudaFree(ctx->d_frameTable); cudaFree(ctx->d_colorMulti);
+  cudaFree(ctx->d_frameTable);
+  for (auto& b : ctx->fb) {
+    cudaFree(b.d_color); cudaFree(b.d_prob); cudaFree(b.d_res);
+    if (b.h_prob) cudaFreeHost(b.h_prob);
+    if (b.h_res) cudaFreeHost(b.h_res);
+    for (auto& e : b.evUpload) if (e) cudaEventDestroy(e);
+    if (b.evDone) cudaEventDestroy(b.evDone);
+  }
   if (ctx->h_frameTable) cudaFreeHost(ctx->h_frameTable);
-  for (auto& e : ctx->evUpload) if (e) cudaEventDestroy(e);
   if (ctx->exportDone) cudaEventDestroy(ctx->exportDone);
   cudaFree(ctx->d_color); cudaFree(ctx->d_B); cudaFree(ctx->d_stage); cudaFree(ctx->d_mask); cudaFree(ctx->d_mask_all); cudaFree(ctx->d_ptlist); cudaFree(ctx->d_owner);
   cudaFree(ctx->d_scan); cudaFree(ctx->d_counts); cudaFree(ctx->d_flush);

@@ -376,11 +376,12 @@ int nalo_images_run_multi(nalo_ctx* ctx, int n, const int* slots, const float* c
     useB = 1;
   }
   if (!ctx->d_frameTable) {
-    NALO_CUDA(ctx, cudaMalloc(&ctx->d_frameTable, sizeof(void*) * 2 * NALO_MAX_HYPOTHESES * 4));
-    NALO_CUDA(ctx, cudaHostAlloc(&ctx->h_frameTable, sizeof(void*) * 2 * NALO_MAX_HYPOTHESES * 4, cudaHostAllocDefault));
+    NALO_CUDA(ctx, cudaMalloc(&ctx->d_frameTable, sizeof(void*) * 2 * NALO_MAX_HYPOTHESES * nalo_ctx::kFrameTableRegions));
+    NALO_CUDA(ctx, cudaHostAlloc(&ctx->h_frameTable, sizeof(void*) * 2 * NALO_MAX_HYPOTHESES * nalo_ctx::kFrameTableRegions, cudaHostAllocDefault));
   }
-  // four table regions used round-robin, so a second call may be enqueued while the first one's copy is still in flight
-  const int region = (ctx->frameTableNext++) & 3;
+  // table regions used round-robin, so further calls (up to two whole submissions of nalo_track_frames_submit) may be
+  // enqueued while the copies of earlier ones are still in flight
+  const int region = (int)((ctx->frameTableNext++) % nalo_ctx::kFrameTableRegions);
   const void** ht = ctx->h_frameTable + (size_t)region * 2 * NALO_MAX_HYPOTHESES;
   const void** dt = ctx->d_frameTable + (size_t)region * 2 * NALO_MAX_HYPOTHESES;
   for (int i = 0; i < n; i++) {

@@ -271,17 +271,37 @@ int nalo_winner_rule(int nHyp, const double* poses7, const double* affs2, const 
 // re-localisation candidates): per frame the pyramid is built into its own slot, then ONE launch of the persistent
 // tracking kernel aligns all of them (a group of CTAs per frame, dynamic queue). Same per-frame semantics as
 // nalo_track_frame; no abort thresholds. n <= NALO_MAX_HYPOTHESES.
-int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const float* const* colors_host, const float* const* colors_dev,
-                      const float* B256, float exposure_new, double* poses7, double* affs2, int coarsestLvl, int* ok_out, double* lastRes5_out,
-                      NaloTrackStats* stats) {
-  if (!ctx || trk < 0 || trk >= NALO_MAX_TRACKERS || !new_slots || !poses7 || !affs2 || (!colors_host && !colors_dev)) return NALO_E_ARG;
+// The work is split into an enqueue half (everything asynchronous: uploads on the copy stream, pyramids + tracking +
+// result copy on the main stream, nothing waited for) and a collect half, over two complete staging sets
+// (nalo_ctx::FramesBuf), so that nalo_track_frames_submit / _wait can keep two submissions in flight: the host images of
+// submission k+1 cross PCIe while submission k is tracked. nalo_track_frames is submit + wait.
+}  // extern "C" (helpers below are internal)
+
+static int frames_buf_alloc(nalo_ctx* ctx, nalo_ctx::FramesBuf& B) {
+  if (B.d_prob) return NALO_OK;
+  NALO_CUDA(ctx, cudaMalloc(&B.d_prob, sizeof(NaloTrackProblem) * NALO_MAX_HYPOTHESES));
+  NALO_CUDA(ctx, cudaMalloc(&B.d_res, sizeof(NaloTrackResult) * NALO_MAX_HYPOTHESES));
+  NALO_CUDA(ctx, cudaHostAlloc(&B.h_prob, sizeof(NaloTrackProblem) * NALO_MAX_HYPOTHESES, cudaHostAllocDefault));
+  NALO_CUDA(ctx, cudaHostAlloc(&B.h_res, sizeof(NaloTrackResult) * NALO_MAX_HYPOTHESES, cudaHostAllocDefault));
+  for (auto& e : B.evUpload) NALO_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  NALO_CUDA(ctx, cudaEventCreateWithFlags(&B.evDone, cudaEventDisableTiming));
+  return NALO_OK;
+}
+
+static int frames_enqueue(nalo_ctx* ctx, nalo_ctx::FramesBuf& B, int trk, int n, const int* new_slots, const float* const* colors_host,
+                          const float* const* colors_dev, const float* B256, float exposure_new, const double* poses7, const double* affs2,
+                          int coarsestLvl, bool timing) {
+  if (trk < 0 || trk >= NALO_MAX_TRACKERS || !new_slots || !poses7 || !affs2 || (!colors_host && !colors_dev)) return NALO_E_ARG;
   if (n < 1 || n > NALO_MAX_HYPOTHESES) return nalo_fail(ctx, NALO_E_ARG, "n %d out of [1,%d]", n, NALO_MAX_HYPOTHESES);
   if (coarsestLvl < 0 || coarsestLvl >= NALO_TRACK_LEVELS || coarsestLvl >= ctx->levels) return NALO_E_ARG;
   NaloTrackerState& T = ctx->trk[trk];
   if (!T.haveK || !T.haveRef) return nalo_fail(ctx, NALO_E_STATE, "tracker %d has no reference", trk);
   NALO_CUDA(ctx, cudaSetDevice(ctx->device));
-  const long long l0 = ctx->launches;
-  const bool timing = stats && ctx->profiling;
+  int rc = frames_buf_alloc(ctx, B);
+  if (rc != NALO_OK) return rc;
+  B.launches0 = ctx->launches;
+  B.timing = timing;
+  B.n = n;
   if (timing) NALO_CUDA(ctx, cudaEventRecord(ctx->evS, ctx->stream));
   for (int i = 0; i < n; i++) {
     const int slot = new_slots[i];
@@ -289,10 +309,11 @@ int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const
     for (int k = 0; k < i; k++)
       if (new_slots[k] == slot) return nalo_fail(ctx, NALO_E_ARG, "frame slot %d listed twice", slot);
     if (!colors_dev && (!colors_host || !colors_host[i])) return NALO_E_ARG;
+    B.slots[i] = slot;
   }
   // problems of all frames (pointers into the frame slots do not depend on the pyramids being built yet)
   for (int i = 0; i < n; i++) {
-    NaloTrackProblem* P = ctx->h_problems + i;
+    NaloTrackProblem* P = B.h_prob + i;
     T.newSlot = new_slots[i];
     T.newExposure = exposure_new;
     ctx->frames[new_slots[i]].valid = true;
@@ -303,7 +324,13 @@ int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const
     P->coarsestLvl = coarsestLvl;
     P->useAbort = 0;
   }
-  NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_problems, ctx->h_problems, sizeof(NaloTrackProblem) * n, cudaMemcpyHostToDevice, ctx->stream));
+  // The problem table (tens of KB: a copy-engine transfer, not an inlined one) travels at the head of this submission's
+  // uploads on the copy stream. On the main stream it would become runnable only when the previous submission's tracking
+  // ends and then queue behind every image upload already handed to the H2D engine - measured (torch.profiler timeline,
+  // tools/prof_stream_timeline.py): with two submissions in flight no kernel of a submission started before ALL queued
+  // uploads, the next submission's included, had finished (8.1 ms per 148-frame step instead of the 5.6 ms PCIe takes).
+  NALO_CUDA(ctx, cudaMemcpyAsync(B.d_prob, B.h_prob, sizeof(NaloTrackProblem) * n, cudaMemcpyHostToDevice,
+                                 colors_dev ? ctx->stream : ctx->copyStream));
   // the frames' pyramids (10 MB each) exceed L2 from ~10 frames on: the evaluation then streams texels from HBM
   const bool streamed = (size_t)n * ctx->totPix * sizeof(float4) > ((size_t)96 << 20);
   const size_t n0 = (size_t)ctx->w0 * ctx->h0;
@@ -319,28 +346,25 @@ int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const
   if (nParts > n) nParts = n;
   auto partLo = [&](int p) { return (int)((long long)n * p / nParts); };
   if (!colors_dev) {
-    if (!ctx->d_colorMulti) {
-      NALO_CUDA(ctx, cudaMalloc(&ctx->d_colorMulti, sizeof(float) * n0 * NALO_MAX_HYPOTHESES));
-      for (auto& e : ctx->evUpload) NALO_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
-    // order the uploads after everything already enqueued on the main stream (previous users of the staging area)
-    NALO_CUDA(ctx, cudaEventRecord(ctx->evUpload[kMaxParts], ctx->stream));
-    NALO_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evUpload[kMaxParts], 0));
+    if (!B.d_color) NALO_CUDA(ctx, cudaMalloc(&B.d_color, sizeof(float) * n0 * NALO_MAX_HYPOTHESES));
+    // This staging set was last read by the pyramid launches of the submission that used it before; that submission has
+    // been waited for (B.pending is false), so its kernels are complete and the uploads may start at once - also while
+    // the OTHER set's submission is still being tracked on the main stream.
     for (int part = 0; part < nParts; part++) {
       const int lo = partLo(part), hi = partLo(part + 1);
       for (int i = lo; i < hi; i++) {
-        NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_colorMulti + n0 * i, colors_host[i], sizeof(float) * n0, cudaMemcpyHostToDevice, ctx->copyStream));
-        srcs[i] = ctx->d_colorMulti + n0 * i;
+        NALO_CUDA(ctx, cudaMemcpyAsync(B.d_color + n0 * i, colors_host[i], sizeof(float) * n0, cudaMemcpyHostToDevice, ctx->copyStream));
+        srcs[i] = B.d_color + n0 * i;
       }
-      NALO_CUDA(ctx, cudaEventRecord(ctx->evUpload[part], ctx->copyStream));
+      NALO_CUDA(ctx, cudaEventRecord(B.evUpload[part], ctx->copyStream));
     }
   } else {
     for (int i = 0; i < n; i++) srcs[i] = colors_dev[i];
   }
   for (int part = 0; part < nParts; part++) {
     const int lo = partLo(part), cnt = partLo(part + 1) - lo;
-    if (!colors_dev) NALO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evUpload[part], 0));
-    int rc = nalo_images_run_multi(ctx, cnt, new_slots + lo, srcs + lo, B256, ctx->stream);
+    if (!colors_dev) NALO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, B.evUpload[part], 0));
+    rc = nalo_images_run_multi(ctx, cnt, new_slots + lo, srcs + lo, B256, ctx->stream);
     if (rc != NALO_OK) return rc;
     if (timing && part == 0) NALO_CUDA(ctx, cudaEventRecord(ctx->evA, ctx->stream));
     int G = ctx->maxGroups / cnt;
@@ -348,18 +372,27 @@ int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const
     static const char* envG = getenv("NALO_FRAMES_G");        // measurement switches
     static const char* envH = getenv("NALO_FRAMES_HELP");
     if (envG && atoi(envG) > 0) G = atoi(envG);
-    rc = nalo_track_launch(ctx, cnt, G, ctx->d_problems + lo, ctx->d_results + lo, streamed, /*helpAll=*/envH && atoi(envH) > 0);
+    rc = nalo_track_launch(ctx, cnt, G, B.d_prob + lo, B.d_res + lo, streamed, /*helpAll=*/envH && atoi(envH) > 0);
     if (rc != NALO_OK) return rc;
   }
   if (timing) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));
-  NALO_CUDA(ctx, cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(NaloTrackResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
-  NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  NALO_CUDA(ctx, cudaMemcpyAsync(B.h_res, B.d_res, sizeof(NaloTrackResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  NALO_CUDA(ctx, cudaEventRecord(B.evDone, ctx->stream));
+  B.pending = true;
+  return NALO_OK;
+}
+
+static int frames_collect(nalo_ctx* ctx, nalo_ctx::FramesBuf& B, double* poses7, double* affs2, int* ok_out, double* lastRes5_out,
+                          NaloTrackStats* stats) {
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  B.pending = false;  // (also on error: the set is free again)
+  NALO_CUDA(ctx, cudaEventSynchronize(B.evDone));
+  const int n = B.n;
   if (stats) memset(stats, 0, sizeof(*stats));
   for (int i = 0; i < n; i++) {
-    const NaloTrackResult& R = ctx->h_results[i];
-    for (int k = 0; k < 7; k++) poses7[7 * i + k] = R.pose[k];
-    affs2[2 * i] = R.aff[0];
-    affs2[2 * i + 1] = R.aff[1];
+    const NaloTrackResult& R = B.h_res[i];
+    if (poses7) for (int k = 0; k < 7; k++) poses7[7 * i + k] = R.pose[k];
+    if (affs2) { affs2[2 * i] = R.aff[0]; affs2[2 * i + 1] = R.aff[1]; }
     if (ok_out) ok_out[i] = R.ok;
     if (lastRes5_out) for (int k = 0; k < 5; k++) lastRes5_out[5 * i + k] = R.lastRes[k];
     if (stats) {
@@ -370,13 +403,57 @@ int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const
     }
   }
   if (stats) {
-    stats->launches = (int)(ctx->launches - l0);
-    if (timing) {
+    stats->launches = (int)(ctx->launches - B.launches0);
+    if (B.timing) {
       NALO_CUDA(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->evA, ctx->evB));
       NALO_CUDA(ctx, cudaEventElapsedTime(&stats->step_ms, ctx->evS, ctx->evB));
     }
   }
   return NALO_OK;
+}
+
+extern "C" {
+
+int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const float* const* colors_host, const float* const* colors_dev,
+                      const float* B256, float exposure_new, double* poses7, double* affs2, int coarsestLvl, int* ok_out, double* lastRes5_out,
+                      NaloTrackStats* stats) {
+  if (!ctx) return NALO_E_ARG;
+  if (ctx->fb[0].pending || ctx->fb[1].pending)
+    return nalo_fail(ctx, NALO_E_STATE, "nalo_track_frames: a submission of nalo_track_frames_submit has not been waited for");
+  nalo_ctx::FramesBuf& B = ctx->fb[0];
+  int rc = frames_enqueue(ctx, B, trk, n, new_slots, colors_host, colors_dev, B256, exposure_new, poses7, affs2, coarsestLvl,
+                          stats && ctx->profiling);
+  if (rc != NALO_OK) { B.pending = false; return rc; }
+  return frames_collect(ctx, B, poses7, affs2, ok_out, lastRes5_out, stats);
+}
+
+int nalo_track_frames_submit(nalo_ctx* ctx, int trk, int n, const int* new_slots, const float* const* colors_host,
+                             const float* const* colors_dev, const float* B256, float exposure_new, const double* poses7,
+                             const double* affs2, int coarsestLvl, unsigned* ticket_out) {
+  if (!ctx || !ticket_out) return NALO_E_ARG;
+  nalo_ctx::FramesBuf* B = !ctx->fb[0].pending ? &ctx->fb[0] : (!ctx->fb[1].pending ? &ctx->fb[1] : nullptr);
+  if (!B) return nalo_fail(ctx, NALO_E_STATE, "nalo_track_frames_submit: two submissions are already in flight");
+  // frame slots of the submission still in flight must not be rebuilt under its tracking kernel
+  const nalo_ctx::FramesBuf& O = ctx->fb[B == &ctx->fb[0] ? 1 : 0];
+  if (O.pending && new_slots)
+    for (int i = 0; i < n && i < NALO_MAX_HYPOTHESES; i++)
+      for (int k = 0; k < O.n; k++)
+        if (O.slots[k] == new_slots[i])
+          return nalo_fail(ctx, NALO_E_ARG, "frame slot %d belongs to the submission still in flight", new_slots[i]);
+  int rc = frames_enqueue(ctx, *B, trk, n, new_slots, colors_host, colors_dev, B256, exposure_new, poses7, affs2, coarsestLvl, false);
+  if (rc != NALO_OK) { B->pending = false; return rc; }
+  B->ticket = ctx->framesTicketNext++;
+  if (ctx->framesTicketNext == 0) ctx->framesTicketNext = 1;
+  *ticket_out = B->ticket;
+  return NALO_OK;
+}
+
+int nalo_track_frames_wait(nalo_ctx* ctx, unsigned ticket, double* poses7_out, double* affs2_out, int* ok_out, double* lastRes5_out,
+                           NaloTrackStats* stats) {
+  if (!ctx) return NALO_E_ARG;
+  for (auto& B : ctx->fb)
+    if (B.pending && B.ticket == ticket) return frames_collect(ctx, B, poses7_out, affs2_out, ok_out, lastRes5_out, stats);
+  return nalo_fail(ctx, NALO_E_STATE, "nalo_track_frames_wait: no submission with ticket %u in flight", ticket);
 }
 
 }  // extern "C"

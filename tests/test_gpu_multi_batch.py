@@ -215,3 +215,55 @@ def test_track_frames_pipelined_parts(small_pair, gpu_ctx_small, oracle):
                 assert dt < 1e-6 and dr < 1e-6, (i, dt, dr)
     finally:
         ctx.close()
+
+
+def test_track_frames_submit_wait(small_pair, gpu_ctx_small, oracle):
+    """nalo_track_frames_submit / _wait: two submissions in flight (uploads of the second overlap the tracking of the first)
+    give exactly the results of the synchronous calls; misuse is reported, not executed."""
+    P = small_pair
+    w, h, L = P["w"], P["h"], P["L"]
+    n = 20
+    ctx = capi.Context(w, h, L, device=0, max_frames=2 * n + 1)
+    ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)
+    try:
+        T, idw, ws = make_oracle_tracker(oracle, P)
+        ctx.make_images(0, P["ref"])
+        ctx.make_k(0, *P["scene"].K)
+        ctx.set_ref_dense(0, 0, idw, ws)
+        rng = np.random.default_rng(10)
+        pins = []
+        for i in range(2 * n):
+            xi, aff = synth.random_motion(rng, 0.5)
+            a = capi.pinned_array((h, w), np.float32)
+            a[...] = synth.render_new(P["scene"], synth.se3_exp(xi), aff)
+            pins.append(a)
+        p0s, a0s = np.tile(synth.pose_identity(), (n, 1)), np.zeros((n, 2))
+        slotsA, slotsB = list(range(1, n + 1)), list(range(n + 1, 2 * n + 1))
+        refA = ctx.track_frames(0, slotsA, p0s, a0s, colors_host=pins[:n])
+        refB = ctx.track_frames(0, slotsB, p0s, a0s, colors_host=pins[n:])
+        assert refA["ok"].all() and refB["ok"].all()
+        for rep in range(3):  # every staging set is reused
+            tA = ctx.track_frames_submit(0, slotsA, p0s, a0s, colors_host=pins[:n])
+            with pytest.raises(capi.NaloError):  # slots of a submission in flight
+                ctx.track_frames_submit(0, slotsA, p0s, a0s, colors_host=pins[:n])
+            tB = ctx.track_frames_submit(0, slotsB, p0s, a0s, colors_host=pins[n:])
+            with pytest.raises(capi.NaloError):  # a third submission
+                ctx.track_frames_submit(0, slotsA, p0s, a0s, colors_host=pins[:n])
+            with pytest.raises(capi.NaloError):  # the synchronous call while submissions are in flight
+                ctx.track_frames(0, slotsA, p0s, a0s, colors_host=pins[:n])
+            with pytest.raises(capi.NaloError):  # unknown ticket
+                ctx.track_frames_wait(tA + 1000)
+            first, second = (tA, tB) if rep != 1 else (tB, tA)  # waiting out of order is allowed
+            outs = {first: ctx.track_frames_wait(first), second: ctx.track_frames_wait(second)}
+            for t, ref in ((tA, refA), (tB, refB)):
+                o = outs[t]
+                assert np.array_equal(o["ok"], ref["ok"])
+                assert np.array_equal(o["poses"], ref["poses"]) and np.array_equal(o["affs"], ref["affs"])
+                assert np.array_equal(o["lastRes"], ref["lastRes"], equal_nan=True)
+                assert o["stats"]["residuals"] == ref["stats"]["residuals"]
+            with pytest.raises(capi.NaloError):  # already waited for
+                ctx.track_frames_wait(tA)
+        again = ctx.track_frames(0, slotsA, p0s, a0s, colors_host=pins[:n])  # synchronous path still works afterwards
+        assert np.array_equal(again["poses"], refA["poses"])
+    finally:
+        ctx.close()
