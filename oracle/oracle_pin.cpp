@@ -2,6 +2,7 @@
 // restatements (oracle_acc9.h) with the same signatures as oracle/ref_harness.cpp's drivers of the reference's own
 // MatrixAccumulators.h, so that tests/test_ref_pin.py can compare the two bit for bit.
 #include "oracle_acc9.h"
+#include "oracle_math.h"
 
 extern "C" {
 
@@ -48,5 +49,11 @@ void oracle_pin_acc11(int n, const float* v, int n4, const float* v4, float* A, 
   acc.finish();
   *A = acc.A;
   *num = (double)acc.num;
+}
+void oracle_pin_aff_from_to(int n, const double* in, double* out) {
+  for (int i = 0; i < n; i++) {
+    const double* p = in + 6 * i;
+    orc::aff_from_to((float)p[0], (float)p[1], p[2], p[3], p[4], p[5], out + 2 * i);
+  }
 }
 }  // extern "C"

@@ -6,6 +6,7 @@
 //                                              scalar arithmetic + the 1k/1m shift-up hierarchy), AccumulatorXX / X
 //   util/globalFuncs.h                         getInterpolatedElement33 / 31 / 33BiLin
 //   util/settings.cpp                          every setting_* default
+//   util/NumType.h                             AffLight::fromToVecExposure
 //   util/globalCalib.cpp                       setGlobalCalib: number of pyramid levels, per-level w, h, fx, fy, cx, cy
 //                                              (the same formulas as CoarseTracker::makeK, CoarseTracker.cpp:116-145)
 // Nothing here is used by the product; tests/test_ref_pin.py compares the oracle's restatements (oracle_pin_* hooks)
@@ -184,5 +185,14 @@ int ref_pin_global_calib(int w, int h, float fx, float fy, float cx, float cy, f
     o[6] = fxiG[l]; o[7] = fyiG[l]; o[8] = cxiG[l]; o[9] = cyiG[l];
   }
   return pyrLevelsUsed;
+}
+// util/NumType.h AffLight::fromToVecExposure (the affLL of calcRes, CoarseTracker.cpp:897, and of linearize). in: [n][6] =
+// exposureF, exposureT, g2F.a, g2F.b, g2T.a, g2T.b; out: [n][2]
+void ref_pin_aff_from_to(int n, const double* in, double* out) {
+  for (int i = 0; i < n; i++) {
+    const double* p = in + 6 * i;
+    Vec2 r = AffLight::fromToVecExposure((float)p[0], (float)p[1], AffLight(p[2], p[3]), AffLight(p[4], p[5]));
+    out[2 * i] = r[0]; out[2 * i + 1] = r[1];
+  }
 }
 }  // extern "C"

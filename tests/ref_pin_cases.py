@@ -86,6 +86,21 @@ def run_cases(L, prefix, sizes=("tiny", "tier1k", "tier1m")):
     out["interp31"] = o1.copy()
     getattr(L, prefix + "interp33bilin")(_p(img), w_, n, _p(xy), _p(o3))
     out["interp33bilin"] = o3.copy()
+    # AffLight::fromToVecExposure incl. the exposure == 0 special case
+    rng = np.random.default_rng(5)
+    n = 256
+    aff = np.empty((n, 6), np.float64)
+    aff[:, 0:2] = rng.uniform(0.002, 0.05, (n, 2)).astype(np.float32)
+    aff[:8, 0] = 0.0
+    aff[8:16, 1] = 0.0
+    aff[:, 2] = rng.uniform(-0.3, 0.3, n)
+    aff[:, 3] = rng.uniform(-20, 20, n)
+    aff[:, 4] = rng.uniform(-0.3, 0.3, n)
+    aff[:, 5] = rng.uniform(-20, 20, n)
+    aff = np.ascontiguousarray(aff)
+    o2 = np.zeros((n, 2), np.float64)
+    getattr(L, prefix + "aff_from_to")(n, _p(aff), _p(o2))
+    out["aff_from_to"] = o2.copy()
     return out
 
 
