@@ -14,6 +14,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnalo_gpu.so")
+if os.environ.get("NALO_LIB"):  # experiment builds (tools/): another in-tree build of the same library
+    LIB_PATH = os.path.abspath(os.environ["NALO_LIB"])
 _P = C.c_void_p
 _f32 = np.float32
 
