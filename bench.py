@@ -193,6 +193,21 @@ def run_b200(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local_rank)
+    # Host threads and (by first touch) the pinned image buffers of this rank go to the NUMA node its GPU hangs off: with
+    # 8 ranks uploading 49 GB/s each, cross-socket copies would share the inter-socket link. Best effort (NVML's ideal
+    # CPU set for the device); NALO_BENCH_NO_AFFINITY=1 switches it off.
+    if not os.environ.get("NALO_BENCH_NO_AFFINITY"):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[local_rank]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else local_rank
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx))
+            if len(os.sched_getaffinity(0)) < 2:  # a degenerate set would starve the submit thread: undo
+                pynvml.nvmlDeviceClearCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx))
+        except Exception as e:  # noqa: BLE001
+            log(f"[rank {rank}] no NUMA affinity: {e}")
     dist = None
     if world > 1:
         import torch.distributed as dist_
