@@ -129,15 +129,6 @@ __device__ __forceinline__ float value_at(const float* __restrict__ color, int w
                 value_at<LVL - 1>(color, w0, 2 * x, 2 * y + 1), value_at<LVL - 1>(color, w0, 2 * x + 1, 2 * y + 1));
   }
 }
-__device__ __forceinline__ float value_at_lvl(int lvl, const float* __restrict__ color, int w0, int x, int y) {
-  switch (lvl) {
-    case 0: return value_at<0>(color, w0, x, y);
-    case 1: return value_at<1>(color, w0, x, y);
-    case 2: return value_at<2>(color, w0, x, y);
-    case 3: return value_at<3>(color, w0, x, y);
-    default: return value_at<4>(color, w0, x, y);
-  }
-}
 
 constexpr int FT_W = 64, FT_H = 32, FT_M = 16;             // tile and margin at level 0
 constexpr int FR_W = FT_W + 2 * FT_M, FR_H = FT_H + 2 * FT_M;  // staged region 96 x 64

@@ -131,7 +131,6 @@ __device__ __forceinline__ void aff_from_to(float expF, float expT, const double
 __device__ __forceinline__ void ldlt_solve_warp(double* m, int n, double* d, int* tr) {
   const int lane = threadIdx.x & 31;
 #define M_(i, j) m[(i) * 9 + (j)]
-  bool zero_diag = false;
   for (int k = 0; k < n; k++) {
     int idx = k;
     double big = fabs(M_(k, k));
@@ -161,7 +160,6 @@ __device__ __forceinline__ void ldlt_solve_warp(double* m, int n, double* d, int
     if (lane == 0) M_(k, k) = akk;
     if (k == 0 && !pivot_ok) {
       if (lane < n) tr[lane] = lane;
-      zero_diag = true;
       __syncwarp();
       break;
     }
@@ -172,7 +170,6 @@ __device__ __forceinline__ void ldlt_solve_warp(double* m, int n, double* d, int
     }
     __syncwarp();
   }
-  (void)zero_diag;
   if (lane == 0) {
     for (int k = 0; k < n; k++)
       if (tr[k] != k) { const double t0 = d[k]; d[k] = d[tr[k]]; d[tr[k]] = t0; }
