@@ -1,4 +1,5 @@
 set -x
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/r01_bench_ref.json 2> gpurun_out/r01_bench_ref.log
 python bench.py > gpurun_out/r01_bench_f148.json 2> gpurun_out/r01_bench_f148.log && \
