@@ -6,12 +6,19 @@
 //                                              scalar arithmetic + the 1k/1m shift-up hierarchy), AccumulatorXX / X
 //   util/globalFuncs.h                         getInterpolatedElement33 / 31 / 33BiLin
 //   util/settings.cpp                          every setting_* default
+//   FullSystem/PixelSelector2.cpp              PixelSelector: constructor (randomPattern), makeHists, select, makeMaps - the
+//                                              whole a2-a4 selection, against a three-member stub of FrameHessian
 //   util/NumType.h                             AffLight::fromToVecExposure
 //   util/globalCalib.cpp                       setGlobalCalib: number of pyramid levels, per-level w, h, fx, fy, cx, cy
 //                                              (the same formulas as CoarseTracker::makeK, CoarseTracker.cpp:116-145)
 // Nothing here is used by the product; tests/test_ref_pin.py compares the oracle's restatements (oracle_pin_* hooks)
 // with these, bit for bit, and tests/golden/ref_pin.npz keeps outputs of this library for boxes without /root/reference.
 #include "OptimizationBackend/MatrixAccumulators.h"
+#define private public  // this translation unit only: read PixelSelector::thsSmoothed / call select(); PixelSelector2.cpp itself is compiled as is
+#include "FullSystem/PixelSelector2.h"
+#undef private
+#include "FullSystem/HessianBlocks.h"  // the stub in ref_standin/ (three FrameHessian members)
+#include "IOWrapper/ImageDisplay.h"
 #include "util/globalFuncs.h"
 #include "util/globalCalib.h"
 #include "util/settings.h"
@@ -195,4 +202,62 @@ void ref_pin_aff_from_to(int n, const double* in, double* out) {
     out[2 * i] = r[0]; out[2 * i + 1] = r[1];
   }
 }
+// ---- FullSystem/PixelSelector2.cpp (compiled as its own translation unit by `make ref`)
+static PixelSelector* g_sel = nullptr;
+static FrameHessian g_fh;
+// wG/hG/pyrLevelsUsed come from the reference's setGlobalCalib; the constructor draws randomPattern from glibc rand()
+// after srand(3141592), exactly as in the reference process
+void ref_pin_selector_create(int w, int h) {
+  Eigen::Matrix3f K;
+  K << 500.0, 0.0, 0.5 * w, 0.0, 500.0, 0.5 * h, 0.0, 0.0, 1.0;
+  setGlobalCalib(w, h, K);
+  delete g_sel;
+  g_sel = new PixelSelector(w, h);
+}
+void ref_pin_selector_settings(float cut, float add, float dw, int dirDist) {
+  setting_minGradHistCut = cut; setting_minGradHistAdd = add; setting_gradDownweightPerLevel = dw; setting_selectDirectionDistribution = dirDist != 0;
+}
+void ref_pin_selector_set_potential(int p) { g_sel->currentPotential = p; }
+int ref_pin_selector_get_potential() { return g_sel->currentPotential; }
+const unsigned char* ref_pin_selector_random_pattern() { return g_sel->randomPattern; }
+static void set_frame(const float* dI3, const float* ag0, const float* ag1, const float* ag2) {
+  g_fh.dI = reinterpret_cast<Eigen::Vector3f*>(const_cast<float*>(dI3));
+  g_fh.dIp[0] = g_fh.dI;
+  g_fh.absSquaredGrad[0] = const_cast<float*>(ag0);
+  g_fh.absSquaredGrad[1] = const_cast<float*>(ag1);
+  g_fh.absSquaredGrad[2] = const_cast<float*>(ag2);
+  g_fh.mask = nullptr;
+}
+// makeHists; ths / thsSmoothed copied out ((w/32)*(h/32) entries each)
+void ref_pin_selector_make_hists(const float* ag0, float* ths, float* thsSmoothed) {
+  set_frame(nullptr, ag0, nullptr, nullptr);
+  g_sel->gradHistFrame = nullptr;
+  g_sel->makeHists(&g_fh);
+  const int n = (wG[0] / 32) * (hG[0] / 32);
+  for (int i = 0; i < n; i++) { ths[i] = g_sel->ths[i]; thsSmoothed[i] = g_sel->thsSmoothed[i]; }
+}
+// select at a fixed potential (histograms of the same frame must have been made); n3 = per-level counts
+void ref_pin_selector_select(const float* dI3, const float* ag0, const float* ag1, const float* ag2, float* map_out, int pot,
+                             float thFactor, int* n3) {
+  set_frame(dI3, ag0, ag1, ag2);
+  Eigen::Vector3i n = g_sel->select(&g_fh, map_out, pot, thFactor);
+  n3[0] = n[0]; n3[1] = n[1]; n3[2] = n[2];
+}
+// makeMaps incl. the recursion, the potential update and the randomPattern sub-sampling; always rebuilds the histograms
+int ref_pin_selector_make_maps(const float* dI3, const float* ag0, const float* ag1, const float* ag2, float* map_out, float density,
+                               int recursionsLeft, float thFactor) {
+  set_frame(dI3, ag0, ag1, ag2);
+  g_sel->gradHistFrame = nullptr;
+  return g_sel->makeMaps(&g_fh, map_out, density, recursionsLeft, false, thFactor);
+}
 }  // extern "C"
+
+// IOWrapper/ImageDisplay.h: declared by the reference, defined in its OpenCV/Pangolin wrappers; PixelSelector2.cpp refers
+// to displayImage in plotting branches that are never taken here
+namespace dso { namespace IOWrap {
+void displayImage(const char*, const MinimalImageB*, bool) {}
+void displayImage(const char*, const MinimalImageB3*, bool) {}
+void displayImage(const char*, const MinimalImageF*, bool) {}
+void displayImage(const char*, const MinimalImageF3*, bool) {}
+void displayImage(const char*, const MinimalImageB16*, bool) {}
+}}

@@ -11,6 +11,7 @@ import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import ref_pin_cases as R  # noqa: E402
 
@@ -20,6 +21,7 @@ out = R.run_cases(L, "ref_pin_")
 settings, pattern = R.ref_settings(L)
 out["settings"] = np.array([settings[k] for k in R.SETTINGS_NAMES], np.float64)
 out["pattern"] = pattern
+out.update(R.run_selector_cases(lambda w, h: R._RefSel(L, w, h)))
 for i, a in enumerate(R.ref_global_calib(L)):
     out[f"global_calib/{i}"] = a
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_pin.npz"), **out)

@@ -136,3 +136,183 @@ def ref_global_calib(L):
         n = L.ref_pin_global_calib(w, h, C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(out))
         res.append(out[:n].copy())
     return res
+
+
+# ---------------------------------------------------------------------------------------------- PixelSelector (a2-a4)
+SELECTOR_SIZES = [(640, 480), (1248, 384)]
+
+
+class _OracleSel:
+    """oracle/oracle_frontend.cpp through its C entry points."""
+
+    def __init__(self, L, w, h):
+        self.L, self.w, self.h = L, w, h
+        L.oracle_selector_create.restype = _P
+        L.oracle_selector_random_pattern.restype = C.POINTER(C.c_ubyte)
+        self.h_ = _P(L.oracle_selector_create(w, h))
+
+    def settings(self, cut, add, dw, dd):
+        self.L.oracle_selector_set_settings(self.h_, C.c_float(cut), C.c_float(add), C.c_float(dw), dd)
+
+    def pattern(self):
+        return np.ctypeslib.as_array(self.L.oracle_selector_random_pattern(self.h_), shape=(self.w * self.h,)).copy()
+
+    def set_pot(self, p):
+        self.L.oracle_selector_set_potential(self.h_, p)
+
+    def get_pot(self):
+        return int(self.L.oracle_selector_get_potential(self.h_))
+
+    def hists(self, fr):
+        self.L.oracle_selector_make_hists(self.h_, _p(fr[2]))
+        n = (self.w // 32) * (self.h // 32)
+        m = int(self.L.oracle_selector_ths_size(self.h_))
+        a, b = np.zeros(m, np.float32), np.zeros(m, np.float32)
+        self.L.oracle_selector_get_ths(self.h_, _p(a), _p(b))
+        return a[:n].copy(), b[:n].copy()
+
+    def select(self, fr, pot, thf):
+        _, dI0, ag0, ag1, ag2 = fr
+        m, n = np.zeros(self.w * self.h, np.float32), np.zeros(3, np.int32)
+        self.L.oracle_selector_select(self.h_, _p(dI0), _p(ag0), _p(ag1), _p(ag2), _p(m), pot, C.c_float(thf), _p(n))
+        return m, n
+
+    def make_maps(self, fr, density, rec, thf):
+        _, dI0, ag0, ag1, ag2 = fr
+        m = np.zeros(self.w * self.h, np.float32)
+        n = self.L.oracle_selector_make_maps(self.h_, _p(dI0), _p(ag0), _p(ag1), _p(ag2), _p(m), C.c_float(density), rec, C.c_float(thf), 0)
+        return int(n), m
+
+
+class _RefSel:
+    """The reference's FullSystem/PixelSelector2.cpp compiled into oracle/_ref/libnalo_ref.so."""
+
+    def __init__(self, L, w, h):
+        self.L, self.w, self.h = L, w, h
+        L.ref_pin_selector_random_pattern.restype = C.POINTER(C.c_ubyte)
+        L.ref_pin_selector_create(w, h)
+
+    def settings(self, cut, add, dw, dd):
+        self.L.ref_pin_selector_settings(C.c_float(cut), C.c_float(add), C.c_float(dw), dd)
+
+    def pattern(self):
+        return np.ctypeslib.as_array(self.L.ref_pin_selector_random_pattern(), shape=(self.w * self.h,)).copy()
+
+    def set_pot(self, p):
+        self.L.ref_pin_selector_set_potential(p)
+
+    def get_pot(self):
+        return int(self.L.ref_pin_selector_get_potential())
+
+    def hists(self, fr):
+        n = (self.w // 32) * (self.h // 32)
+        a, b = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self.L.ref_pin_selector_make_hists(_p(fr[2]), _p(a), _p(b))
+        return a, b
+
+    def select(self, fr, pot, thf):
+        _, dI0, ag0, ag1, ag2 = fr
+        m, n = np.zeros(self.w * self.h, np.float32), np.zeros(3, np.int32)
+        self.L.ref_pin_selector_select(_p(dI0), _p(ag0), _p(ag1), _p(ag2), _p(m), pot, C.c_float(thf), _p(n))
+        return m, n
+
+    def make_maps(self, fr, density, rec, thf):
+        _, dI0, ag0, ag1, ag2 = fr
+        m = np.zeros(self.w * self.h, np.float32)
+        n = self.L.ref_pin_selector_make_maps(_p(dI0), _p(ag0), _p(ag1), _p(ag2), _p(m), C.c_float(density), rec, C.c_float(thf))
+        return int(n), m
+
+
+def selector_frames(w, h, n_frames=3):
+    """Seeded synthetic frames -> per frame (image, dI0 [w*h,3], ag0, ag1, ag2) from the oracle's makeImages (the inputs of the
+    selector are identical for both sides; only the selection is under test)."""
+    from nalo_slam_b200 import synth
+    from oracle import oracle_py as O
+
+    offs, _ = O.level_offsets(w, h, 3)
+    frames = []
+    for f in range(n_frames):
+        sc = synth.make_scene(w, h, seed=100 + f)
+        img = synth.render_ref(sc)
+        dIp, ag = O.make_images(img, w, h, 3)
+        n1, n2 = (w >> 1) * (h >> 1), (w >> 2) * (h >> 2)
+        frames.append((np.ascontiguousarray(img, dtype=np.float32), np.ascontiguousarray(dIp[offs[0] : offs[0] + w * h]), np.ascontiguousarray(ag[offs[0] : offs[0] + w * h]),
+                       np.ascontiguousarray(ag[offs[1] : offs[1] + n1]), np.ascontiguousarray(ag[offs[2] : offs[2] + n2])))
+    return frames
+
+
+def run_selector_cases(make_sel):
+    """make_sel(w, h) -> adapter. Returns dict name -> ndarray (maps as uint8: the reference writes 0 / 1 / 2 / 4)."""
+    out = {}
+    for (w, h) in SELECTOR_SIZES:
+        key = f"selector/{w}x{h}"
+        S = make_sel(w, h)
+        S.settings(0.5, 7.0, 0.75, 1)
+        pat = S.pattern()
+        if pat is not None:
+            out[f"{key}/pattern_head"] = pat[:4096]
+            out[f"{key}/pattern_sum"] = np.int64(pat.astype(np.int64).sum())
+        frames = selector_frames(w, h)
+        ths, thsS = S.hists(frames[0])
+        out[f"{key}/ths"], out[f"{key}/thsSmoothed"] = ths, thsS
+        for pot, thf in ((1, 1.0), (3, 1.0), (5, 2.0)):
+            m, n = S.select(frames[0], pot, thf)
+            out[f"{key}/select_p{pot}_t{thf}/map"] = m.astype(np.uint8)
+            out[f"{key}/select_p{pot}_t{thf}/n"] = n
+            assert np.array_equal(m.astype(np.uint8).astype(np.float32), m)
+        # a sequence of makeMaps calls: the potential carries over from call to call, as in FullSystem::makeNewTraces
+        S.set_pot(3)
+        for i, (density, rec, thf) in enumerate(((2000.0, 1, 1.0), (600.0, 1, 1.0), (20000.0, 1, 1.0), (4000.0, 0, 1.0), (1500.0, 1, 2.0))):
+            n, m = S.make_maps(frames[i % len(frames)], density, rec, thf)
+            out[f"{key}/makemaps{i}/map"] = m.astype(np.uint8)
+            out[f"{key}/makemaps{i}/n_pot"] = np.array([n, S.get_pot()], np.int64)
+        # other settings: no direction distribution, lower threshold offset, other level down-weight
+        S.settings(0.6, 3.0, 0.9, 0)
+        S.set_pot(2)
+        n, m = S.make_maps(frames[1], 3000.0, 1, 1.0)
+        out[f"{key}/makemaps_alt/map"] = m.astype(np.uint8)
+        out[f"{key}/makemaps_alt/n_pot"] = np.array([n, S.get_pot()], np.int64)
+        S.settings(0.5, 7.0, 0.75, 1)
+    return out
+
+
+class _GpuSel:
+    """The product: nalo_selector_* / nalo_select_pixels through the C ABI (frames built on the device by nalo_make_images)."""
+
+    def __init__(self, w, h):
+        from nalo_slam_b200 import capi
+
+        self.w, self.h = w, h
+        self.ctx = capi.Context(w, h, 3, device=0, max_frames=2)
+        self.pot = 3
+
+    def settings(self, cut, add, dw, dd):
+        self.ctx.set_params(minGradHistCut=cut, minGradHistAdd=add, gradDownweightPerLevel=dw, selectDirectionDistribution=dd)
+
+    def pattern(self):
+        return None  # not exposed by the ABI; it is exercised through the sub-sampling of makeMaps
+
+    def set_pot(self, p):
+        self.pot = p
+
+    def get_pot(self):
+        return self.pot
+
+    def hists(self, fr):
+        self.ctx.make_images(0, fr[0])
+        a, b = self.ctx.selector_make_hists(0)
+        n = (self.w // 32) * (self.h // 32)
+        return a[:n].copy(), b[:n].copy()
+
+    def select(self, fr, pot, thf):
+        self.ctx.make_images(0, fr[0])
+        self.ctx.selector_make_hists(0)
+        return self.ctx.selector_select(0, pot, thf)
+
+    def make_maps(self, fr, density, rec, thf):
+        self.ctx.make_images(0, fr[0])
+        n, m, self.pot = self.ctx.select_pixels(0, density, self.pot, rec, thf)
+        return int(n), m
+
+    def close(self):
+        self.ctx.close()

@@ -40,7 +40,7 @@ def _same_bits(a, b):
 
 
 def test_oracle_matches_reference_fixture(oracle_out, gold):
-    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith("global_calib")]
+    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/"))]
     assert len(keys) >= 30
     for k in keys:
         assert k in oracle_out, k
@@ -62,6 +62,9 @@ def test_compiled_reference_matches_fixture_and_oracle(oracle_out, gold):
     assert np.array_equal(pattern, gold["pattern"])
     for i, a in enumerate(R.ref_global_calib(L)):
         assert _same_bits(a, gold[f"global_calib/{i}"]), f"fixture is stale: global_calib/{i}"
+    sel = R.run_selector_cases(lambda w, h: R._RefSel(L, w, h))
+    for k, v in sel.items():
+        assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
 
 
 def test_fixture_is_the_weighted_gram_sum(gold):
@@ -129,3 +132,35 @@ def test_gpu_make_k_matches_set_global_calib(gold):
             Ki = K[l, 4:].reshape(3, 3)
             assert np.allclose([Ki[0, 0], Ki[1, 1], Ki[0, 2], Ki[1, 2]], g[l, 6:10], rtol=1e-6, atol=0)
         ctx.close()
+
+
+def test_pixel_selector_matches_reference(gold, oracle):
+    """a2-a4: the oracle's PixelSelector restatement against the outputs of the reference's own FullSystem/PixelSelector2.cpp
+    (compiled unmodified; fixture): glibc randomPattern, ths / thsSmoothed, select() maps and per-level counts at fixed
+    potentials, and a sequence of makeMaps calls with the potential carried over (recursion, sub-sampling) - bit-exact."""
+    got = R.run_selector_cases(lambda w, h: R._OracleSel(oracle.lib(), w, h))
+    keys = [k for k in gold if k.startswith("selector/")]
+    assert len(keys) == 44 and set(keys) == set(got)
+    for k in keys:
+        assert _same_bits(got[k], gold[k]), f"oracle PixelSelector differs from the reference: {k}"
+    assert int(gold["selector/1248x384/makemaps0/n_pot"][0]) > 1500  # the cases select something
+
+
+@pytest.mark.gpu
+def test_gpu_pixel_selector_matches_reference(gold):
+    """a2-a4 on the device (nalo_make_images -> nalo_selector_make_hists / nalo_selector_select / nalo_select_pixels)
+    against the same reference outputs: selection maps, counts, thresholds and potentials bit-exact."""
+    sels = []
+
+    def mk(w, h):
+        sels.append(R._GpuSel(w, h))
+        return sels[-1]
+
+    try:
+        got = R.run_selector_cases(mk)
+    finally:
+        for s in sels:
+            s.close()
+    for k, v in got.items():
+        assert _same_bits(v, gold[k]), f"device PixelSelector differs from the reference: {k}"
+    assert len(got) == 40  # everything but the pattern entries
