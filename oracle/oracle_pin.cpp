@@ -56,4 +56,7 @@ void oracle_pin_aff_from_to(int n, const double* in, double* out) {
     orc::aff_from_to((float)p[0], (float)p[1], p[2], p[3], p[4], p[5], out + 2 * i);
   }
 }
+// rotation matrix (row-major, double) of a pose7 = {qx, qy, qz, qw, tx, ty, tz} exactly as the oracle's tracker derives
+// it, so that the reference's calcRes / calcGSSSE (oracle/ref_tracker.cpp) can be given the same transform
+void oracle_pin_pose_to_R(const double* pose7, double* R9) { orc::quat_to_R(pose7, R9); }
 }  // extern "C"

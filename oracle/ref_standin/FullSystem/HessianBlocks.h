@@ -4,6 +4,8 @@
 // members of a FrameHessian (src/FullSystem/HessianBlocks.h:128-137: dI, dIp, absSquaredGrad; :180 mask). Declaring just
 // those lets PixelSelector2.cpp itself (makeHists, select, makeMaps: the a2-a4 rows) be compiled unmodified from
 // /root/reference/src and run against the oracle's restatement. Nothing else of FrameHessian is implied.
+// CoarseTracker::calcRes / calcGSSSE (extracted verbatim by ref_extract.py) additionally read ab_exposure and dIp, and use
+// the SCALE_* constants of the real header, which `make ref` copies out of it (scale_defs.inc) instead of restating them.
 #pragma once
 #include <fstream>
 #include <iostream>
@@ -11,6 +13,7 @@
 
 #include "util/NumType.h"
 #include "util/globalCalib.h"
+#include "scale_defs.inc"  // `#define SCALE_*` lines of the reference's FullSystem/HessianBlocks.h (generated into oracle/_ref/)
 
 namespace dso {
 struct FrameHessian {
@@ -18,5 +21,6 @@ struct FrameHessian {
   Eigen::Vector3f* dIp[PYR_LEVELS];        // per level
   float* absSquaredGrad[PYR_LEVELS];       // per level dx*dx + dy*dy
   float* mask;                             // (only read by the lidar / mask variants, which are out of scope)
+  float ab_exposure;                       // HessianBlocks.h:139, read by CoarseTracker::calcRes / calcGSSSE
 };
 }  // namespace dso

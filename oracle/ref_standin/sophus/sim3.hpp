@@ -1,7 +1,3 @@
-// sophus stand-in (see ../Eigen/Core): util/NumType.h only names these types in typedefs.
+// sophus stand-in (see se3.hpp)
 #pragma once
-namespace Sophus {
-struct SE3d;
-struct Sim3d;
-struct SO3d;
-}  // namespace Sophus
+#include "sophus/se3.hpp"

@@ -22,6 +22,10 @@ settings, pattern = R.ref_settings(L)
 out["settings"] = np.array([settings[k] for k in R.SETTINGS_NAMES], np.float64)
 out["pattern"] = pattern
 out.update(R.run_selector_cases(lambda w, h: R._RefSel(L, w, h)))
+from oracle import oracle_py as O  # noqa: E402  (inputs of the tracker cases: pyramids, camera table, reference cloud)
+
+for photo in R.TRACKER_PHOTO:
+    out.update(R.run_tracker_cases_ref(R.tracker_problem(photo), L, O.lib()))
 for i, a in enumerate(R.ref_global_calib(L)):
     out[f"global_calib/{i}"] = a
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_pin.npz"), **out)

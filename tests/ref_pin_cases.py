@@ -316,3 +316,99 @@ class _GpuSel:
 
     def close(self):
         self.ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- CoarseTracker calcRes / calcGSSSE (a6, a7)
+TRACKER_SIZE = (320, 192, 4)
+
+
+TRACKER_PHOTO = {"A": (1.0, 1.0, 0.0, 0.0), "B": (0.02, 0.025, 0.01, -0.8)}  # exposure_ref, exposure_new, a_ref, b_ref
+
+
+def _digest(wbuf):
+    """(count, SHA-256 of the bytes) of the eight warped buffers: keeps the fixture small, still a bit-exact check."""
+    import hashlib
+
+    b = np.ascontiguousarray(wbuf, dtype=np.float32)
+    return np.int64(b.shape[1]), np.frombuffer(hashlib.sha256(b.tobytes()).digest(), dtype=np.uint8).copy()
+
+
+def tracker_problem(photo="A"):
+    """One seeded dense frame pair at 320x192, 4 levels (the tests' small pair): oracle pyramids, the oracle's makeK table
+    and its dense reference cloud (a5), plus a list of evaluation points (level, pose7, aff2, cutoff)."""
+    from nalo_slam_b200 import synth
+    from oracle import oracle_py as O
+
+    w, h, L = TRACKER_SIZE
+    sc = synth.make_scene(w, h, seed=11)
+    rng = np.random.default_rng(11)
+    xi, aff = synth.random_motion(rng, 0.5)
+    gt = synth.se3_exp(xi)
+    ref, new = synth.render_ref(sc), synth.render_new(sc, gt, aff)
+    dref, agref = O.make_images(ref, w, h, L)
+    dnew, _ = O.make_images(new, w, h, L)
+    idw, ws = synth.dense_reference_maps(sc, agref[: w * h])
+    T = O.Tracker(w, h, L)
+    T.makeK(*sc.K)
+    e_ref, e_new, a_ref, b_ref = TRACKER_PHOTO[photo]
+    T.set_ref_frame(dref, exposure=e_ref, aff=(a_ref, b_ref))
+    T.set_new_frame(dnew, exposure=e_new)
+    T.make_depth_dense(idw, ws)
+    evals = []
+    ident = synth.pose_identity()
+    for lvl in range(L - 1, -1, -1):
+        evals.append((lvl, ident, (0.0, 0.0), 20.0 * (1 if lvl else 1)))
+        evals.append((lvl, np.asarray(gt, dtype=np.float64), (float(aff[0]), float(aff[1])), 20.0))
+        xi2, aff2 = synth.random_motion(rng, 1.5)
+        evals.append((lvl, np.asarray(synth.se3_exp(xi2), dtype=np.float64), (float(aff2[0]), float(aff2[1])), 5.0))  # low cutoff: saturated terms
+    return dict(w=w, h=h, L=L, T=T, dnew=dnew, evals=evals, exposures=(e_ref, e_new), aff_ref=(a_ref, b_ref), tag=photo,
+                ref_img=ref, new_img=new, idw=idw, ws=ws, K=sc.K)
+
+
+def run_tracker_cases_oracle(P):
+    out = {}
+    T = P["T"]
+    for k, (lvl, pose, aff, cutoff) in enumerate(P["evals"]):
+        rs, _ = T.calc_res(lvl, pose, aff, cutoff)
+        wbuf = T.warped()
+        H, b = T.calc_gs(lvl, pose, aff)
+        g = f"tracker/{P['tag']}/{k}"
+        out[f"{g}/rs"], out[f"{g}/H"], out[f"{g}/b"] = rs, H, b
+        out[f"{g}/warped_n"], out[f"{g}/warped_sha256"] = _digest(wbuf)
+    return out
+
+
+def run_tracker_cases_ref(P, L_ref, L_oracle):
+    """The reference's CoarseTracker::calcRes / calcGSSSE on the same cloud, pyramids, camera table and transforms."""
+    from oracle import oracle_py as O
+
+    w, h, L = P["w"], P["h"], P["L"]
+    T = P["T"]
+    K13 = np.ascontiguousarray(T.get_K(), dtype=np.float32)
+    L_ref.ref_pin_tracker_create(w, h, L, _p(K13))
+    L_ref.ref_pin_tracker_settings(C.c_float(9.0))
+    L_ref.ref_pin_tracker_set_photometric(C.c_float(P["exposures"][0]), C.c_float(P["exposures"][1]), C.c_double(P["aff_ref"][0]), C.c_double(P["aff_ref"][1]))
+    offs, _ = O.level_offsets(w, h, L)
+    for lvl in range(L):
+        u, v, idp, col = T.get_pc(lvl)
+        L_ref.ref_pin_tracker_set_pc(lvl, int(u.size), _p(u), _p(v), _p(idp), _p(col))
+        n = (w >> lvl) * (h >> lvl)
+        img = np.ascontiguousarray(P["dnew"][offs[lvl] : offs[lvl] + n])
+        L_ref.ref_pin_tracker_set_new_level(lvl, _p(img))
+    out = {}
+    for k, (lvl, pose, aff, cutoff) in enumerate(P["evals"]):
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        R9 = np.zeros(9, np.float64)
+        L_oracle.oracle_pin_pose_to_R(_p(pose), _p(R9))
+        t3 = np.ascontiguousarray(pose[4:7])
+        a2 = np.array(aff, np.float64)
+        rs = np.zeros(6, np.float64)
+        n = L_ref.ref_pin_tracker_calc_res(lvl, _p(R9), _p(t3), _p(a2), C.c_float(cutoff), _p(rs))
+        wbuf = np.zeros((8, n), np.float32)
+        L_ref.ref_pin_tracker_get_warped(_p(wbuf))
+        H, b = np.zeros((8, 8), np.float64), np.zeros(8, np.float64)
+        L_ref.ref_pin_tracker_calc_gs(lvl, _p(R9), _p(t3), _p(a2), _p(H), _p(b))
+        g = f"tracker/{P['tag']}/{k}"
+        out[f"{g}/rs"], out[f"{g}/H"], out[f"{g}/b"] = rs, H, b
+        out[f"{g}/warped_n"], out[f"{g}/warped_sha256"] = _digest(wbuf)
+    return out
