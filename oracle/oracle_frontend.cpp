@@ -16,8 +16,10 @@
 //   * ths / thsSmoothed are zero-initialised, so the ragged bottom strip (y >= 32*h32) and the wrapped
 //     column (x >= 32*w32) read whatever the reference's index formula lands on, with never-written
 //     slots being 0.
-// Parity unpinned by the reference (no tests / golden vectors exist for this path); pinned by the
-// analytic KATs in tests/test_oracle_frontend.py. Build with -ffp-contract=off (see Makefile).
+// Parity: the PixelSelector part (constructor / randomPattern, makeHists, select, makeMaps) is PINNED bit for bit to the
+// reference's own FullSystem/PixelSelector2.cpp compiled by `make ref` (oracle/_ref; tests/test_ref_pin.py, fixture
+// tests/golden/ref_pin.npz). makeImages is unpinned by the reference (no tests / golden vectors upstream, the file cannot
+// be compiled here); pinned by the analytic KATs in tests/test_oracle_frontend.py. Build with -ffp-contract=off.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
