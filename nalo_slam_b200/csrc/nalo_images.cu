@@ -24,6 +24,12 @@ struct PyrLevels {
   int total;                       // total dense pixels
 };
 
+// float -> int as the reference's x86 build does it (CalibHessian::getBGradOnly, HessianBlocks.h:404: `int c = color+0.5f`):
+// cvttss2si returns the "integer indefinite" 0x80000000 for NaN and for anything outside int range, where CUDA's
+// conversion saturates (+Inf -> INT_MAX). After the clamp to [5, 250] the difference shows for +Inf / huge pixels only:
+// index 5 on x86, 250 with the saturating conversion. Found by the pin against the reference's own makeImages
+// (tests/test_ref_pin.py, non-finite image with an inverse-response table).
+__device__ __forceinline__ int cvt_x86(float t) { return (t >= -2147483648.f && t < 2147483648.f) ? (int)t : (int)0x80000000; }
 __device__ __forceinline__ float box4(float a, float b, float c, float d) {
   return __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d));
 }
@@ -102,7 +108,7 @@ __global__ void __launch_bounds__(256) grad_kernel(const float* __restrict__ col
     if (!isfinite(dy)) dy = 0.f;
     ag = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
     if (useB) {
-      int c = (int)__fadd_rn(I, 0.5f);
+      int c = cvt_x86(__fadd_rn(I, 0.5f));
       if (c < 5) c = 5;
       if (c > 250) c = 250;
       const float gw = __fsub_rn(__ldg(B + c + 1), __ldg(B + c));
@@ -154,7 +160,7 @@ __device__ __forceinline__ void fused_grad_store(const float* __restrict__ S, in
     if (!isfinite(dy)) dy = 0.f;
     ag = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
     if (useB) {
-      int cc = (int)__fadd_rn(I, 0.5f);
+      int cc = cvt_x86(__fadd_rn(I, 0.5f));
       if (cc < 5) cc = 5;
       if (cc > 250) cc = 250;
       const float gw = __fsub_rn(__ldg(B + cc + 1), __ldg(B + cc));

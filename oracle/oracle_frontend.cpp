@@ -18,8 +18,8 @@
 //     slots being 0.
 // Parity: the PixelSelector part (constructor / randomPattern, makeHists, select, makeMaps) is PINNED bit for bit to the
 // reference's own FullSystem/PixelSelector2.cpp compiled by `make ref` (oracle/_ref; tests/test_ref_pin.py, fixture
-// tests/golden/ref_pin.npz). makeImages is unpinned by the reference (no tests / golden vectors upstream, the file cannot
-// be compiled here); pinned by the analytic KATs in tests/test_oracle_frontend.py. Build with -ffp-contract=off.
+// tests/golden/ref_pin.npz), and so is makeImages (the reference's FrameHessian::makeImages copied verbatim at build time,
+// oracle/ref_images.cpp). Analytic KATs on top: tests/test_oracle_frontend.py. Build with -ffp-contract=off.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

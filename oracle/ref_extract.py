@@ -3,8 +3,8 @@ Copies whole function definitions VERBATIM out of a reference source file into a
 (git-ignored, never committed), so that functions of a translation unit that cannot be compiled as a whole here
 (FullSystem/CoarseTracker.cpp needs OpenCV, PCL, Sophus and most of DSO) can still be compiled and run as the reference
 wrote them: ref_tracker.cpp #includes the intermediate inside `namespace dso`.
-A definition starts at the line that begins with the given signature prefix and ends at the first following line that is
-exactly `}` (the reference closes every top-level function in column 0).
+A definition starts at the line that begins with the given signature prefix (leading whitespace included) and ends at the
+first following line that is exactly `}` at the same indentation (the reference closes every function that way).
 usage: ref_extract.py <source> <out.inc> <signature prefix> [<signature prefix> ...]
        ref_extract.py --defines <header> <out.inc> <macro prefix>      (copies `#define <prefix>...` lines)"""
 import sys
@@ -24,8 +24,9 @@ def main():
         starts = [i for i, l in enumerate(text) if l.startswith(sig)]
         assert len(starts) == 1, f"{sig!r}: {len(starts)} definitions in {src}"
         i = starts[0]
+        indent = text[i][: len(text[i]) - len(text[i].lstrip())]  # a member function defined inside a class ends at `<indent>}`
         j = i
-        while text[j].rstrip() != "}":
+        while text[j].rstrip("\r\n ") != indent + "}":
             j += 1
         chunks.append(f"// ---- {src}:{i + 1}-{j + 1} (verbatim)\n" + "\n".join(text[i : j + 1]) + "\n")
     open(out, "w").write("\n".join(chunks))

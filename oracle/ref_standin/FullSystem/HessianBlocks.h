@@ -16,11 +16,19 @@
 #include "scale_defs.inc"  // `#define SCALE_*` lines of the reference's FullSystem/HessianBlocks.h (generated into oracle/_ref/)
 
 namespace dso {
+// CalibHessian: FrameHessian::makeImages reads the inverse-response table through getBGradOnly, whose definition is the
+// reference's own (copied verbatim out of the real header at build time)
+struct CalibHessian {
+  float Binv[256];
+  float B[256];
+#include "calib_bgrad_extract.inc"
+};
 struct FrameHessian {
   Eigen::Vector3f* dI;                     // level-0 {I, dx, dy}
   Eigen::Vector3f* dIp[PYR_LEVELS];        // per level
   float* absSquaredGrad[PYR_LEVELS];       // per level dx*dx + dy*dy
   float* mask;                             // (only read by the lidar / mask variants, which are out of scope)
   float ab_exposure;                       // HessianBlocks.h:139, read by CoarseTracker::calcRes / calcGSSSE
+  void makeImages(float* color, CalibHessian* HCalib);  // HessianBlocks.h:161; definition: the reference's (ref_images.cpp)
 };
 }  // namespace dso

@@ -412,3 +412,57 @@ def run_tracker_cases_ref(P, L_ref, L_oracle):
         out[f"{g}/rs"], out[f"{g}/H"], out[f"{g}/b"] = rs, H, b
         out[f"{g}/warped_n"], out[f"{g}/warped_sha256"] = _digest(wbuf)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- FrameHessian::makeImages (a1)
+IMAGE_CASES = [(320, 192, 4), (1241, 376, 5), (640, 480, 4)]
+
+
+def _digest_nan_aware(a):
+    """SHA-256 of a float32 array with every NaN replaced by one canonical pattern (NaN payloads are not compared)."""
+    import hashlib
+
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    canon = np.where(np.isnan(a), np.float32(0), a).view(np.uint32) | (np.isnan(a).astype(np.uint32) * np.uint32(0x7FC00000))
+    return np.frombuffer(hashlib.sha256(canon.tobytes()).digest(), dtype=np.uint8).copy()
+
+
+def image_inputs():
+    """-> list of (key, w, h, levels, image, B256 or None): plain, with an inverse-response table, with non-finite pixels."""
+    from nalo_slam_b200 import synth
+
+    cases = []
+    for (w, h, lv) in IMAGE_CASES:
+        sc = synth.make_scene(w, h, seed=3)
+        img = np.ascontiguousarray(synth.render_ref(sc), dtype=np.float32)
+        bad = img.copy()
+        bad[50, 60] = np.nan
+        bad[10, 11] = np.inf
+        B = (np.linspace(0, 255, 256) ** 1.1 / 255 ** 0.1).astype(np.float32)
+        for name, im, b in (("plain", img, None), ("B", img, B), ("nonfinite", bad, None), ("nonfiniteB", bad, B)):
+            cases.append((f"images/{w}x{h}x{lv}/{name}", w, h, lv, im, b))
+    return cases
+
+
+def run_image_cases(make_images):
+    """make_images(img, w, h, levels, B256) -> (dIp [tot,3], absgrad [tot]); returns digests."""
+    out = {}
+    for key, w, h, lv, im, b in image_inputs():
+        d, a = make_images(im, w, h, lv, b)
+        out[f"{key}/dIp_sha256"], out[f"{key}/absgrad_sha256"] = _digest_nan_aware(d), _digest_nan_aware(a)
+        out[f"{key}/n_nan"] = np.int64(np.isnan(d).sum())
+    return out
+
+
+def ref_make_images(L):
+    from oracle import oracle_py as O
+
+    def f(img, w, h, lv, B):
+        _, tot = O.level_offsets(w, h, lv)
+        d, a = np.zeros((tot, 3), np.float32), np.zeros(tot, np.float32)
+        img = np.ascontiguousarray(img, dtype=np.float32).reshape(-1)
+        Bp = None if B is None else np.ascontiguousarray(B, dtype=np.float32)
+        L.ref_pin_make_images(w, h, lv, _p(img), None if Bp is None else _p(Bp), _p(d), _p(a))
+        return d, a
+
+    return f

@@ -44,7 +44,7 @@ def _same_bits(a, b):
 
 
 def test_oracle_matches_reference_fixture(oracle_out, gold):
-    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/", "tracker/"))]
+    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/", "tracker/", "images/"))]
     assert len(keys) >= 30
     for k in keys:
         assert k in oracle_out, k
@@ -74,6 +74,8 @@ def test_compiled_reference_matches_fixture_and_oracle(oracle_out, gold):
     for photo in R.TRACKER_PHOTO:
         for k, v in R.run_tracker_cases_ref(R.tracker_problem(photo), L, O.lib()).items():
             assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
+    for k, v in R.run_image_cases(R.ref_make_images(L)).items():
+        assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
 
 
 def test_fixture_is_the_weighted_gram_sum(gold):
@@ -155,6 +157,19 @@ def test_pixel_selector_matches_reference(gold, oracle):
     assert int(gold["selector/1248x384/makemaps0/n_pot"][0]) > 1500  # the cases select something
 
 
+def test_make_images_matches_reference(gold, oracle):
+    """a1: the oracle's makeImages against the reference's own FrameHessian::makeImages (compiled verbatim,
+    oracle/ref_images.cpp; fixture holds SHA-256 digests of its outputs): 320x192x4, 1241x376x5 (odd width), 640x480x4,
+    each plain, with an inverse-response table (getBGradOnly weighting), and with NaN / Inf pixels - bit-exact over every
+    level (NaN payloads canonicalised; the rows the reference leaves uninitialised are 0 by this repository's definition)."""
+    got = R.run_image_cases(lambda im, w, h, lv, B: oracle.make_images(im, w, h, lv, B))
+    keys = [k for k in gold if k.startswith("images/")]
+    assert len(keys) == 36 and set(keys) == set(got)
+    for k in keys:
+        assert _same_bits(got[k], gold[k]), f"oracle makeImages differs from the reference: {k}"
+    assert int(gold["images/1241x376x5/nonfinite/n_nan"]) >= 4
+
+
 def test_calc_res_and_gs_match_reference(gold, oracle):
     """a6 + a7: the oracle's calcRes / calcGSSSE against the outputs of the reference's own CoarseTracker::calcRes and
     CoarseTracker::calcGSSSE (compiled verbatim, oracle/ref_tracker.cpp; fixture) on a dense 320x192 x 4-level pair, two
@@ -227,3 +242,25 @@ def test_gpu_calc_res_and_gs_match_reference(gold):
                 assert np.all(np.abs(b - b_ref) <= 1e-4 * d * np.sqrt(rr) + 1e-300), (g, np.max(np.abs(b - b_ref) / (d * np.sqrt(rr) + 1e-300)))
         finally:
             ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_make_images_matches_reference(gold):
+    """a1 on the device (nalo_make_images, host copies in the reference's layout) against the digests of the reference's own
+    FrameHessian::makeImages outputs: bit-exact for every level of every case."""
+    from nalo_slam_b200 import capi
+
+    ctxs = {}
+
+    def mk(img, w, h, lv, B):
+        if (w, h, lv) not in ctxs:
+            ctxs[(w, h, lv)] = capi.Context(w, h, lv, device=0, max_frames=1)
+        return ctxs[(w, h, lv)].make_images(0, img, B256=B, want_host=True)
+
+    try:
+        got = R.run_image_cases(mk)
+    finally:
+        for c in ctxs.values():
+            c.close()
+    for k, v in got.items():
+        assert _same_bits(v, gold[k]), f"device makeImages differs from the reference: {k}"
