@@ -14,8 +14,9 @@
 // allPoints order, residuals in residualsAll order) and therefore the fp32 summation order of one
 // reference worker thread (tid 0, EnergyFunctional.cpp:208-214 non-MT branch) is reproduced exactly.
 // Parity: the accumulator classes (AccApprox / AccXX / AccX) are pinned bit for bit to the reference's own
-// MatrixAccumulators.h compiled by `make ref` (tests/test_ref_pin.py); addPoint / stitch logic is unpinned by the
-// reference (no tests upstream) and pinned by closed-form KATs in tests/test_oracle_ba.py.
+// MatrixAccumulators.h compiled by `make ref`, and addPoint<0/1/2>, the Schur addPoint and takeDataF to the reference's
+// own definitions copied verbatim at build time (oracle/ref_ba.cpp, tests/test_ref_pin.py); the stitch logic is unpinned
+// by the reference (no tests upstream) and pinned by closed-form KATs in tests/test_oracle_ba.py.
 #include <xmmintrin.h>
 
 #include <atomic>

@@ -27,6 +27,7 @@ from oracle import oracle_py as O  # noqa: E402  (inputs of the tracker cases: p
 for photo in R.TRACKER_PHOTO:
     out.update(R.run_tracker_cases_ref(R.tracker_problem(photo), L, O.lib()))
 out.update(R.run_image_cases(R.ref_make_images(L)))
+out.update(R.compact(R.run_ba_cases_ref(R.ba_problem(), L)))
 for i, a in enumerate(R.ref_global_calib(L)):
     out[f"global_calib/{i}"] = a
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_pin.npz"), **out)

@@ -466,3 +466,72 @@ def ref_make_images(L):
         return d, a
 
     return f
+
+
+# ---------------------------------------------------------------------------------------------- windowed-BA accumulation (a9, a10)
+def ba_problem():
+    """Seeded synthetic window: 7 keyframes x 500 points, residuals to the other frames, 20 % linearized, some dropped."""
+    from nalo_slam_b200 import synth
+
+    return synth.make_ba_problem(nf=7, pts_per_frame=500, seed=4, lin_fraction=0.2)
+
+
+def run_ba_cases_oracle(prob):
+    from oracle import oracle_py as O
+
+    out = {}
+    pp = {}
+    for mode in (0, 1, 2):
+        H, p6, nres = O.ba_top(prob, mode=mode, nThreads=1)
+        out[f"ba/top{mode}/H"], out[f"ba/top{mode}/perPoint"], out[f"ba/top{mode}/nres"] = H, p6, np.int64(nres)
+        pp[mode] = p6
+    J = O.ba_take_data(prob)
+    out["ba/JpJdF"] = J
+    for shift in (1, 0):
+        r = O.ba_sc(prob, J, pp[0], pp[1], shiftPriorToZero=bool(shift), nThreads=1)
+        for k, v in r.items():
+            out[f"ba/sc{shift}/{k}"] = v
+    return out
+
+
+def run_ba_cases_ref(prob, L):
+    """The reference's own addPoint<0/1/2>, takeDataF and Schur addPoint (oracle/ref_ba.cpp) on the same flat problem."""
+    nf, nP, nR = prob["nf"], prob["n_pts"], prob["n_res"]
+    out = {}
+    pp = {}
+    for mode in (0, 1, 2):
+        H, p6, nres = np.zeros((nf * nf, 13, 13)), np.zeros((nP, 6), np.float32), C.c_int(0)
+        L.ref_pin_ba_top(mode, nf, nP, nR, _p(prob["rec"]), _p(prob["res_toZero"]), _p(prob["pt_begin"]), _p(prob["pt_res"]),
+                         _p(prob["deltaF"]), _p(prob["adHTdeltaF"]), _p(prob["cDeltaF"]), _p(H), _p(p6), C.byref(nres))
+        out[f"ba/top{mode}/H"], out[f"ba/top{mode}/perPoint"], out[f"ba/top{mode}/nres"] = H, p6, np.int64(nres.value)
+        pp[mode] = p6
+    J = np.zeros((nR, 8), np.float32)
+    L.ref_pin_ba_take_data(nR, _p(prob["rec"]), _p(J))
+    out["ba/JpJdF"] = J
+    for shift in (1, 0):
+        A, Lp = pp[0], pp[1]
+        cols = lambda a: (np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1]), np.ascontiguousarray(a[:, 2:6]))
+        HddA, bdA, HcdA = cols(A)
+        HddL, bdL, HcdL = cols(Lp)
+        accD, accE, accEB = np.zeros((nf**3, 8, 8)), np.zeros((nf**2, 8, 4)), np.zeros((nf**2, 8))
+        accHcc, accbc, p3 = np.zeros((4, 4)), np.zeros(4), np.zeros((nP, 3), np.float32)
+        L.ref_pin_ba_sc(nf, nP, nR, _p(prob["rec"]), _p(J), _p(prob["pt_begin"]), _p(prob["pt_res"]), _p(HddA), _p(bdA), _p(HcdA),
+                        _p(HddL), _p(bdL), _p(HcdL), _p(prob["priorF"]), _p(prob["deltaF"]), shift, _p(accD), _p(accE), _p(accEB),
+                        _p(accHcc), _p(accbc), _p(p3))
+        for k, v in dict(accD=accD, accE=accE, accEB=accEB, accHcc=accHcc, accbc=accbc, perPoint=p3).items():
+            out[f"ba/sc{shift}/{k}"] = v
+    return out
+
+
+def compact(out, limit=65536):
+    """Arrays above `limit` bytes are replaced by their SHA-256 (bit-exactness is still what is compared)."""
+    import hashlib
+
+    res = {}
+    for k, v in out.items():
+        v = np.ascontiguousarray(v)
+        if v.nbytes > limit:
+            res[k + "#sha256"] = np.frombuffer(hashlib.sha256(v.tobytes()).digest(), dtype=np.uint8).copy()
+        else:
+            res[k] = v
+    return res
