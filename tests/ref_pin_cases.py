@@ -523,7 +523,7 @@ def run_ba_cases_ref(prob, L):
     return out
 
 
-def compact(out, limit=65536):
+def compact(out, limit=70000):
     """Arrays above `limit` bytes are replaced by their SHA-256 (bit-exactness is still what is compared)."""
     import hashlib
 
