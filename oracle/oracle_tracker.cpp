@@ -17,8 +17,8 @@
 //   bilinear = ((dxdy*p11 + (dy-dxdy)*p01) + (dx-dxdy)*p10) + (((1-dx)-dy)+dxdy)*p00
 // Build with -ffp-contract=off (see Makefile). Parity: calcRes and calcGSSSE are PINNED bit for bit to the reference's
 // own CoarseTracker::calcRes / calcGSSSE (copied verbatim at build time and compiled by `make ref`: oracle/ref_tracker.cpp,
-// tests/test_ref_pin.py, fixture tests/golden/ref_pin.npz); makeCoarseDepthL0 and the LM loop of trackNewestCoarse are
-// unpinned by the reference (no tests upstream) and pinned by the analytic KATs in tests/test_oracle_tracker.py.
+// tests/test_ref_pin.py, fixture tests/golden/ref_pin.npz), and so is makeCoarseDepthL0 in its sparse form; the LM loop of
+// trackNewestCoarse is unpinned by the reference (no tests upstream) and pinned by the analytic KATs in tests/test_oracle_tracker.py.
 #include <xmmintrin.h>
 
 #include <algorithm>

@@ -9,10 +9,12 @@
 #pragma once
 #include <fstream>
 #include <iostream>
+#include <utility>
 #include <vector>
 
 #include "util/NumType.h"
 #include "util/globalCalib.h"
+#include "FullSystem/Residuals.h"  // the reference's real header (ResState, PointFrameResidual), as the real HessianBlocks.h includes it
 #include "scale_defs.inc"  // `#define SCALE_*` lines of the reference's FullSystem/HessianBlocks.h (generated into oracle/_ref/)
 
 namespace dso {
@@ -23,12 +25,23 @@ struct CalibHessian {
   float B[256];
 #include "calib_bgrad_extract.inc"
 };
+class EFPoint;
+// PointHessian: CoarseTracker::makeCoarseDepthL0 reads lastResiduals[0] and efPoint->HdiF (HessianBlocks.h:425, 476)
+struct PointHessian {
+  EFPoint* efPoint;
+  std::pair<PointFrameResidual*, ResState> lastResiduals[2];
+  bool onground = false;  // :HessianBlocks.h, written by the plane branch only
+};
 struct FrameHessian {
   Eigen::Vector3f* dI;                     // level-0 {I, dx, dy}
   Eigen::Vector3f* dIp[PYR_LEVELS];        // per level
   float* absSquaredGrad[PYR_LEVELS];       // per level dx*dx + dy*dy
   float* mask;                             // (only read by the lidar / mask variants, which are out of scope)
   float ab_exposure;                       // HessianBlocks.h:139, read by CoarseTracker::calcRes / calcGSSSE
+  std::vector<PointHessian*> pointHessians;  // HessianBlocks.h:153 (makeCoarseDepthL0 walks the active points of every keyframe)
+  float* last_ground;                        // :138-140, only touched by the plane branch of makeCoarseDepthL0 (dense_track)
+  Eigen::Matrix<float, 4, 1> groundP;
+  bool haveground = false;
   void makeImages(float* color, CalibHessian* HCalib);  // HessianBlocks.h:161; definition: the reference's (ref_images.cpp)
 };
 }  // namespace dso

@@ -9,12 +9,15 @@
 // buffer it fills (u, v, idepth, dx, dy, residual, weight, refColor, count incl. the zero padding), and H / b of calcGSSSE.
 // The camera table (K, Ki per level) is set from the caller: the 3x3 inverse inside makeK is Eigen arithmetic that the
 // stand-in would only imitate.
+#define NDEBUG  // as in the reference's Release build: makeCoarseDepthL0 asserts on bookkeeping (efResidual, target) that is not modelled here
 #include <algorithm>
+#include <cfloat>
 #include <cstdint>
 #define private public  // this translation unit only
 #include "FullSystem/CoarseTracker.h"
 #undef private
 #include "FullSystem/HessianBlocks.h"  // stub: FrameHessian{dI, dIp, absSquaredGrad, mask, ab_exposure} + the reference's SCALE_*
+#include "OptimizationBackend/EnergyFunctionalStructs.h"  // real: EFPoint::HdiF
 #include "IOWrapper/ImageDisplay.h"
 #include "util/globalCalib.h"
 #include "util/globalFuncs.h"
@@ -26,10 +29,19 @@ namespace dso {
 using namespace dso;
 
 namespace dso { namespace IOWrap { int waitKey(int) { return 0; } } }
+// members the extracted code refers to but never reaches here: the plane branch of makeCoarseDepthL0 (its step 6, PCL
+// RANSAC - out of scope) only runs with dense_track set, which the driver clears
+namespace dso {
+void CoarseTracker::makeMaskDistMap(float*, std::vector<std::vector<Vec4f>>&, float*, float*, float*, int) {}
+bool CoarseTracker::fitPlane(std::vector<Vec4f>, Vec3f&, float&, float&) { return false; }
+PointFrameResidual::PointFrameResidual() {}   // (defined in FullSystem/Residuals.cpp; plain construction is all that is needed)
+PointFrameResidual::~PointFrameResidual() {}
+int PointFrameResidual::instanceCounter = 0;
+}  // namespace dso
 
 static CoarseTracker* g_trk = nullptr;
 static FrameHessian g_ref, g_new;
-static std::vector<std::vector<float>> g_newLevels;
+static std::vector<std::vector<float>> g_newLevels, g_refLevels;
 
 extern "C" {
 
@@ -51,6 +63,7 @@ void ref_pin_tracker_create(int w, int h, int levels, const float* K13) {
   g_trk->lastRef = &g_ref;
   g_trk->newFrame = &g_new;
   g_newLevels.assign(levels, {});
+  g_refLevels.assign(levels, {});
 }
 void ref_pin_tracker_settings(float huberTH) { setting_huberTH = huberTH; }
 void ref_pin_tracker_set_pc(int lvl, int n, const float* u, const float* v, const float* id, const float* color) {
@@ -92,5 +105,45 @@ void ref_pin_tracker_calc_gs(int lvl, const double* R9, const double* t3, const 
   Mat88 H; Vec8 b;
   g_trk->calcGSSSE(lvl, H, b, make_se3(R9, t3), AffLight(aff2[0], aff2[1]));
   for (int r = 0; r < 8; r++) { for (int c = 0; c < 8; c++) H64[8 * r + c] = H(r, c); b8[r] = b[r]; }
+}
+// ---- a5: CoarseTracker::makeCoarseDepthL0 (CoarseTracker.cpp:382-538 + the plane branch, which is switched off)
+void ref_pin_tracker_set_ref_level(int lvl, const float* dIp3) {
+  const size_t n = (size_t)g_trk->w[lvl] * g_trk->h[lvl] * 3;
+  g_refLevels[lvl].assign(dIp3, dIp3 + n);
+  g_ref.dIp[lvl] = reinterpret_cast<Eigen::Vector3f*>(g_refLevels[lvl].data());
+  if (lvl == 0) g_ref.dI = g_ref.dIp[0];
+}
+// n active points of one host keyframe, each with an IN residual to the reference frame:
+// centerProjectedTo = (u, v, idepth) and EFPoint::HdiF = hdi - what step 1 reads
+void ref_pin_tracker_make_depth_sparse(int n, const float* u, const float* v, const float* idepth, const float* hdi) {
+  dense_track = false;
+  std::vector<PointFrameResidual> res(n);
+  std::vector<PointHessian> ph(n);
+  std::vector<char> efMem(sizeof(EFPoint) * (size_t)n + 64);
+  EFPoint* ef = reinterpret_cast<EFPoint*>((reinterpret_cast<uintptr_t>(efMem.data()) + 63) & ~(uintptr_t)63);  // (no constructor: it needs a PointHessian of the real kind)
+  FrameHessian host;
+  for (int i = 0; i < n; i++) {
+    res[i].centerProjectedTo = Vec3f(u[i], v[i], idepth[i]);
+    res[i].target = &g_ref;
+    res[i].efResidual = nullptr;
+    ef[i].HdiF = hdi[i];
+    ph[i].efPoint = &ef[i];
+    ph[i].lastResiduals[0] = std::make_pair(&res[i], ResState::IN);
+    ph[i].lastResiduals[1] = std::make_pair((PointFrameResidual*)nullptr, ResState::OOB);
+    host.pointHessians.push_back(&ph[i]);
+  }
+  std::vector<FrameHessian*> frames = {&host, &g_ref};
+  g_trk->lastRef = &g_ref;
+  g_trk->makeCoarseDepthL0(frames);
+}
+int ref_pin_tracker_pc_n(int lvl) { return g_trk->pc_n[lvl]; }
+void ref_pin_tracker_get_pc(int lvl, float* u, float* v, float* id, float* color) {
+  const int n = g_trk->pc_n[lvl];
+  std::copy(g_trk->pc_u[lvl], g_trk->pc_u[lvl] + n, u); std::copy(g_trk->pc_v[lvl], g_trk->pc_v[lvl] + n, v);
+  std::copy(g_trk->pc_idepth[lvl], g_trk->pc_idepth[lvl] + n, id); std::copy(g_trk->pc_color[lvl], g_trk->pc_color[lvl] + n, color);
+}
+void ref_pin_tracker_get_depth_maps(int lvl, float* idepth, float* wsum) {
+  const int n = g_trk->w[lvl] * g_trk->h[lvl];
+  std::copy(g_trk->idepth[lvl], g_trk->idepth[lvl] + n, idepth); std::copy(g_trk->weightSums[lvl], g_trk->weightSums[lvl] + n, wsum);
 }
 }  // extern "C"

@@ -28,6 +28,9 @@ for photo in R.TRACKER_PHOTO:
     out.update(R.run_tracker_cases_ref(R.tracker_problem(photo), L, O.lib()))
 out.update(R.run_image_cases(R.ref_make_images(L)))
 out.update(R.compact(R.run_ba_cases_ref(R.ba_problem(), L)))
+_P = R.depth_problem()
+_, _T = R.run_depth_cases_oracle(_P)  # (only for the camera table handed to the reference side)
+out.update(R.compact(R.run_depth_cases_ref(_P, L, _T)))
 for i, a in enumerate(R.ref_global_calib(L)):
     out[f"global_calib/{i}"] = a
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_pin.npz"), **out)

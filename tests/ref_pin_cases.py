@@ -535,3 +535,76 @@ def compact(out, limit=70000):
         else:
             res[k] = v
     return res
+
+
+# ---------------------------------------------------------------------------------------------- makeCoarseDepthL0, sparse (a5)
+def depth_problem():
+    """Seeded sparse reference: 2 500 points with centerProjectedTo inside the image, HdiF over three decades."""
+    from nalo_slam_b200 import synth
+    from oracle import oracle_py as O
+
+    w, h, lv = TRACKER_SIZE
+    sc = synth.make_scene(w, h, seed=11)
+    dref, _ = O.make_images(synth.render_ref(sc), w, h, lv)
+    rng = np.random.default_rng(2)
+    n = 2500
+    u = rng.uniform(0.6, w - 1.6, n).astype(np.float32)
+    v = rng.uniform(0.6, h - 1.6, n).astype(np.float32)
+    idp = rng.uniform(0.02, 0.5, n).astype(np.float32)
+    hdi = (10.0 ** rng.uniform(-4, -1, n)).astype(np.float32)
+    return dict(w=w, h=h, L=lv, K=sc.K, dref=dref, u=u, v=v, idepth=idp, hdi=hdi)
+
+
+def _mask_oob_reads(out, P):
+    """Levels 0 and 1: the dilation (CoarseTracker.cpp:449-460) reads weightSums_bak[i-1-wl] at i = wl and [i+1+wl] at
+    i = wl*hl-wl-1, one float before / after the grid. The reference gets whatever the heap holds there; this repository
+    defines it as weight 0. The two pixels whose value can depend on it are excluded from the
+    comparison (they lie in the 2-pixel border, so no point of the cloud comes from them)."""
+    for l in (0, 1):
+        wl, hl = P["w"] >> l, P["h"] >> l
+        for k in ("idepth", "weightSums"):
+            a = out[f"depth/{l}/{k}"]
+            a[wl] = 0
+            a[wl * hl - wl - 1] = 0
+    return out
+
+
+def run_depth_cases_oracle(P):
+    from oracle import oracle_py as O
+
+    T = O.Tracker(P["w"], P["h"], P["L"])
+    T.makeK(*P["K"])
+    T.set_ref_frame(P["dref"])
+    T.make_depth_sparse(P["u"], P["v"], P["idepth"], P["hdi"])
+    out = {}
+    for l in range(P["L"]):
+        pc = T.get_pc(l)
+        out[f"depth/{l}/pc"] = np.stack(pc) if pc[0].size else np.zeros((4, 0), np.float32)
+        di, ws = T.get_depth_maps(l)
+        out[f"depth/{l}/idepth"], out[f"depth/{l}/weightSums"] = di, ws
+    return _mask_oob_reads(out, P), T
+
+
+def run_depth_cases_ref(P, L_ref, T_oracle):
+    from oracle import oracle_py as O
+
+    w, h, lv = P["w"], P["h"], P["L"]
+    K13 = np.ascontiguousarray(T_oracle.get_K(), dtype=np.float32)
+    L_ref.ref_pin_tracker_create(w, h, lv, _p(K13))
+    offs, _ = O.level_offsets(w, h, lv)
+    for l in range(lv):
+        nn = (w >> l) * (h >> l)
+        img = np.ascontiguousarray(P["dref"][offs[l] : offs[l] + nn])
+        L_ref.ref_pin_tracker_set_ref_level(l, _p(img))
+    L_ref.ref_pin_tracker_make_depth_sparse(int(P["u"].size), _p(P["u"]), _p(P["v"]), _p(P["idepth"]), _p(P["hdi"]))
+    out = {}
+    for l in range(lv):
+        n = int(L_ref.ref_pin_tracker_pc_n(l))
+        a = [np.zeros(n, np.float32) for _ in range(4)]
+        L_ref.ref_pin_tracker_get_pc(l, *[_p(x) for x in a])
+        out[f"depth/{l}/pc"] = np.stack(a) if n else np.zeros((4, 0), np.float32)
+        nn = (w >> l) * (h >> l)
+        di, ws = np.zeros(nn, np.float32), np.zeros(nn, np.float32)
+        L_ref.ref_pin_tracker_get_depth_maps(l, _p(di), _p(ws))
+        out[f"depth/{l}/idepth"], out[f"depth/{l}/weightSums"] = di, ws
+    return _mask_oob_reads(out, P)

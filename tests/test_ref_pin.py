@@ -44,7 +44,7 @@ def _same_bits(a, b):
 
 
 def test_oracle_matches_reference_fixture(oracle_out, gold):
-    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/", "tracker/", "images/", "ba/"))]
+    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/", "tracker/", "images/", "ba/", "depth/"))]
     assert len(keys) >= 30
     for k in keys:
         assert k in oracle_out, k
@@ -77,6 +77,10 @@ def test_compiled_reference_matches_fixture_and_oracle(oracle_out, gold):
     for k, v in R.run_image_cases(R.ref_make_images(L)).items():
         assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
     for k, v in R.compact(R.run_ba_cases_ref(R.ba_problem(), L)).items():
+        assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
+    P = R.depth_problem()
+    _, T = R.run_depth_cases_oracle(P)
+    for k, v in R.compact(R.run_depth_cases_ref(P, L, T)).items():
         assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
 
 
@@ -202,6 +206,20 @@ def test_ba_accumulation_matches_reference(gold, oracle):
     for k in keys:
         assert _same_bits(got[k], gold[k]), f"oracle BA accumulation differs from the reference: {k}"
     assert int(np.asarray(gold["ba/top0/nres"]).reshape(-1)[0]) > 10000 and int(np.asarray(gold["ba/top1/nres"]).reshape(-1)[0]) > 1000
+
+
+def test_coarse_depth_matches_reference(gold, oracle):
+    """a5 (sparse form): the oracle's makeCoarseDepthL0 against the reference's own CoarseTracker::makeCoarseDepthL0
+    (compiled verbatim with its plane branch switched off, oracle/ref_tracker.cpp; fixture): 2 500 reference points ->
+    weighted idepth maps, dilation, pooling and the per-level point clouds (count, u, v, idepth, colour) - bit-exact, the
+    two pixels per level whose value depends on an out-of-bounds read in the reference excepted."""
+    got, _ = R.run_depth_cases_oracle(R.depth_problem())
+    got = R.compact(got)
+    keys = [k for k in gold if k.startswith("depth/")]
+    assert len(keys) == 12 and set(keys) == set(got)
+    for k in keys:
+        assert _same_bits(got[k], gold[k]), f"oracle makeCoarseDepthL0 differs from the reference: {k}"
+    assert gold["depth/3/pc"].shape[1] > 500
 
 
 @pytest.mark.gpu
