@@ -13,7 +13,8 @@
 //    alphaEnergy = alphaW * |t|^2 * npts and alphaOpt depends on the translation only;
 //  * point->maxstep is updated inside the pattern loop, i.e. also for points that turn out bad later in the loop;
 //  * a point that fails keeps JbBuffer_new partially accumulated (up to the failing pattern pixel).
-// Parity is unpinned by the reference (no tests / golden vectors for this path); pinned here by analytic KATs
+// Parity: PINNED bit for bit to the reference's own CoarseInitializer::calcResAndGS copied verbatim at build time and
+// compiled by `make ref` (oracle/ref_init.cpp, tests/test_ref_pin.py, fixture tests/golden/ref_pin.npz); analytic KATs on top
 // (tests/test_oracle_initializer.py).
 #include <cmath>
 #include <cstdint>
@@ -237,4 +238,14 @@ void oracle_init_calc_res_gs(int wl, int hl, const float* colorRef, const float*
   res3[2] = (float)E.num;
 }
 
+// pin hook (tests/test_ref_pin.py): the quantities calcResAndGS derives with Eigen / Sophus arithmetic (inverse camera
+// matrix, rotation matrix, SE3 log), exactly as this oracle derives them, so that the reference's own calcResAndGS
+// (oracle/ref_init.cpp) can be given the same values - everything after that is the reference's arithmetic.
+void oracle_pin_init_inputs(const float K4[4], const double pose7[7], double* Ki9, double* R9, double* log6) {
+  const double K[9] = {K4[0], 0, K4[2], 0, K4[1], K4[3], 0, 0, 1};
+  mat33d_inverse(K, Ki9);
+  orc::SE3 T = orc::se3_from_array(pose7);
+  orc::quat_to_R(T.q, R9);
+  orc::se3_log(T, log6);
+}
 }  // extern "C"

@@ -31,6 +31,7 @@ out.update(R.compact(R.run_ba_cases_ref(R.ba_problem(), L)))
 _P = R.depth_problem()
 _, _T = R.run_depth_cases_oracle(_P)  # (only for the camera table handed to the reference side)
 out.update(R.compact(R.run_depth_cases_ref(_P, L, _T)))
+out.update(R.compact(R.run_init_cases_ref(L, O.lib())))
 for i, a in enumerate(R.ref_global_calib(L)):
     out[f"global_calib/{i}"] = a
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_pin.npz"), **out)

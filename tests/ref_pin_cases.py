@@ -608,3 +608,67 @@ def run_depth_cases_ref(P, L_ref, T_oracle):
         L_ref.ref_pin_tracker_get_depth_maps(l, _p(di), _p(ws))
         out[f"depth/{l}/idepth"], out[f"depth/{l}/weightSums"] = di, ws
     return _mask_oob_reads(out, P)
+
+
+# ---------------------------------------------------------------------------------------------- CoarseInitializer::calcResAndGS (f3)
+def init_problems():
+    """Seeded initializer calls on levels 0..2 of the 320x192 pair: (key, wl, hl, ref level image, new level image, K4, pose7,
+    aff2, points) - identity, ground-truth motion and a far-off pose, with a few points already marked bad."""
+    from nalo_slam_b200 import synth
+    from oracle import oracle_py as O
+
+    w, h, L = TRACKER_SIZE
+    sc = synth.make_scene(w, h, seed=11)
+    rng = np.random.default_rng(11)
+    xi, aff = synth.random_motion(rng, 0.5)
+    gt = synth.se3_exp(xi)
+    dref, _ = O.make_images(synth.render_ref(sc), w, h, L)
+    dnew, _ = O.make_images(synth.render_new(sc, gt, aff), w, h, L)
+    offs, _ = O.level_offsets(w, h, L)
+    probs = []
+    for lvl in (0, 1, 2):
+        wl, hl = w >> lvl, h >> lvl
+        ref3 = np.ascontiguousarray(dref[offs[lvl] : offs[lvl] + wl * hl])
+        new3 = np.ascontiguousarray(dnew[offs[lvl] : offs[lvl] + wl * hl])
+        K4 = np.ascontiguousarray(synth.level_K(sc.K, lvl), dtype=np.float32)
+        pts = synth.make_init_points(sc, lvl, step=2, bad_fraction=0.05)
+        xi2, aff2 = synth.random_motion(rng, 2.0)
+        for name, pose, a2 in (("identity", synth.pose_identity(), (0.0, 0.0)), ("gt", gt, (float(aff[0]), float(aff[1]))),
+                               ("far", synth.se3_exp(xi2), (float(aff2[0]), float(aff2[1])))):
+            probs.append((f"init/{lvl}/{name}", wl, hl, ref3, new3, K4, np.ascontiguousarray(pose, dtype=np.float64), np.array(a2, np.float64), pts))
+    return probs
+
+
+_INIT_OUT = ("H", "b", "Hsc", "bsc", "res", "maxstep", "isGood_new", "energy_new", "lastHessian_new", "JbBuffer_new")
+
+
+def run_init_cases_oracle():
+    from oracle import oracle_py as O
+
+    out = {}
+    for key, wl, hl, ref3, new3, K4, pose, aff, pts in init_problems():
+        r = O.init_calc_res_gs(ref3, new3, wl, hl, K4, pose, aff, pts)
+        for k in _INIT_OUT:
+            out[f"{key}/{k}"] = np.ascontiguousarray(r[k])
+    return out
+
+
+def run_init_cases_ref(L_ref, L_oracle):
+    out = {}
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    for key, wl, hl, ref3, new3, K4, pose, aff, pts in init_problems():
+        n = int(len(pts["u"]))
+        Ki9, R9, log6 = np.zeros(9), np.zeros(9), np.zeros(6)
+        L_oracle.oracle_pin_init_inputs(_p(K4), _p(pose), _p(Ki9), _p(R9), _p(log6))
+        t3 = np.ascontiguousarray(pose[4:7])
+        u, v, idn, iR, en, oth = (f32(pts[k]) for k in ("u", "v", "idepth_new", "iR", "energy", "outlierTH"))
+        good = np.ascontiguousarray(pts["isGood"], dtype=np.uint8)
+        ms, g, e2, lh, jb = np.zeros(n, np.float32), np.zeros(n, np.uint8), np.zeros((n, 2), np.float32), np.zeros(n, np.float32), np.zeros((n, 10), np.float32)
+        H, b, Hsc, bsc, res = np.zeros(64, np.float32), np.zeros(8, np.float32), np.zeros(64, np.float32), np.zeros(8, np.float32), np.zeros(3, np.float32)
+        L_ref.ref_pin_init_calc_res_gs(wl, hl, _p(ref3), _p(new3), _p(K4), _p(Ki9), _p(R9), _p(t3), _p(log6), _p(aff), n, _p(u), _p(v), _p(idn),
+                                       _p(iR), _p(good), _p(en), _p(oth), C.c_float(150.0 * 150.0), C.c_float(2.5 * 2.5), C.c_float(1.0),
+                                       C.c_float(9.0), _p(ms), _p(g), _p(e2), _p(lh), _p(jb), _p(H), _p(b), _p(Hsc), _p(bsc), _p(res))
+        r = dict(H=H.reshape(8, 8), b=b, Hsc=Hsc.reshape(8, 8), bsc=bsc, res=res, maxstep=ms, isGood_new=g, energy_new=e2, lastHessian_new=lh, JbBuffer_new=jb)
+        for k in _INIT_OUT:
+            out[f"{key}/{k}"] = np.ascontiguousarray(r[k])
+    return out

@@ -44,7 +44,7 @@ def _same_bits(a, b):
 
 
 def test_oracle_matches_reference_fixture(oracle_out, gold):
-    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/", "tracker/", "images/", "ba/", "depth/"))]
+    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/", "tracker/", "images/", "ba/", "depth/", "init/"))]
     assert len(keys) >= 30
     for k in keys:
         assert k in oracle_out, k
@@ -81,6 +81,8 @@ def test_compiled_reference_matches_fixture_and_oracle(oracle_out, gold):
     P = R.depth_problem()
     _, T = R.run_depth_cases_oracle(P)
     for k, v in R.compact(R.run_depth_cases_ref(P, L, T)).items():
+        assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
+    for k, v in R.compact(R.run_init_cases_ref(L, O.lib())).items():
         assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
 
 
@@ -220,6 +222,18 @@ def test_coarse_depth_matches_reference(gold, oracle):
     for k in keys:
         assert _same_bits(got[k], gold[k]), f"oracle makeCoarseDepthL0 differs from the reference: {k}"
     assert gold["depth/3/pc"].shape[1] > 500
+
+
+def test_initializer_matches_reference(gold, oracle):
+    """f3: the oracle's CoarseInitializer::calcResAndGS against the reference's own definition (compiled verbatim against
+    its real CoarseInitializer.h, oracle/ref_init.cpp; fixture) on levels 0-2 of the 320x192 pair x {identity, ground truth,
+    far-off pose}: H, b, Hsc, bsc, the result triple and per point maxstep, isGood_new, energy_new, lastHessian_new and the
+    ten JbBuffer_new entries - bit-exact (Ki, R and the SE3 log are handed to the reference side; see ref_init.cpp)."""
+    got = R.compact(R.run_init_cases_oracle())
+    keys = [k for k in gold if k.startswith("init/")]
+    assert len(keys) == 90 and set(keys) == set(got)
+    for k in keys:
+        assert _same_bits(got[k], gold[k]), f"oracle calcResAndGS differs from the reference: {k}"
 
 
 @pytest.mark.gpu
