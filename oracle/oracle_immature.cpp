@@ -7,7 +7,8 @@
 //   pattern 8, settings            src/util/settings.cpp:99-100,146,165-174,297; settings.h:232-234
 // Eigen expressions are restated with a fixed evaluation order (coefficient-wise, left to right):
 //   M*Vec3f(u,v,1) = (m0*u + m1*v) + m2 ; a^T G b = (a0*G00 + a1*G10)*b0 + (a0*G01 + a1*G11)*b1 ; Vec3f*0.01 uses 0.01f.
-// Parity is unpinned by the reference (no tests / golden vectors for this path); pinned here by analytic KATs
+// Parity: PINNED bit for bit to the reference's own ImmaturePoint constructor and traceOn copied verbatim at build time and
+// compiled by `make ref` (oracle/ref_immature.cpp, tests/test_ref_pin.py, fixture tests/golden/ref_pin.npz); analytic KATs on top
 // (tests/test_oracle_immature.py).
 #include <cmath>
 #include <cstdint>

@@ -32,6 +32,8 @@ struct PointHessian {
   std::pair<PointFrameResidual*, ResState> lastResiduals[2];
   bool onground = false;  // :HessianBlocks.h, written by the plane branch only
 };
+// FrameShell: ImmaturePoint::traceOn prints host->shell->id / frame->shell->id in its debug branch (util/FrameShell.h needs PCL)
+struct FrameShell { int id = 0; };
 struct FrameHessian {
   Eigen::Vector3f* dI;                     // level-0 {I, dx, dy}
   Eigen::Vector3f* dIp[PYR_LEVELS];        // per level
@@ -42,6 +44,7 @@ struct FrameHessian {
   float* last_ground;                        // :138-140, only touched by the plane branch of makeCoarseDepthL0 (dense_track)
   Eigen::Matrix<float, 4, 1> groundP;
   bool haveground = false;
+  FrameShell* shell = nullptr;               // :HessianBlocks.h, only dereferenced by debug prints
   void makeImages(float* color, CalibHessian* HCalib);  // HessianBlocks.h:161; definition: the reference's (ref_images.cpp)
 };
 }  // namespace dso

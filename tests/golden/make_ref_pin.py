@@ -32,6 +32,7 @@ _P = R.depth_problem()
 _, _T = R.run_depth_cases_oracle(_P)  # (only for the camera table handed to the reference side)
 out.update(R.compact(R.run_depth_cases_ref(_P, L, _T)))
 out.update(R.compact(R.run_init_cases_ref(L, O.lib())))
+out.update(R.compact(R.canon_nan(R.run_immature_cases_ref(R.immature_problem(), L))))
 for i, a in enumerate(R.ref_global_calib(L)):
     out[f"global_calib/{i}"] = a
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_pin.npz"), **out)

@@ -672,3 +672,78 @@ def run_init_cases_ref(L_ref, L_oracle):
         for k in _INIT_OUT:
             out[f"{key}/{k}"] = np.ascontiguousarray(r[k])
     return out
+
+
+# ---------------------------------------------------------------------------------------------- ImmaturePoint ctor + traceOn (f4)
+_IMM_STATE = ("color", "weights", "gradH", "energyTH", "idepth_min", "idepth_max", "quality", "status", "lastTraceUV", "lastTracePixelInterval")
+
+
+def immature_problem():
+    """One host keyframe at 320x192 and four later frames with growing baselines (the depth filter is traced on each in
+    turn, its state carried over): candidates on a 4-pixel grid, a NaN patch in the host image."""
+    from nalo_slam_b200 import synth
+    from oracle import oracle_py as O
+
+    w, h, L = 320, 192, 1
+    sc = synth.make_scene(w, h, seed=21)
+    rng = np.random.default_rng(21)
+    ref = np.ascontiguousarray(synth.render_ref(sc), dtype=np.float32)
+    ref[60:63, 100:103] = np.nan
+    dref, _ = O.make_images(ref, w, h, L)
+    u, v, _ = synth.immature_candidates(sc, step=4)
+    frames = []
+    for k in range(4):
+        xi, aff = synth.random_motion(rng, 0.4 + 0.5 * k)
+        gt = synth.se3_exp(xi)
+        dnew, _ = O.make_images(synth.render_new(sc, gt, aff), w, h, L)
+        frames.append((np.ascontiguousarray(dnew[: w * h]), synth.trace_geometry(sc.K, gt, aff)))
+    return dict(w=w, h=h, dref=np.ascontiguousarray(dref[: w * h]), u=np.ascontiguousarray(u, np.float32), v=np.ascontiguousarray(v, np.float32), frames=frames)
+
+
+def run_immature_cases_oracle(P):
+    from oracle import oracle_py as O
+
+    out = {}
+    st = O.immature_init(P["dref"], P["w"], P["u"], P["v"])
+    for k in _IMM_STATE[:4]:
+        out[f"immature/init/{k}"] = np.ascontiguousarray(st[k]).copy()
+    for i, (dnew, (KRKi, Kt, a2)) in enumerate(P["frames"]):
+        O.immature_trace(st, dnew, P["w"], P["h"], KRKi, Kt, a2)
+        for k in _IMM_STATE[4:]:
+            out[f"immature/trace{i}/{k}"] = np.ascontiguousarray(st[k]).copy()
+    return out
+
+
+def run_immature_cases_ref(P, L_ref):
+    from oracle import oracle_py as O
+
+    S = O.TraceSettings.default()
+    w, h, n = P["w"], P["h"], int(P["u"].size)
+    f32 = np.float32
+    st = dict(color=np.zeros((n, 8), f32), weights=np.zeros((n, 8), f32), gradH=np.zeros((n, 4), f32), energyTH=np.zeros(n, f32),
+              idepth_min=np.zeros(n, f32), idepth_max=np.full(n, np.nan, f32), quality=np.full(n, 10000.0, f32),
+              status=np.full(n, O.IPS_UNINITIALIZED, np.int32), lastTraceUV=np.zeros((n, 2), f32), lastTracePixelInterval=np.zeros(n, f32))
+    L_ref.ref_pin_immature_init(w, h, _p(P["dref"]), n, _p(P["u"]), _p(P["v"]), C.byref(S), _p(st["color"]), _p(st["weights"]), _p(st["gradH"]), _p(st["energyTH"]))
+    out = {}
+    for k in _IMM_STATE[:4]:
+        out[f"immature/init/{k}"] = st[k].copy()
+    for i, (dnew, (KRKi, Kt, a2)) in enumerate(P["frames"]):
+        K9, t3, a = (np.ascontiguousarray(x, dtype=f32).reshape(-1) for x in (KRKi, Kt, a2))
+        L_ref.ref_pin_immature_trace(w, h, _p(dnew), n, _p(P["u"]), _p(P["v"]), _p(st["color"]), _p(st["weights"]), _p(st["gradH"]), _p(st["energyTH"]),
+                                     _p(K9), _p(t3), _p(a), C.byref(S), _p(st["idepth_min"]), _p(st["idepth_max"]), _p(st["quality"]), _p(st["status"]),
+                                     _p(st["lastTraceUV"]), _p(st["lastTracePixelInterval"]))
+        for k in _IMM_STATE[4:]:
+            out[f"immature/trace{i}/{k}"] = st[k].copy()
+    return out
+
+
+def canon_nan(out):
+    """Every NaN replaced by one canonical quiet NaN (payloads and signs of NaNs are not compared)."""
+    res = {}
+    for k, v in out.items():
+        v = np.ascontiguousarray(v)
+        if v.dtype == np.float32:
+            bits = np.where(np.isnan(v), np.uint32(0x7FC00000), v.view(np.uint32)).astype(np.uint32)
+            v = bits.view(np.float32)
+        res[k] = v
+    return res

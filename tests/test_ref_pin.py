@@ -44,7 +44,7 @@ def _same_bits(a, b):
 
 
 def test_oracle_matches_reference_fixture(oracle_out, gold):
-    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/", "tracker/", "images/", "ba/", "depth/", "init/"))]
+    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/", "tracker/", "images/", "ba/", "depth/", "init/", "immature/"))]
     assert len(keys) >= 30
     for k in keys:
         assert k in oracle_out, k
@@ -83,6 +83,8 @@ def test_compiled_reference_matches_fixture_and_oracle(oracle_out, gold):
     for k, v in R.compact(R.run_depth_cases_ref(P, L, T)).items():
         assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
     for k, v in R.compact(R.run_init_cases_ref(L, O.lib())).items():
+        assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
+    for k, v in R.compact(R.canon_nan(R.run_immature_cases_ref(R.immature_problem(), L))).items():
         assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
 
 
@@ -234,6 +236,23 @@ def test_initializer_matches_reference(gold, oracle):
     assert len(keys) == 90 and set(keys) == set(got)
     for k in keys:
         assert _same_bits(got[k], gold[k]), f"oracle calcResAndGS differs from the reference: {k}"
+
+
+def test_immature_point_matches_reference(gold, oracle):
+    """f4: the oracle's ImmaturePoint constructor and traceOn against the reference's own definitions (compiled verbatim
+    against its real ImmaturePoint.h, oracle/ref_immature.cpp; fixture): 3 344 candidates of a 320x192 keyframe with a NaN
+    patch (colour, weights, gradH, energyTH), then the depth filter traced over four later frames with the state carried
+    over - idepth_min / max, quality, status, lastTraceUV, lastTracePixelInterval after every frame, all five outcome
+    classes occurring - bit-exact."""
+    got = R.compact(R.canon_nan(R.run_immature_cases_oracle(R.immature_problem())))
+    keys = [k for k in gold if k.startswith("immature/")]
+    assert len(keys) == 28 and set(keys) == set(got)
+    for k in keys:
+        assert _same_bits(got[k], gold[k]), f"oracle ImmaturePoint differs from the reference: {k}"
+    seen = set()
+    for i in range(4):
+        seen |= set(np.unique(gold[f"immature/trace{i}/status"]).tolist())
+    assert {0, 1, 2, 3, 4} <= seen  # GOOD, OOB, OUTLIER, SKIPPED, BADCONDITION
 
 
 @pytest.mark.gpu
