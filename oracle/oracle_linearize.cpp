@@ -9,8 +9,9 @@
 // The reference walks PointFrameResidual objects; here one residual is one row of flat arrays and the output is the
 // 76-word record of include/nalo_gpu.h (what EFResidual::takeDataF / AccumulatedTopHessianSSE::addPoint consume).
 // Floating-point order is fixed (compiled with -ffp-contract=off): 3x3*vec3 products as ((m0*x + m1*y) + m2*z),
-// everything else left to right as written in the reference. Parity unpinned by the reference (no tests upstream);
-// pinned by closed-form / finite-difference KATs in tests/test_oracle_linearize.py.
+// everything else left to right as written in the reference. Parity: PINNED bit for bit to the reference's own
+// PointFrameResidual::linearize copied verbatim at build time and compiled by `make ref` (oracle/ref_linearize.cpp,
+// tests/test_ref_pin.py); closed-form / finite-difference KATs on top in tests/test_oracle_linearize.py.
 #include <cmath>
 #include <cstdint>
 #include <cstring>

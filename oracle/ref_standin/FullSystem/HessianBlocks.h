@@ -24,10 +24,36 @@ struct CalibHessian {
   float Binv[256];
   float B[256];
 #include "calib_bgrad_extract.inc"
+  // scaled intrinsics and their inverses (HessianBlocks.h:349-360, :374-377: value_scaledi = 1.0f / value_scaledf, set by the
+  // driver with that formula); PointFrameResidual::linearize / projectPoint read them through these accessors
+  float value_scaledf[4], value_scaledi[4];
+  inline float& fxl() { return value_scaledf[0]; }
+  inline float& fyl() { return value_scaledf[1]; }
+  inline float& cxl() { return value_scaledf[2]; }
+  inline float& cyl() { return value_scaledf[3]; }
+  inline float& fxli() { return value_scaledi[0]; }
+  inline float& fyli() { return value_scaledi[1]; }
+  inline float& cxli() { return value_scaledi[2]; }
+  inline float& cyli() { return value_scaledi[3]; }
+};
+struct FrameHessian;
+// FrameFramePrecalc: the data members of the real struct (HessianBlocks.h:80-107); PointFrameResidual::linearize reads them
+struct FrameFramePrecalc {
+  FrameHessian* host = nullptr;
+  FrameHessian* target = nullptr;
+  Mat33f PRE_RTll, PRE_KRKiTll, PRE_RKiTll, PRE_RTll_0;
+  Vec2f PRE_aff_mode;
+  float PRE_b0_mode;
+  Vec3f PRE_tTll, PRE_KtTll, PRE_tTll_0;
+  float distanceLL;
 };
 class EFPoint;
 // PointHessian: CoarseTracker::makeCoarseDepthL0 reads lastResiduals[0] and efPoint->HdiF (HessianBlocks.h:425, 476)
 struct PointHessian {
+  float color[MAX_RES_PER_POINT];    // :HessianBlocks.h, read by PointFrameResidual::linearize together with weights, u, v,
+  float weights[MAX_RES_PER_POINT];  // idepth_scaled and idepth_zero_scaled
+  float u, v;
+  float idepth_scaled, idepth_zero_scaled;
   EFPoint* efPoint;
   std::pair<PointFrameResidual*, ResState> lastResiduals[2];
   bool onground = false;  // :HessianBlocks.h, written by the plane branch only
@@ -44,6 +70,9 @@ struct FrameHessian {
   float* last_ground;                        // :138-140, only touched by the plane branch of makeCoarseDepthL0 (dense_track)
   Eigen::Matrix<float, 4, 1> groundP;
   bool haveground = false;
+  int idx = 0;                                      // index in the window (linearize: host->targetPrecalc[target->idx])
+  float frameEnergyTH = 0;
+  std::vector<FrameFramePrecalc> targetPrecalc;
   FrameShell* shell = nullptr;               // :HessianBlocks.h, only dereferenced by debug prints
   void makeImages(float* color, CalibHessian* HCalib);  // HessianBlocks.h:161; definition: the reference's (ref_images.cpp)
 };

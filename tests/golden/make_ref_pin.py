@@ -33,6 +33,8 @@ _, _T = R.run_depth_cases_oracle(_P)  # (only for the camera table handed to the
 out.update(R.compact(R.run_depth_cases_ref(_P, L, _T)))
 out.update(R.compact(R.run_init_cases_ref(L, O.lib())))
 out.update(R.compact(R.canon_nan(R.run_immature_cases_ref(R.immature_problem(), L))))
+_LP, _LD = R.linearize_problem()
+out.update(R.compact(R.canon_nan(R.run_linearize_ref(_LP, _LD, L))))
 for i, a in enumerate(R.ref_global_calib(L)):
     out[f"global_calib/{i}"] = a
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_pin.npz"), **out)

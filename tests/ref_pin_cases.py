@@ -747,3 +747,47 @@ def canon_nan(out):
             v = bits.view(np.float32)
         res[k] = v
     return res
+
+
+# ---------------------------------------------------------------------------------------------- PointFrameResidual::linearize (f1)
+def linearize_problem():
+    """Seeded 4-keyframe window at 320x192 (1 600 points, residuals to the other frames, FEJ noise), 10 % of the residuals
+    arriving OOB; images from the oracle's makeImages."""
+    from nalo_slam_b200 import synth
+    from oracle import oracle_py as O
+
+    w, h, L = 320, 192, 1
+    sc = synth.make_scene(w, h, seed=3)
+    P = synth.make_lin_problem(sc, nf=4, pts_per_frame=400, seed=3, fej_noise=1e-3)
+    rng = np.random.default_rng(1)
+    P["state_in"] = (rng.random(P["n_res"]) < 0.1).astype(np.uint8)
+    P["energy_in"] = rng.uniform(0, 50, P["n_res"]).astype(np.float32)
+    dIs = [np.ascontiguousarray(O.make_images(img, w, h, L)[0][: w * h]) for img in P["images"]]
+    return P, dIs
+
+
+def run_linearize_oracle(P, dIs):
+    from oracle import oracle_py as O
+
+    r = O.linearize(P, dIs)
+    live = r["state"] != 1  # centre / pattern projections of residuals that ended OOB are not defined by the reference
+    out = {f"linearize/{k}": np.ascontiguousarray(v) for k, v in r.items() if k not in ("center", "proj")}
+    out["linearize/center_live"] = np.ascontiguousarray(r["center"][live])
+    out["linearize/proj_live"] = np.ascontiguousarray(r["proj"][live])
+    return out
+
+
+def run_linearize_ref(P, dIs, L_ref):
+    n, nf = P["n_res"], P["nf"]
+    frames = [np.ascontiguousarray(f, dtype=np.float32) for f in dIs]
+    fp = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
+    rec = np.zeros((n, 76), np.float32)
+    state, en, eno = np.zeros(n, np.uint8), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    center, proj = np.zeros((n, 3), np.float32), np.zeros((n, 16), np.float32)
+    fx, fy, cx, cy = P["K"]
+    L_ref.ref_pin_linearize(n, nf, P["w"], P["h"], C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), C.c_float(9.0), C.c_float(2500.0),
+                            C.c_float(0.0), C.c_float(0.0), fp, _p(P["pairs"]), _p(P["pt4"]), _p(P["color"]), _p(P["weights"]), _p(P["pack"]),
+                            _p(P["point"]), _p(P["state_in"]), _p(P["energy_in"]), _p(rec), _p(state), _p(en), _p(eno), _p(center), _p(proj))
+    live = state != 1
+    return {"linearize/rec": rec, "linearize/state": state, "linearize/energy": en, "linearize/energy_outlier": eno,
+            "linearize/center_live": np.ascontiguousarray(center[live]), "linearize/proj_live": np.ascontiguousarray(proj[live])}

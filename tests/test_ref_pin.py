@@ -44,7 +44,7 @@ def _same_bits(a, b):
 
 
 def test_oracle_matches_reference_fixture(oracle_out, gold):
-    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/", "tracker/", "images/", "ba/", "depth/", "init/", "immature/"))]
+    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/", "tracker/", "images/", "ba/", "depth/", "init/", "immature/", "linearize/"))]
     assert len(keys) >= 30
     for k in keys:
         assert k in oracle_out, k
@@ -85,6 +85,9 @@ def test_compiled_reference_matches_fixture_and_oracle(oracle_out, gold):
     for k, v in R.compact(R.run_init_cases_ref(L, O.lib())).items():
         assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
     for k, v in R.compact(R.canon_nan(R.run_immature_cases_ref(R.immature_problem(), L))).items():
+        assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
+    LP, LD = R.linearize_problem()
+    for k, v in R.compact(R.canon_nan(R.run_linearize_ref(LP, LD, L))).items():
         assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
 
 
@@ -253,6 +256,21 @@ def test_immature_point_matches_reference(gold, oracle):
     for i in range(4):
         seen |= set(np.unique(gold[f"immature/trace{i}/status"]).tolist())
     assert {0, 1, 2, 3, 4} <= seen  # GOOD, OOB, OUTLIER, SKIPPED, BADCONDITION
+
+
+def test_linearize_matches_reference(gold, oracle):
+    """f1: the oracle's PointFrameResidual::linearize against the reference's own definition (compiled verbatim against its
+    real Residuals.h / ResidualProjections.h / RawResidualJacobian.h, oracle/ref_linearize.cpp; fixture): 4 710 residuals of a
+    4-keyframe window, 10 % arriving OOB - the whole 76-word records (incl. the partially written ones of residuals that
+    leave the image mid-pattern), new states (IN / OOB / OUTLIER all occur), energies with and without the outlier clamp,
+    centre and pattern projections of the surviving residuals - bit-exact."""
+    P, dIs = R.linearize_problem()
+    got = R.compact(R.canon_nan(R.run_linearize_oracle(P, dIs)))
+    keys = [k for k in gold if k.startswith("linearize/")]
+    assert len(keys) == 6 and set(keys) == set(got)
+    for k in keys:
+        assert _same_bits(got[k], gold[k]), f"oracle linearize differs from the reference: {k}"
+    assert np.all(np.bincount(gold["linearize/state"], minlength=3) > 0)
 
 
 @pytest.mark.gpu
