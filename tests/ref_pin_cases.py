@@ -691,13 +691,25 @@ def immature_problem():
     ref[60:63, 100:103] = np.nan
     dref, _ = O.make_images(ref, w, h, L)
     u, v, _ = synth.immature_candidates(sc, step=4)
-    frames = []
+    frames, new_imgs = [], []
     for k in range(4):
         xi, aff = synth.random_motion(rng, 0.4 + 0.5 * k)
         gt = synth.se3_exp(xi)
-        dnew, _ = O.make_images(synth.render_new(sc, gt, aff), w, h, L)
+        img = np.ascontiguousarray(synth.render_new(sc, gt, aff), dtype=np.float32)
+        new_imgs.append(img)
+        dnew, _ = O.make_images(img, w, h, L)
         frames.append((np.ascontiguousarray(dnew[: w * h]), synth.trace_geometry(sc.K, gt, aff)))
-    return dict(w=w, h=h, dref=np.ascontiguousarray(dref[: w * h]), u=np.ascontiguousarray(u, np.float32), v=np.ascontiguousarray(v, np.float32), frames=frames)
+    return dict(w=w, h=h, dref=np.ascontiguousarray(dref[: w * h]), u=np.ascontiguousarray(u, np.float32), v=np.ascontiguousarray(v, np.float32), frames=frames,
+                ref_img=ref, new_imgs=new_imgs)
+
+
+def immature_ok_views(out):
+    """Adds `<key>_ok` entries: the rows of points whose constructor did not bail out on a non-finite colour (FullSystem::
+    makeNewTraces drops the others before they are ever traced, so only these rows are defined for every implementation)."""
+    ok = np.isfinite(out["immature/init/energyTH"])
+    for k in list(out):
+        out[k + "_ok"] = np.ascontiguousarray(out[k][ok])
+    return out
 
 
 def run_immature_cases_oracle(P):
@@ -711,7 +723,7 @@ def run_immature_cases_oracle(P):
         O.immature_trace(st, dnew, P["w"], P["h"], KRKi, Kt, a2)
         for k in _IMM_STATE[4:]:
             out[f"immature/trace{i}/{k}"] = np.ascontiguousarray(st[k]).copy()
-    return out
+    return immature_ok_views(out)
 
 
 def run_immature_cases_ref(P, L_ref):
@@ -734,7 +746,7 @@ def run_immature_cases_ref(P, L_ref):
                                      _p(st["lastTraceUV"]), _p(st["lastTracePixelInterval"]))
         for k in _IMM_STATE[4:]:
             out[f"immature/trace{i}/{k}"] = st[k].copy()
-    return out
+    return immature_ok_views(out)
 
 
 def canon_nan(out):

@@ -249,7 +249,7 @@ def test_immature_point_matches_reference(gold, oracle):
     classes occurring - bit-exact."""
     got = R.compact(R.canon_nan(R.run_immature_cases_oracle(R.immature_problem())))
     keys = [k for k in gold if k.startswith("immature/")]
-    assert len(keys) == 28 and set(keys) == set(got)
+    assert len(keys) == 56 and set(keys) == set(got)
     for k in keys:
         assert _same_bits(got[k], gold[k]), f"oracle ImmaturePoint differs from the reference: {k}"
     seen = set()
