@@ -85,6 +85,14 @@ void* nalo_stream(nalo_ctx* ctx);        /* the context's cudaStream_t (for even
 long long nalo_kernel_launches(const nalo_ctx* ctx); /* kernels launched so far by this context */
 void* nalo_host_alloc(size_t bytes);     /* pinned host memory (cudaHostAlloc) */
 void nalo_host_free(void* p);
+/* Test hook: trace the LM loop of the following nalo_track / nalo_track_frame calls. One record of 8 doubles
+ * per calcRes evaluation of CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:1099-1221): {level, kind (0 = first
+ * evaluation of a level or its cutoff repeat :1104-1113, 1 = LM iteration :1133), accepted (:1186), lambda after the
+ * update (:1188-1205), E, numTermsInE, levelCutoffRepeat, |inc| (:1208)}. capacity 0 = off. */
+int nalo_set_track_trace(nalo_ctx* ctx, int capacity);
+int nalo_get_track_trace(nalo_ctx* ctx, double* records_out /* [capacity][8] */, int* n_out);
+/* Test hook: set the 16-bit launch counter that forms the high half of the tracking kernel's exchange-word epochs. */
+int nalo_debug_set_track_launch_id(nalo_ctx* ctx, unsigned id);
 /* Write `bytes` of a scratch buffer larger than L2 (bench hygiene: cold-L2 timing). */
 int nalo_flush_l2(nalo_ctx* ctx);
 

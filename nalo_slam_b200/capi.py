@@ -209,6 +209,20 @@ class Context:
     def set_profiling(self, on=True):
         self._ck(self.L.nalo_set_profiling(self.h_, C.c_int(1 if on else 0)))
 
+    def set_track_trace(self, capacity):
+        self._trace_cap = capacity
+        self._ck(self.L.nalo_set_track_trace(self.h_, C.c_int(capacity)))
+
+    def get_track_trace(self):
+        """LM trace of the last nalo_track call: array [n][8] {lvl, kind, accepted, lambda, E, n, cutoffRepeat, |inc|}."""
+        out = np.zeros((self._trace_cap, 8))
+        n = C.c_int(0)
+        self._ck(self.L.nalo_get_track_trace(self.h_, _ptr(out), C.byref(n)))
+        return out[: min(n.value, self._trace_cap)].copy()
+
+    def debug_set_track_launch_id(self, launch_id):
+        self._ck(self.L.nalo_debug_set_track_launch_id(self.h_, C.c_uint(launch_id)))
+
     def sync(self):
         self._ck(self.L.nalo_sync(self.h_))
 

@@ -1251,11 +1251,31 @@ int nalo_ba_upload(nalo_ba* ba, const NaloBAProblem* p) {
   if (p->nf < 1 || p->nf > NALO_BA_MAX_FRAMES || p->n_res < 0 || p->n_res > ba->maxRes || p->n_pts < 0 || p->n_pts > ba->maxPts)
     return nalo_fail(ctx, NALO_E_ARG, "BA problem out of range: nf=%d n_res=%d n_pts=%d", p->nf, p->n_res, p->n_pts);
   if (!p->rec || !p->bucket_begin || !p->pt_begin || !p->pt_res || !p->adHTdeltaF || !p->cDeltaF) return NALO_E_ARG;
+  // Validate the whole index structure before anything is read through it or copied, and before the handle changes.
+  const int nb = p->nf * p->nf;
+  if (p->bucket_begin[0] != 0 || p->bucket_begin[nb] != p->n_res) return nalo_fail(ctx, NALO_E_ARG, "bucket_begin does not cover [0, n_res]");
+  for (int b = 0; b < nb; b++)
+    if (p->bucket_begin[b + 1] < p->bucket_begin[b]) return nalo_fail(ctx, NALO_E_ARG, "bucket_begin[%d] decreases", b + 1);
+  if (p->pt_begin[0] != 0) return nalo_fail(ctx, NALO_E_ARG, "pt_begin[0] must be 0");
+  for (int q = 0; q < p->n_pts; q++) {
+    const int len = p->pt_begin[q + 1] - p->pt_begin[q];
+    if (len < 0 || p->pt_begin[q + 1] > ba->maxRes) return nalo_fail(ctx, NALO_E_ARG, "pt_begin[%d] = %d is not monotone within [0, max_res]", q + 1, p->pt_begin[q + 1]);
+    if (len > 8) return nalo_fail(ctx, NALO_E_ARG, "point %d lists %d residuals; at most 8 (one per target frame) are supported", q, len);
+  }
+  {
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(p->rec);
+    for (int k = 0; k < p->pt_begin[p->n_pts]; k++) {
+      const int ri = p->pt_res[k];
+      if (ri < 0 || ri >= p->n_res) return nalo_fail(ctx, NALO_E_ARG, "pt_res[%d] = %d out of range", k, ri);
+      const int h = (int)(rw[(size_t)ri * REC + O_PACK] & 0xFF);
+      if (h >= p->nf) return nalo_fail(ctx, NALO_E_ARG, "record host index %d >= nf", h);
+    }
+  }
   NALO_CUDA(ctx, cudaSetDevice(ctx->device));
-  ba->nf = p->nf; ba->nPts = p->n_pts; ba->nRes = p->n_res;
+  // the handle describes no problem until this upload has gone through completely (sizes are committed at the end)
+  ba->nf = 0; ba->nPts = 0; ba->nRes = 0;
   ba->haveA = ba->haveL = ba->haveJpJd = ba->haveJpJdDev = ba->haveSC = ba->haveX = false;
   cudaStream_t st = ctx->stream;
-  const int nb = p->nf * p->nf;
   NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_rec, p->rec, sizeof(float) * REC * (size_t)p->n_res, cudaMemcpyHostToDevice, st));
   if (p->res_toZero) NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_rtz, p->res_toZero, sizeof(float) * 8 * (size_t)p->n_res, cudaMemcpyHostToDevice, st));
   else NALO_CUDA(ctx, cudaMemsetAsync(ba->d_rtz, 0, sizeof(float) * 8 * (size_t)p->n_res, st));
@@ -1330,6 +1350,7 @@ int nalo_ba_upload(nalo_ba* ba, const NaloBAProblem* p) {
   NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_itemRange, ba->topRange.data(), sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, st));
   NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_itemRange + 80, ba->scRange.data(), sizeof(int) * (p->nf + 1), cudaMemcpyHostToDevice, st));
   NALO_CUDA(ctx, cudaStreamSynchronize(st));  // host vectors above go out of scope
+  ba->nf = p->nf; ba->nPts = p->n_pts; ba->nRes = p->n_res;
   return NALO_OK;
 }
 

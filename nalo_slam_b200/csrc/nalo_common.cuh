@@ -64,6 +64,12 @@ struct NaloTrackProblem {
   float refExposure, newExposure;
   int coarsestLvl;
   int useAbort;  // 0: never abort on minRes (multi-hypothesis / batch mode)
+  // LM trace (nalo_set_track_trace; nullptr = off): trace[0] = number of records, record k at trace[8*(k+1)]:
+  // {lvl, kind (0 first evaluation of a level / cutoff repeat, 1 LM iteration), accepted, lambda after the update, E, n,
+  //  levelCutoffRepeat, |inc|}
+  double* trace;
+  int traceCap;
+  int padTrace;
 };
 
 struct NaloTrackResult {
@@ -144,6 +150,8 @@ struct nalo_ctx {
   int* h_gridInit = nullptr;               // pinned table h_gridInit[g] == g
   int* d_trackQueue = nullptr;             // atomic work queue of single-CTA groups (batched alignments)
   uint32_t doneToken = 0;
+  double* d_trace = nullptr;               // LM trace of single-problem launches (nalo_set_track_trace)
+  int traceCap = 0;
   bool profiling = false;                  // record CUDA events around the tracking kernel (NaloTrackStats::kernel_ms)
   unsigned long long* d_xchg = nullptr;  // flagged 64-bit exchange words of the tracking groups
   size_t xchgBytes = 0;

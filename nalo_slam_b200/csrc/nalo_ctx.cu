@@ -67,7 +67,7 @@ int nalo_create(int w, int h, int levels, int device, int max_frames, nalo_ctx**
     cudaError_t e__ = (call);                                                                      \
     if (e__ != cudaSuccess) {                                                                      \
       nalo_fail(nullptr, NALO_E_CUDA, "nalo_create: %s: %s", #call, cudaGetErrorString(e__));      \
-      delete ctx;                                                                                  \
+      nalo_destroy(ctx); /* frees whatever was created so far (tolerates null members) */          \
       return NALO_E_CUDA;                                                                          \
     }                                                                                              \
   } while (0)

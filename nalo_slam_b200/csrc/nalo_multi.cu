@@ -316,8 +316,7 @@ static int frames_enqueue(nalo_ctx* ctx, nalo_ctx::FramesBuf& B, int trk, int n,
     NaloTrackProblem* P = B.h_prob + i;
     T.newSlot = new_slots[i];
     T.newExposure = exposure_new;
-    ctx->frames[new_slots[i]].valid = true;
-    nalo_fill_problem(ctx, trk, P);
+    nalo_fill_problem(ctx, trk, P);  // (the slot becomes `valid` when its pyramid launch has been enqueued, nalo_images_run_multi)
     for (int k = 0; k < 7; k++) P->pose[k] = poses7[7 * i + k];
     P->aff[0] = affs2[2 * i];
     P->aff[1] = affs2[2 * i + 1];

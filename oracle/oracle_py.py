@@ -250,6 +250,13 @@ class Tracker:
         ok = self.L.oracle_tracker_track(self.h_, _ptr(pose), _ptr(aff), C.c_int(coarsestLvl), _ptr(mr), _ptr(lr), _ptr(fl))
         return bool(ok), pose, aff, lr, fl
 
+    def trace(self):
+        """LM trace of the last track(): [n][8] {lvl, kind, accepted, lambda, E, n, cutoffRepeat, |inc|}."""
+        n = self.L.oracle_tracker_trace(self.h_, None, C.c_int(0))
+        out = np.zeros((max(n, 1), 8))
+        self.L.oracle_tracker_trace(self.h_, _ptr(out), C.c_int(n))
+        return out[:n]
+
     def stats(self, reset=False):
         out = np.zeros(3, dtype=np.int64)
         self.L.oracle_tracker_stats(self.h_, _ptr(out), C.c_int(1 if reset else 0))

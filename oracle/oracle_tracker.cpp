@@ -89,7 +89,15 @@ struct OTracker {
   long long statResiduals = 0;
   long long statCalcRes = 0;
   long long statIters = 0;
+  // LM trace of the last tracker_track (test aid: the divergence log of SURVEY.md H3). 8 doubles per calcRes evaluation:
+  // {lvl, kind (0 first evaluation / cutoff repeat, 1 LM iteration), accepted, lambda after the update, E, n,
+  //  levelCutoffRepeat, |inc|}
+  std::vector<double> trace;
 };
+static void trace_rec(OTracker* T, int lvl, int kind, int accepted, float lambda, const double* rs, float rep, double nrm) {
+  const double r[8] = {(double)lvl, (double)kind, (double)accepted, (double)lambda, rs[0], rs[1], (double)rep, nrm};
+  T->trace.insert(T->trace.end(), r, r + 8);
+}
 
 void tracker_make_k(OTracker* T, float fx0, float fy0, float cx0, float cy0) {
   T->fx[0] = fx0; T->fy[0] = fy0; T->cx[0] = cx0; T->cy[0] = cy0;
@@ -382,6 +390,7 @@ void tracker_calc_gs(OTracker* T, int lvl, double* H_out, double* b_out, const o
 bool tracker_track(OTracker* T, orc::SE3& lastToNew_out, double* aff_g2l_out, int coarsestLvl, const double* minResForAbort) {
   for (int i = 0; i < 5; i++) T->lastResiduals[i] = NAN;
   for (int i = 0; i < 3; i++) T->lastFlowIndicators[i] = 1000;
+  T->trace.clear();
   const int maxIterations[] = {10, 20, 50, 50, 50};
   const float lambdaExtrapolationLimit = 0.001f;
   orc::SE3 refToNew_current = lastToNew_out;
@@ -396,10 +405,12 @@ bool tracker_track(OTracker* T, orc::SE3& lastToNew_out, double* aff_g2l_out, in
     tracker_calc_res(T, lvl, refToNew_current, aff_g2l_current, T->setting_coarseCutoffTH * levelCutoffRepeat, resOld);
     while (resOld[5] > 0.6 && levelCutoffRepeat < 50) {
       levelCutoffRepeat *= 2;
+      trace_rec(T, lvl, 0, 0, 0.f, resOld, levelCutoffRepeat, 0.0);
       tracker_calc_res(T, lvl, refToNew_current, aff_g2l_current, T->setting_coarseCutoffTH * levelCutoffRepeat, resOld);
     }
     tracker_calc_gs(T, lvl, H, b, refToNew_current, aff_g2l_current);
     float lambda = 0.01;
+    trace_rec(T, lvl, 0, 1, lambda, resOld, levelCutoffRepeat, 0.0);
 
     for (int iteration = 0; iteration < maxIterations[lvl]; iteration++) {
       T->statIters++;
@@ -463,6 +474,7 @@ bool tracker_track(OTracker* T, orc::SE3& lastToNew_out, double* aff_g2l_out, in
       double nrm = 0;
       for (int i = 0; i < 8; i++) nrm += inc[i] * inc[i];
       nrm = std::sqrt(nrm);
+      trace_rec(T, lvl, 1, accept ? 1 : 0, lambda, resNew, levelCutoffRepeat, nrm);
       if (!(nrm > 1e-3)) break;
     }
     T->lastResiduals[lvl] = sqrtf((float)(resOld[0] / resOld[1]));
@@ -649,6 +661,13 @@ int oracle_tracker_track(void* p, double* pose7, double* aff2, int coarsestLvl, 
   for (int i = 0; i < 3; i++) flow3[i] = T->lastFlowIndicators[i];
   return ok ? 1 : 0;
 }
+int oracle_tracker_trace(void* p, double* out, int cap_records) {
+  OTracker* T = (OTracker*)p;
+  const int n = (int)(T->trace.size() / 8);
+  if (out) memcpy(out, T->trace.data(), sizeof(double) * 8 * (size_t)std::min(n, cap_records));
+  return n;
+}
+
 void oracle_tracker_stats(void* p, long long* out3, int reset) {
   OTracker* T = (OTracker*)p;
   out3[0] = T->statResiduals; out3[1] = T->statCalcRes; out3[2] = T->statIters;
