@@ -150,17 +150,21 @@ def cpu_arm(sc, ref, news, n_threads, budget_s, fast=True):
     O.frames_batch(trackers, [news[i % len(news)] for i in range(n_threads)], p0, a0, LEVELS - 1)
     t_tot, frames, res, iters = 0.0, 0, 0, 0
     k = 0
+    ref_poses = {}  # distinct image index -> (ok, pose7, lastRes5) of the oracle: the parity reference of the bench line
     while t_tot < budget_s:
         cols = [news[(k + i) % len(news)] for i in range(n_threads)]
         t0 = time.perf_counter()
         ok, poses, affs, lr, st = O.frames_batch(trackers, cols, p0, a0, LEVELS - 1)
         t_tot += time.perf_counter() - t0
+        for i in range(n_threads):
+            ref_poses.setdefault((k + i) % len(news), (int(ok[i]), poses[i].copy(), lr[i].copy()))
         frames += n_threads
         res += st["residuals"]
         iters += st["iters"]
         k += n_threads
     return dict(value=res / t_tot, ms_per_frame=1e3 * t_tot / frames * 1.0, frames=frames, seconds=t_tot,
-                gn_iters_per_s=iters / t_tot, residuals_per_frame=res / frames, pc_n=[trackers[0].pc_n(l) for l in range(LEVELS)])
+                gn_iters_per_s=iters / t_tot, residuals_per_frame=res / frames, pc_n=[trackers[0].pc_n(l) for l in range(LEVELS)],
+                ref_poses=ref_poses)
 
 
 def run_reference(args, rank, world):
@@ -448,6 +452,24 @@ def run_b200(args, rank, world, local_rank):
             line["batched"] = batched
         if world == 1 and not args.no_cpu:
             r = cpu_arm(sc, ref, news, 1, args.cpu_budget, fast=True)
+            # parity of the timed step itself: every frame the device tracked in the K timed steps against the oracle's pose
+            # for the same image (the oracle tracks the distinct images once in this leg)
+            max_dt = max_dr = max_lr = 0.0
+            checked, distinct = 0, set()
+            for row in range(K * F):
+                img = ((row // F * F + row % F) % NB) % N_FRAMES
+                if img not in r["ref_poses"]:
+                    continue
+                ok_o, pose_o, lr_o = r["ref_poses"][img]
+                dt, dr = synth.pose_distance(results[row, 1:8], pose_o)
+                max_dt, max_dr = max(max_dt, dt), max(max_dr, dr)
+                fin = np.isfinite(lr_o)
+                max_lr = max(max_lr, float(np.max(np.abs(results[row, 10:15][fin] - lr_o[fin]) / np.abs(lr_o[fin]))) if fin.any() else 0.0)
+                checked += int(results[row, 0] == ok_o)
+                distinct.add(img)
+            line["parity"] = {"against": "CPU oracle (oracle/, -O3 -march=x86-64-v3 build) on the same images", "max_dt": max_dt, "max_dr": max_dr,
+                              "max_rel_lastResiduals": max_lr, "frames": K * F, "frames_ok_flag_equal": checked, "distinct_images": len(distinct),
+                              "tolerance": 1e-5, "pass": bool(max_dt < 1e-5 and max_dr < 1e-5 and checked == K * F)}
             line["cpu_baseline"] = {"value": r["value"], "unit": "residuals/s", "cores": 1, "kind": "port",
                                     "ms_per_frame": r["ms_per_frame"],
                                     "sample": f"{r['frames']} frames ({r['seconds']:.1f} s) of the same workload on 1 host core (the reference tracker is single-threaded), oracle -O3 -march=x86-64-v3"}

@@ -54,6 +54,7 @@ SE3d mul(const SE3d& a, const SE3d& b) {  // se3.hpp:239-272
 SE3d inv(const SE3d& a) {  // se3.hpp:169-173
   SE3d r;
   r.q[0] = -a.q[0]; r.q[1] = -a.q[1]; r.q[2] = -a.q[2]; r.q[3] = a.q[3];
+  qnorm(r.q);  // so3.hpp:171-173: SO3Group(unit_quaternion().conjugate()) - that constructor normalises (reference pin se3/inverse)
   const double nt[3] = {-a.t[0], -a.t[1], -a.t[2]};
   qrot(r.q, nt, r.t);
   return r;

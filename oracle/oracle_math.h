@@ -90,6 +90,8 @@ inline SE3 se3_mul(const SE3& a, const SE3& b) {
 inline SE3 se3_inverse(const SE3& a) {  // se3.hpp:169-173
   SE3 r;
   r.q[0] = -a.q[0]; r.q[1] = -a.q[1]; r.q[2] = -a.q[2]; r.q[3] = a.q[3];
+  quat_normalize(r.q);  // so3.hpp:171-173: inverse() goes through the SO3Group(Quaternion) constructor, which normalises
+                        // (found by the reference pin: tests/test_ref_pin.py, se3/inverse)
   double nt[3] = {a.t[0] * -1.0, a.t[1] * -1.0, a.t[2] * -1.0};
   quat_rotate(r.q, nt, r.t);
   return r;

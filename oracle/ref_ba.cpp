@@ -21,8 +21,23 @@
 namespace dso {
 class PointFrameResidual { public: RawResidualJacobian* J; };
 class PointHessian { public: float idepth_hessian, maxRelBaseline; };
-class EnergyFunctional { public: VecCf cDeltaF; Mat18f* adHTdeltaF; };
+class EnergyFunctional {  // the members addPoint and stitchDoubleInternal read (OptimizationBackend/EnergyFunctional.h:94-141)
+ public:
+  VecCf cDeltaF;
+  Mat18f* adHTdeltaF;
+  Mat88* adHost;
+  Mat88* adTarget;
+  VecC cPrior;
+  std::vector<EFFrame*> frames;
+};
 void EFPoint::takeData() {}  // (called by EFPoint's inline constructor; the real one reads a PointHessian - not under test)
+void EFFrame::takeData() {}  // (likewise: prior / delta_prior are set by the driver)
+// stitchDoubleMT's multi-threaded branch (not taken: MT = false) names these; util/IndexThreadReduce.h needs boost threads
+template <class R> class IndexThreadReduce { public: template <class F> void reduce(F, int, int, int) {} };
+}  // namespace dso
+namespace boost { template <class... A> int bind(A...) { return 0; } }
+static int _1, _2, _3, _4;
+namespace dso {
 
 class AccumulatedTopHessianSSE {
  public:
@@ -30,6 +45,8 @@ class AccumulatedTopHessianSSE {
   int nframes[NUM_THREADS];
   int nres[NUM_THREADS];
   template <int mode> void addPoint(EFPoint* p, EnergyFunctional const* const ef, int tid = 0);
+  void stitchDoubleInternal(MatXX* H, VecX* b, EnergyFunctional const* const EF, bool usePrior, int min, int max, Vec10* stats, int tid);
+#include "ba_stitch_top_mt_extract.inc"  // stitchDoubleMT, verbatim from AccumulatedTopHessian.h (incl. "make diagonal by copying over parts")
 };
 class AccumulatedSCHessianSSE {
  public:
@@ -40,12 +57,16 @@ class AccumulatedSCHessianSSE {
   AccumulatorX<CPARS> accbc[NUM_THREADS];
   int nframes[NUM_THREADS];
   void addPoint(EFPoint* p, bool shiftPriorToZero, int tid = 0);
+  void stitchDoubleInternal(MatXX* H, VecX* b, EnergyFunctional const* const EF, int min, int max, Vec10* stats, int tid);
+#include "ba_stitch_sc_mt_extract.inc"  // stitchDoubleMT, verbatim from AccumulatedSCHessian.h
 };
 
 template <int mode>
 #include "ba_top_extract.inc"
 #include "ba_sc_extract.inc"
 #include "ba_takedata_extract.inc"
+#include "ba_stitch_top_extract.inc"
+#include "ba_stitch_sc_extract.inc"
 }  // namespace dso
 
 using namespace dso;
@@ -129,6 +150,51 @@ void ref_pin_ba_top(int mode, int nf, int nPts, int nRes, const float* rec, cons
   }
   *nres_out = top.nres[0];
 }
+// f2 (stitch): AccumulatedTopHessianSSE::addPoint<mode> over all points, then stitchDoubleMT(MT = false) = stitchDoubleInternal +
+// the symmetric completion (AccumulatedTopHessian.cpp:241-303, .h:91-139). adHost / adTarget: [nf*nf][64] row-major,
+// framePrior / frameDeltaPrior: [nf][8]. H: [N*N] row-major, b: [N], N = 4 + 8 nf.
+void ref_pin_ba_stitch_top(int mode, int nf, int nPts, int nRes, const float* rec, const float* res_toZero, const int* pt_begin,
+                           const int* pt_res, const float* deltaF, const float* adHTdeltaF, const float* cDeltaF, const double* adHost,
+                           const double* adTarget, int usePrior, const double* cPrior, const double* framePrior,
+                           const double* frameDeltaPrior, double* H_out, double* b_out) {
+  Problem P;
+  build(P, nPts, nRes, rec, res_toZero, pt_begin, pt_res);
+  const int nb = nf * nf;
+  std::vector<Mat18f> ad((size_t)nb);
+  std::vector<Mat88> aH((size_t)nb), aT((size_t)nb);
+  for (int b = 0; b < nb; b++) {
+    for (int k = 0; k < 8; k++) ad[b][k] = adHTdeltaF[8 * b + k];
+    for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) { aH[b](r, c) = adHost[64 * (size_t)b + 8 * r + c]; aT[b](r, c) = adTarget[64 * (size_t)b + 8 * r + c]; }
+  }
+  EnergyFunctional ef;
+  for (int k = 0; k < 4; k++) { ef.cDeltaF[k] = cDeltaF[k]; ef.cPrior[k] = cPrior ? cPrior[k] : 0.0; }
+  ef.adHTdeltaF = ad.data(); ef.adHost = aH.data(); ef.adTarget = aT.data();
+  std::vector<EFFrame*> frames;
+  for (int h = 0; h < nf; h++) {
+    EFFrame* f = new EFFrame(nullptr);
+    for (int k = 0; k < 8; k++) { f->prior[k] = framePrior ? framePrior[8 * h + k] : 0.0; f->delta_prior[k] = frameDeltaPrior ? frameDeltaPrior[8 * h + k] : 0.0; }
+    frames.push_back(f);
+  }
+  ef.frames = frames;
+  AccumulatedTopHessianSSE top;
+  std::vector<AccumulatorApprox> acc((size_t)nb);
+  for (auto& a : acc) a.initialize();
+  top.acc[0] = acc.data(); top.nframes[0] = nf; top.nres[0] = 0;
+  for (int p = 0; p < nPts; p++) {
+    EFPoint* e = P.pts[p];
+    e->deltaF = deltaF ? deltaF[p] : 0.f;
+    if (mode == 0) top.addPoint<0>(e, &ef, 0);
+    if (mode == 1) top.addPoint<1>(e, &ef, 0);
+    if (mode == 2) top.addPoint<2>(e, &ef, 0);
+  }
+  MatXX H;
+  VecX b;
+  top.stitchDoubleMT(nullptr, H, b, &ef, usePrior != 0, false);
+  const int N = CPARS + 8 * nf;
+  for (int r = 0; r < N; r++) { for (int c = 0; c < N; c++) H_out[(size_t)r * N + c] = H(r, c); b_out[r] = b[r]; }
+  for (auto* f : frames) delete f;
+}
+
 // EFResidual::takeDataF on every record (the Jacobian is swapped in from a PointFrameResidual, as in the reference)
 void ref_pin_ba_take_data(int nRes, const float* rec, float* JpJdF) {
   for (int i = 0; i < nRes; i++) {
@@ -143,10 +209,33 @@ void ref_pin_ba_take_data(int nRes, const float* rec, float* JpJdF) {
   }
 }
 // same arguments and outputs as oracle_ba_sc with one worker
+static void ba_sc_impl(int nf, int nPts, int nRes, const float* rec, const float* JpJdF, const int* pt_begin, const int* pt_res,
+                   const float* HddA, const float* bdA, const float* HcdA, const float* HddL, const float* bdL, const float* HcdL,
+                   const float* priorF, const float* deltaF, int shiftPriorToZero, double* accD, double* accE, double* accEB,
+                   double* accHcc, double* accbc, float* perPoint, const double* adHost, const double* adTarget, double* H_out, double* b_out);
 void ref_pin_ba_sc(int nf, int nPts, int nRes, const float* rec, const float* JpJdF, const int* pt_begin, const int* pt_res,
                    const float* HddA, const float* bdA, const float* HcdA, const float* HddL, const float* bdL, const float* HcdL,
                    const float* priorF, const float* deltaF, int shiftPriorToZero, double* accD, double* accE, double* accEB,
                    double* accHcc, double* accbc, float* perPoint) {
+  ba_sc_impl(nf, nPts, nRes, rec, JpJdF, pt_begin, pt_res, HddA, bdA, HcdA, HddL, bdL, HcdL, priorF, deltaF, shiftPriorToZero, accD, accE, accEB,
+             accHcc, accbc, perPoint, nullptr, nullptr, nullptr, nullptr);
+}
+// f2 (stitch): the same accumulation followed by AccumulatedSCHessianSSE::stitchDoubleMT(MT = false)
+// (AccumulatedSCHessian.cpp:78-157, .h:93-133): H_sc [N*N] row-major, b_sc [N]
+void ref_pin_ba_stitch_sc(int nf, int nPts, int nRes, const float* rec, const float* JpJdF, const int* pt_begin, const int* pt_res,
+                          const float* HddA, const float* bdA, const float* HcdA, const float* HddL, const float* bdL, const float* HcdL,
+                          const float* priorF, const float* deltaF, int shiftPriorToZero, const double* adHost, const double* adTarget,
+                          double* H_out, double* b_out) {
+  const size_t n2 = (size_t)nf * nf, n3 = n2 * nf;
+  std::vector<double> D(n3 * 64), E(n2 * 32), EB(n2 * 8), Hcc(16), bc(4);
+  std::vector<float> pp((size_t)nPts * 3 + 3);
+  ba_sc_impl(nf, nPts, nRes, rec, JpJdF, pt_begin, pt_res, HddA, bdA, HcdA, HddL, bdL, HcdL, priorF, deltaF, shiftPriorToZero, D.data(), E.data(),
+             EB.data(), Hcc.data(), bc.data(), pp.data(), adHost, adTarget, H_out, b_out);
+}
+static void ba_sc_impl(int nf, int nPts, int nRes, const float* rec, const float* JpJdF, const int* pt_begin, const int* pt_res,
+                   const float* HddA, const float* bdA, const float* HcdA, const float* HddL, const float* bdL, const float* HcdL,
+                   const float* priorF, const float* deltaF, int shiftPriorToZero, double* accD, double* accE, double* accEB,
+                   double* accHcc, double* accbc, float* perPoint, const double* adHost, const double* adTarget, double* H_out, double* b_out) {
   Problem P;
   build(P, nPts, nRes, rec, nullptr, pt_begin, pt_res);
   for (int i = 0; i < nRes; i++) for (int k = 0; k < 8; k++) P.res[i]->JpJdF[k] = JpJdF[8 * (size_t)i + k];
@@ -182,5 +271,17 @@ void ref_pin_ba_sc(int nf, int nPts, int nRes, const float* rec, const float* Jp
   sc.accHcc[0].finish(); sc.accbc[0].finish();
   for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) accHcc[4 * i + j] = (double)sc.accHcc[0].A1m(i, j);
   for (int i = 0; i < 4; i++) accbc[i] = (double)sc.accbc[0].A1m[i];
+  if (H_out) {  // (finish() is idempotent: stitchDoubleInternal calls it again on every accumulator)
+    std::vector<Mat88> aH(n2), aT(n2);
+    for (size_t b = 0; b < n2; b++)
+      for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) { aH[b](r, c) = adHost[64 * b + 8 * r + c]; aT[b](r, c) = adTarget[64 * b + 8 * r + c]; }
+    EnergyFunctional ef;
+    ef.adHost = aH.data(); ef.adTarget = aT.data();
+    MatXX H;
+    VecX bv;
+    sc.stitchDoubleMT(nullptr, H, bv, &ef, false);
+    const int N = CPARS + 8 * nf;
+    for (int r = 0; r < N; r++) { for (int c = 0; c < N; c++) H_out[(size_t)r * N + c] = H(r, c); b_out[r] = bv[r]; }
+  }
 }
 }  // extern "C"

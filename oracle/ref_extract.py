@@ -5,6 +5,7 @@ Copies whole function definitions VERBATIM out of a reference source file into a
 wrote them: ref_tracker.cpp #includes the intermediate inside `namespace dso`.
 A definition starts at the line that begins with the given signature prefix (leading whitespace included) and ends at the
 first following line that is exactly `}` at the same indentation (the reference closes every function that way).
+A signature written as `<prefix>@-N` also takes the N lines before it (Sophus puts `inline static` on its own line).
 usage: ref_extract.py <source> <out.inc> <signature prefix> [<signature prefix> ...]
        ref_extract.py --defines <header> <out.inc> <macro prefix>      (copies `#define <prefix>...` lines)"""
 import sys
@@ -21,6 +22,10 @@ def main():
     text = open(src, encoding="utf-8", errors="replace").read().split("\n")
     chunks = []
     for sig in sigs:
+        before = 0
+        if "@-" in sig and sig.rsplit("@-", 1)[1].isdigit():
+            sig, nb = sig.rsplit("@-", 1)
+            before = int(nb)
         starts = [i for i, l in enumerate(text) if l.startswith(sig)]
         assert len(starts) == 1, f"{sig!r}: {len(starts)} definitions in {src}"
         i = starts[0]
@@ -28,6 +33,7 @@ def main():
         j = i
         while text[j].rstrip("\r\n ") != indent + "}":
             j += 1
+        i -= before
         chunks.append(f"// ---- {src}:{i + 1}-{j + 1} (verbatim)\n" + "\n".join(text[i : j + 1]) + "\n")
     open(out, "w").write("\n".join(chunks))
 

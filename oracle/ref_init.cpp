@@ -55,8 +55,10 @@ void ref_pin_init_calc_res_gs(int wl, int hl, const float* colorRef, const float
   ci.points[0] = pts.data(); ci.numPoints[0] = npts;
   for (int i = 0; i < npts; i++) ci.JbBuffer_new[i].setZero();
   SE3 T;
-  for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) T.R(r, c) = R9[3 * r + c]; T.t[r] = t3[r]; }
+  T.setRotationDirect(R9);
+  for (int r = 0; r < 3; r++) T.translation()[r] = t3[r];
   for (int k = 0; k < 6; k++) T.logv[k] = log6[k];
+  T.haveLogv = true;
   Mat88f H, Hsc; Vec8f b, bsc;
   Vec3f res = ci.calcResAndGS(0, H, b, Hsc, bsc, T, AffLight(aff2[0], aff2[1]), false);
   for (int r = 0; r < 8; r++) {

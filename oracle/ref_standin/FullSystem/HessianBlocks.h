@@ -59,7 +59,16 @@ struct PointHessian {
   bool onground = false;  // :HessianBlocks.h, written by the plane branch only
 };
 // FrameShell: ImmaturePoint::traceOn prints host->shell->id / frame->shell->id in its debug branch (util/FrameShell.h needs PCL)
-struct FrameShell { int id = 0; };
+// the members FullSystem::trackNewCoarse reads / writes (util/FrameShell.h:38-60) are declared as well
+struct FrameShell {
+  int id = 0;
+  double timestamp = 0;
+  SE3 camToTrackingRef;
+  FrameShell* trackingRef = nullptr;
+  SE3 camToWorld;
+  AffLight aff_g2l;
+  bool poseValid = true;
+};
 struct FrameHessian {
   Eigen::Vector3f* dI;                     // level-0 {I, dx, dy}
   Eigen::Vector3f* dIp[PYR_LEVELS];        // per level

@@ -39,8 +39,8 @@ PointFrameResidual::~PointFrameResidual() {}
 int PointFrameResidual::instanceCounter = 0;
 }  // namespace dso
 
-static CoarseTracker* g_trk = nullptr;
-static FrameHessian g_ref, g_new;
+CoarseTracker* g_trk = nullptr;  // (shared with ref_lm.cpp, which runs trackNewestCoarse / trackNewCoarse on the same tracker)
+FrameHessian g_ref, g_new;
 static std::vector<std::vector<float>> g_newLevels, g_refLevels;
 
 extern "C" {
@@ -83,8 +83,8 @@ void ref_pin_tracker_set_photometric(float exposure_ref, float exposure_new, dou
 }
 static SE3 make_se3(const double* R9, const double* t3) {
   SE3 T;
-  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) T.R(r, c) = R9[3 * r + c];
-  for (int r = 0; r < 3; r++) T.t[r] = t3[r];
+  T.setRotationDirect(R9);
+  for (int r = 0; r < 3; r++) T.translation()[r] = t3[r];
   return T;
 }
 // calcRes: rs6 = its Vec6; returns buf_warped_n (incl. padding)

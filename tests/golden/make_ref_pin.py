@@ -25,9 +25,16 @@ out.update(R.run_selector_cases(lambda w, h: R._RefSel(L, w, h)))
 from oracle import oracle_py as O  # noqa: E402  (inputs of the tracker cases: pyramids, camera table, reference cloud)
 
 for photo in R.TRACKER_PHOTO:
-    out.update(R.run_tracker_cases_ref(R.tracker_problem(photo), L, O.lib()))
+    _TP = R.tracker_problem(photo)
+    out.update(R.run_tracker_cases_ref(_TP, L, O.lib()))
+    out.update(R.run_track_cases_ref(_TP, L))       # a8: CoarseTracker::trackNewestCoarse, verbatim
+    out.update(R.run_candidate_cases_ref(_TP, L))   # a11: FullSystem::trackNewCoarse, verbatim
+out.update(R.run_se3_cases(*R.se3_ops_ref(L)))      # vendored Sophus exp / log / product / inverse
 out.update(R.run_image_cases(R.ref_make_images(L)))
-out.update(R.compact(R.run_ba_cases_ref(R.ba_problem(), L)))
+_BP = R.ba_problem()
+_BA = R.run_ba_cases_ref(_BP, L)
+out.update(R.run_stitch_cases_ref(_BP, L, _BA["ba/top0/perPoint"], _BA["ba/top1/perPoint"], _BA["ba/JpJdF"]))  # f2: stitchDoubleInternal / MT
+out.update(R.compact(_BA))
 _P = R.depth_problem()
 _, _T = R.run_depth_cases_oracle(_P)  # (only for the camera table handed to the reference side)
 out.update(R.compact(R.run_depth_cases_ref(_P, L, _T)))

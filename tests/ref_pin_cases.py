@@ -414,6 +414,218 @@ def run_tracker_cases_ref(P, L_ref, L_oracle):
     return out
 
 
+# ---------------------------------------------------------------------------------------------- Sophus SE3 (exp / log / product / inverse)
+def se3_inputs():
+    """Seeded tangent vectors [upsilon, omega]: generic, large rotation, the LM loop's tiny steps, below Sophus's 1e-10
+    small-angle threshold (both branches of so3.hpp:343-369 / se3.hpp:407-428), exactly zero."""
+    rng = np.random.default_rng(20261018)
+    xs = [rng.standard_normal(6) * s for s in (1.0, 0.3, 1e-2, 1e-3, 1e-5, 1e-8) for _ in range(4)]
+    xs += [np.concatenate([rng.standard_normal(3), rng.standard_normal(3) * 1e-12]) for _ in range(3)]
+    xs += [np.concatenate([rng.standard_normal(3), [0.0, 0.0, 0.0]]), np.zeros(6)]
+    big = rng.standard_normal(6)
+    big[3:] *= 2.9 / np.linalg.norm(big[3:])  # rotation angle 2.9 rad
+    xs.append(big)
+    return [np.ascontiguousarray(x, dtype=np.float64) for x in xs]
+
+
+def run_se3_cases(exp, log, mul, inv):
+    """exp of every input, log of every result, the chain product exp(x_k) * (exp(x_{k-1}) * ...) as the LM loop forms it,
+    inverses of the chain."""
+    out = {}
+    xs = se3_inputs()
+    poses = np.array([exp(x) for x in xs])
+    out["se3/exp"] = poses
+    out["se3/log"] = np.array([log(p) for p in poses])
+    chain, acc = [], poses[0]
+    for p in poses[1:]:
+        acc = mul(p, acc)
+        chain.append(acc)
+    out["se3/chain"] = np.array(chain)
+    out["se3/inverse"] = np.array([inv(p) for p in chain])
+    return out
+
+
+def se3_ops_oracle():
+    from oracle import oracle_py as O
+
+    return O.se3_exp, O.se3_log, O.se3_mul, O.se3_inverse
+
+
+def se3_ops_ref(L):
+    def exp(x):
+        o = np.zeros(7)
+        L.ref_pin_se3_exp(_p(np.ascontiguousarray(x, dtype=np.float64)), _p(o))
+        return o
+
+    def log(p):
+        o = np.zeros(6)
+        L.ref_pin_se3_log(_p(np.ascontiguousarray(p, dtype=np.float64)), _p(o))
+        return o
+
+    def mul(a, b):
+        o = np.zeros(7)
+        L.ref_pin_se3_mul(_p(np.ascontiguousarray(a, dtype=np.float64)), _p(np.ascontiguousarray(b, dtype=np.float64)), _p(o))
+        return o
+
+    def inv(a):
+        o = np.zeros(7)
+        L.ref_pin_se3_inverse(_p(np.ascontiguousarray(a, dtype=np.float64)), _p(o))
+        return o
+
+    return exp, log, mul, inv
+
+
+# ---------------------------------------------------------------------------------------------- trackNewestCoarse (a8), trackNewCoarse (a11)
+# (affineOptModeA, affineOptModeB): the reference default, preset mode=1, and the three "fixed" variants of :1140-1162
+TRACK_MODES = [(1e12, 1e8), (0.0, 0.0), (-1.0, -1.0), (0.0, -1.0), (-1.0, 0.0)]
+
+
+def track_cases(P):
+    """(tag, modeA, modeB, pose0, aff0, coarsestLvl, minRes5) for one tracker problem."""
+    from nalo_slam_b200 import synth
+
+    rng = np.random.default_rng(7)
+    ident = synth.pose_identity()
+    nan5 = np.full(5, np.nan)
+    cases = []
+    for mA, mB in TRACK_MODES:
+        cases.append((f"ident/{mA:g}_{mB:g}", mA, mB, ident, (0.0, 0.0), P["L"] - 1, nan5))
+    far = np.asarray(synth.se3_exp(synth.random_motion(rng, 3.0)[0]), dtype=np.float64)      # far off: cutoff repeats, rejected steps
+    cases.append(("far", 0.0, 0.0, far, (0.0, 0.0), P["L"] - 1, nan5))
+    near = np.asarray(synth.se3_exp(synth.random_motion(rng, 0.2)[0]), dtype=np.float64)
+    cases.append(("near_lvl2", 0.0, 0.0, near, (0.01, 0.5), 2, nan5))                          # coarsestLvl < top
+    cases.append(("abort", 0.0, 0.0, ident, (0.0, 0.0), P["L"] - 1, np.full(5, 1e-3)))         # abort on the coarsest level (:1225-1227)
+    cases.append(("abort_lvl1", 0.0, 0.0, ident, (0.0, 0.0), P["L"] - 1, np.array([1e-3, 1e-3, 1e9, 1e9, 1e9])))
+    cases.append(("aff_recovers", 1e12, 1e8, ident, (2.0, 0.0), P["L"] - 1, nan5))             # starts beyond |a| > 1.2, converges back
+    cases.append(("aff_insane", -1.0, -1.0, ident, (2.0, 0.0), P["L"] - 1, nan5))              # a fixed at 2 > 1.2 -> false (:1241-1243)
+    return cases
+
+
+def _track_out(out, g, ok, pose, aff, lr, fl):
+    out[f"{g}/ok"] = np.int64(ok)
+    out[f"{g}/pose"], out[f"{g}/aff"] = np.array(pose, np.float64), np.array(aff, np.float64)
+    out[f"{g}/lastRes"], out[f"{g}/flow"] = np.array(lr, np.float64), np.array(fl, np.float64)
+
+
+def run_track_cases_oracle(P):
+    out = {}
+    T = P["T"]
+    for tag, mA, mB, pose0, aff0, lvl0, minres in track_cases(P):
+        T.set_settings(affineOptModeA=mA, affineOptModeB=mB)
+        ok, pose, aff, lr, fl = T.track(pose0, aff0, coarsestLvl=lvl0, minRes=minres)
+        _track_out(out, f"track/{P['tag']}/{tag}", ok, pose, aff, lr, fl)
+    T.set_settings(affineOptModeA=0, affineOptModeB=0)
+    return out
+
+
+def _ref_tracker_setup(P, L_ref):
+    from oracle import oracle_py as O
+
+    w, h, L = P["w"], P["h"], P["L"]
+    T = P["T"]
+    K13 = np.ascontiguousarray(T.get_K(), dtype=np.float32)
+    L_ref.ref_pin_tracker_create(w, h, L, _p(K13))
+    L_ref.ref_pin_tracker_set_photometric(C.c_float(P["exposures"][0]), C.c_float(P["exposures"][1]), C.c_double(P["aff_ref"][0]), C.c_double(P["aff_ref"][1]))
+    offs, _ = O.level_offsets(w, h, L)
+    for lvl in range(L):
+        u, v, idp, col = T.get_pc(lvl)
+        L_ref.ref_pin_tracker_set_pc(lvl, int(u.size), _p(u), _p(v), _p(idp), _p(col))
+        n = (w >> lvl) * (h >> lvl)
+        img = np.ascontiguousarray(P["dnew"][offs[lvl] : offs[lvl] + n])
+        L_ref.ref_pin_tracker_set_new_level(lvl, _p(img))
+
+
+def run_track_cases_ref(P, L_ref):
+    """The reference's CoarseTracker::trackNewestCoarse (verbatim, oracle/ref_lm.cpp) on the same cloud, pyramids and camera table."""
+    _ref_tracker_setup(P, L_ref)
+    out = {}
+    for tag, mA, mB, pose0, aff0, lvl0, minres in track_cases(P):
+        L_ref.ref_pin_track_settings(C.c_float(9.0), C.c_float(20.0), C.c_float(mA), C.c_float(mB))
+        pose = np.array(pose0, np.float64)
+        aff = np.array(aff0, np.float64)
+        mr = np.ascontiguousarray(minres, dtype=np.float64)
+        lr, fl = np.zeros(5), np.zeros(3)
+        ok = L_ref.ref_pin_track(_p(pose), _p(aff), lvl0, _p(mr), _p(lr), _p(fl))
+        _track_out(out, f"track/{P['tag']}/{tag}", ok, pose, aff, lr, fl)
+    L_ref.ref_pin_track_settings(C.c_float(9.0), C.c_float(20.0), C.c_float(1e12), C.c_float(1e8))
+    return out
+
+
+def candidate_histories(P):
+    """(tag, sprelast_c2w, slast_c2w, lastF_c2w, valid3, aff_last, lastCoarseRMSE5): camera histories for trackNewCoarse.
+    "cv": constant velocity towards the true pose (the prediction is good: first try wins);
+    "still": the camera did not move before (prediction = identity, the other candidates get their chance);
+    "wrong": history predicts a motion in the opposite direction, lastCoarseRMSE small (no early break: all tries, aborts);
+    "invalid": a shell with poseValid == false collapses the list to the identity (FullSystem.cpp:575-579)."""
+    from nalo_slam_b200 import synth
+    from oracle import oracle_py as O
+
+    rng = np.random.default_rng(3)
+    xi, _ = synth.random_motion(rng, 0.5)
+    true_c2w = O.se3_inverse(np.asarray(synth.se3_exp(xi), dtype=np.float64))
+    ident = synth.pose_identity()
+    half = O.se3_exp(0.5 * O.se3_log(true_c2w))
+    back = O.se3_exp(-0.5 * O.se3_log(true_c2w))
+    kf = O.se3_exp(np.array([0.3, -0.1, 0.2, 0.01, -0.02, 0.015]))  # a keyframe that is not at the origin
+    H = []
+    H.append(("cv", ident, half, ident, (1, 1, 1), (0.0, 0.0), np.full(5, 1e9)))
+    H.append(("still", ident, ident, ident, (1, 1, 1), (0.0, 0.0), np.full(5, 1e9)))
+    H.append(("wrong", ident, back, ident, (1, 1, 1), (0.02, 1.0), np.full(5, 1e-3)))
+    H.append(("kf_offset", O.se3_mul(kf, ident), O.se3_mul(kf, half), kf, (1, 1, 1), (0.0, 0.0), np.array([0.5, 1e9, 1e9, 1e9, 1e9])))
+    H.append(("invalid", ident, half, ident, (1, 0, 1), (0.0, 0.0), np.full(5, 1e9)))
+    # "big_wrong": the history predicts a large motion that did not happen; lastCoarseRMSE is what a good alignment of this
+    # pair achieves, so the loop runs until a candidate gets within 1.5x of it (the zero-motion candidates, index 3 / 4)
+    T = P["T"]
+    T.set_settings(affineOptModeA=0, affineOptModeB=0)
+    _, _, _, good_res, _ = T.track(ident, (0.0, 0.0))
+    big = O.se3_exp(np.array([0.25, -0.12, 0.2, 0.05, -0.08, 0.06]))
+    H.append(("big_wrong", ident, big, ident, (1, 1, 1), (0.0, 0.0), np.array(good_res, np.float64)))
+    return H
+
+
+def run_candidate_cases_oracle(P):
+    from oracle import oracle_py as O
+
+    out = {}
+    T = P["T"]
+    T.set_settings(affineOptModeA=0, affineOptModeB=0)
+    for tag, spre, sl, lf, valid, aff_last, rmse in candidate_histories(P):
+        tries = O.motion_candidates(spre, sl, lf, poses_valid=all(valid))
+        r = T.track_new_coarse(tries, aff_last, rmse)
+        g = f"candidates/{P['tag']}/{tag}"
+        # in the form FullSystem::trackNewCoarse leaves its results: shell->camToTrackingRef = lastF_2_fh^-1 (:674), the
+        # returned Vec4 (achievedRes[0], flowVecs) (:698), lastCoarseRMSE = achievedRes (:668)
+        out[f"{g}/n_tries"] = np.int64(r["tries"])
+        out[f"{g}/camToTrackingRef"], out[f"{g}/aff"] = O.se3_inverse(r["pose"]), r["aff"]
+        out[f"{g}/achievedRes"] = r["lastCoarseRMSE"]
+        out[f"{g}/ret4"] = np.concatenate([[r["lastCoarseRMSE"][0]], r["flow"]])
+    return out
+
+
+def run_candidate_cases_ref(P, L_ref):
+    """The reference's FullSystem::trackNewCoarse (verbatim, oracle/ref_lm.cpp). It stores camToTrackingRef = lastF_2_fh^-1;
+    the fixture keeps that pose as stored plus, for the candidate list, the tries recovered through ref_pin_motion_list."""
+    from oracle import oracle_py as O
+
+    _ref_tracker_setup(P, L_ref)
+    L_ref.ref_pin_track_settings(C.c_float(9.0), C.c_float(20.0), C.c_float(0.0), C.c_float(0.0))
+    out = {}
+    for tag, spre, sl, lf, valid, aff_last, rmse in candidate_histories(P):
+        rm = np.array(rmse, np.float64)
+        c2t, aff, ret4 = np.zeros(7), np.zeros(2), np.zeros(4)
+        nt = C.c_int(0)
+        v3 = np.array(valid, np.int32)
+        L_ref.ref_pin_track_new_coarse(_p(np.ascontiguousarray(spre, dtype=np.float64)), _p(np.ascontiguousarray(sl, dtype=np.float64)),
+                                       _p(np.ascontiguousarray(lf, dtype=np.float64)), _p(v3), _p(np.array(aff_last, np.float64)), _p(rm),
+                                       C.c_float(1.5), _p(c2t), _p(aff), _p(ret4), C.byref(nt))
+        g = f"candidates/{P['tag']}/{tag}"
+        out[f"{g}/n_tries"] = np.int64(nt.value)
+        out[f"{g}/camToTrackingRef"], out[f"{g}/aff"] = c2t, aff
+        out[f"{g}/achievedRes"], out[f"{g}/ret4"] = rm, ret4
+    L_ref.ref_pin_track_settings(C.c_float(9.0), C.c_float(20.0), C.c_float(1e12), C.c_float(1e8))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- FrameHessian::makeImages (a1)
 IMAGE_CASES = [(320, 192, 4), (1241, 376, 5), (640, 480, 4)]
 
@@ -520,6 +732,59 @@ def run_ba_cases_ref(prob, L):
                         _p(accHcc), _p(accbc), _p(p3))
         for k, v in dict(accD=accD, accE=accE, accEB=accEB, accHcc=accHcc, accbc=accbc, perPoint=p3).items():
             out[f"ba/sc{shift}/{k}"] = v
+    return out
+
+
+def stitch_window(nf):
+    """Adjoint-like 8x8 blocks and priors of a window (as tests/test_gpu_solve.py builds them), seeded."""
+    rng = np.random.default_rng(100 + nf)
+    adH = np.ascontiguousarray(-np.eye(8)[None] + 0.2 * rng.normal(size=(nf * nf, 8, 8)))
+    adT = np.ascontiguousarray(np.eye(8)[None] + 0.2 * rng.normal(size=(nf * nf, 8, 8)))
+    return dict(adHost=adH, adTarget=adT, cPrior=np.full(4, 5e9), framePrior=rng.uniform(0, 1e3, (nf, 8)),
+                frameDeltaPrior=rng.normal(0, 1e-3, (nf, 8)))
+
+
+def run_stitch_cases_oracle(prob):
+    """f2 stitch: accumulate (a9 / a10) then stitchDoubleMT for the active set (mode 0, no prior), the linearised set (mode 1,
+    with the priors) and the Schur complement."""
+    from oracle import oracle_py as O
+
+    nf = prob["nf"]
+    Wn = stitch_window(nf)
+    out = {}
+    pp = {}
+    for mode, usePrior in ((0, False), (1, True), (2, True)):
+        accH, pp[mode], _ = O.ba_top(prob, mode=mode, nThreads=1)
+        H, b = O.ba_stitch_top(nf, accH, Wn["adHost"], Wn["adTarget"], usePrior=usePrior, cPrior=Wn["cPrior"], cDeltaF=prob["cDeltaF"],
+                               framePrior=Wn["framePrior"], frameDeltaPrior=Wn["frameDeltaPrior"])
+        out[f"stitch/top{mode}/H"], out[f"stitch/top{mode}/b"] = H, b
+    J = O.ba_take_data(prob)
+    sg = O.ba_sc(prob, J, pp[0], pp[1], shiftPriorToZero=True, nThreads=1)
+    H, b = O.ba_stitch_sc(nf, sg["accD"], sg["accE"], sg["accEB"], sg["accHcc"], sg["accbc"], Wn["adHost"], Wn["adTarget"])
+    out["stitch/sc/H"], out["stitch/sc/b"] = H, b
+    return out
+
+
+def run_stitch_cases_ref(prob, L, ppA, ppL, J):
+    """The reference's own stitchDoubleInternal + stitchDoubleMT (verbatim, oracle/ref_ba.cpp) behind its own addPoint passes.
+    ppA / ppL / J: per-point sums and JpJdF of the preceding passes (bit-identical on both sides, see run_ba_cases_*)."""
+    nf, nP, nR = prob["nf"], prob["n_pts"], prob["n_res"]
+    Wn = stitch_window(nf)
+    N = 4 + 8 * nf
+    out = {}
+    for mode, usePrior in ((0, 0), (1, 1), (2, 1)):
+        H, b = np.zeros((N, N)), np.zeros(N)
+        L.ref_pin_ba_stitch_top(mode, nf, nP, nR, _p(prob["rec"]), _p(prob["res_toZero"]), _p(prob["pt_begin"]), _p(prob["pt_res"]),
+                                _p(prob["deltaF"]), _p(prob["adHTdeltaF"]), _p(prob["cDeltaF"]), _p(Wn["adHost"]), _p(Wn["adTarget"]), usePrior,
+                                _p(Wn["cPrior"]), _p(np.ascontiguousarray(Wn["framePrior"])), _p(np.ascontiguousarray(Wn["frameDeltaPrior"])), _p(H), _p(b))
+        out[f"stitch/top{mode}/H"], out[f"stitch/top{mode}/b"] = H, b
+    cols = lambda a: (np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1]), np.ascontiguousarray(a[:, 2:6]))
+    HddA, bdA, HcdA = cols(ppA)
+    HddL, bdL, HcdL = cols(ppL)
+    H, b = np.zeros((N, N)), np.zeros(N)
+    L.ref_pin_ba_stitch_sc(nf, nP, nR, _p(prob["rec"]), _p(J), _p(prob["pt_begin"]), _p(prob["pt_res"]), _p(HddA), _p(bdA), _p(HcdA),
+                           _p(HddL), _p(bdL), _p(HcdL), _p(prob["priorF"]), _p(prob["deltaF"]), 1, _p(Wn["adHost"]), _p(Wn["adTarget"]), _p(H), _p(b))
+    out["stitch/sc/H"], out["stitch/sc/b"] = H, b
     return out
 
 

@@ -44,7 +44,7 @@ def _same_bits(a, b):
 
 
 def test_oracle_matches_reference_fixture(oracle_out, gold):
-    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/", "tracker/", "images/", "ba/", "depth/", "init/", "immature/", "linearize/"))]
+    keys = [k for k in gold if k not in ("settings", "pattern") and not k.startswith(("global_calib", "selector/", "tracker/", "images/", "ba/", "depth/", "init/", "immature/", "linearize/", "se3/", "track/", "candidates/", "stitch/"))]
     assert len(keys) >= 30
     for k in keys:
         assert k in oracle_out, k
@@ -74,9 +74,19 @@ def test_compiled_reference_matches_fixture_and_oracle(oracle_out, gold):
     for photo in R.TRACKER_PHOTO:
         for k, v in R.run_tracker_cases_ref(R.tracker_problem(photo), L, O.lib()).items():
             assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
+    for photo in R.TRACKER_PHOTO:
+        TP = R.tracker_problem(photo)
+        for k, v in {**R.run_track_cases_ref(TP, L), **R.run_candidate_cases_ref(TP, L)}.items():
+            assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
+    for k, v in R.run_se3_cases(*R.se3_ops_ref(L)).items():
+        assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
     for k, v in R.run_image_cases(R.ref_make_images(L)).items():
         assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
-    for k, v in R.compact(R.run_ba_cases_ref(R.ba_problem(), L)).items():
+    BP = R.ba_problem()
+    BA = R.run_ba_cases_ref(BP, L)
+    for k, v in R.run_stitch_cases_ref(BP, L, BA["ba/top0/perPoint"], BA["ba/top1/perPoint"], BA["ba/JpJdF"]).items():
+        assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
+    for k, v in R.compact(BA).items():
         assert _same_bits(v, gold[k]), f"fixture is stale: {k}"
     P = R.depth_problem()
     _, T = R.run_depth_cases_oracle(P)
@@ -199,6 +209,73 @@ def test_calc_res_and_gs_match_reference(gold, oracle):
             assert got["tracker/A/10/rs"][5] < 0.1 and int(got["tracker/A/10/warped_n"]) > 30000
             assert got["tracker/A/11/rs"][5] > 0.3
     assert n == 120
+
+
+def test_se3_matches_vendored_sophus(gold, oracle):
+    """SE3 exp / log / group product / inverse: the oracle's restatement (oracle/oracle_math.h) against the reference's vendored
+    Sophus code itself (thirdparty/Sophus/sophus/so3.hpp, se3.hpp member functions copied verbatim into the stand-in classes of
+    oracle/ref_standin/sophus/se3.hpp; Eigen's quaternion kernels underneath are the oracle's) on 33 seeded tangent vectors
+    incl. both branches of the small-angle test, a 2.9 rad rotation and zero; chained products as the LM loop forms them -
+    bit-exact. (This pin found a missing re-normalisation in the inverse.)"""
+    got = R.run_se3_cases(*R.se3_ops_oracle())
+    keys = [k for k in gold if k.startswith("se3/")]
+    assert set(keys) == set(got) and len(keys) == 4
+    for k in keys:
+        assert _same_bits(got[k], gold[k]), f"oracle SE3 differs from Sophus: {k}"
+    assert gold["se3/exp"].shape == (len(R.se3_inputs()), 7)
+
+
+def test_track_newest_coarse_matches_reference(gold, oracle):
+    """a8: the oracle's trackNewestCoarse against the reference's own CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:1073-1259,
+    compiled verbatim, oracle/ref_lm.cpp, on top of the reference's own calcRes / calcGSSSE) on the dense 320x192x4 pair, two
+    photometric set-ups x 11 runs: the five affine modes, a far-off start (cutoff repeats, rejected steps), a start below the
+    top level, aborts on the coarsest and on level 1, affine sanity failing and recovering. Return value, pose, affine
+    parameters, lastResiduals (NaN pattern included) and flow indicators - bit-exact, i.e. the lambda schedule, accept rule,
+    level repeat, |inc| break and abort take the same branch at every one of the evaluations."""
+    n = 0
+    for photo in R.TRACKER_PHOTO:
+        got = R.run_track_cases_oracle(R.tracker_problem(photo))
+        keys = [k for k in gold if k.startswith(f"track/{photo}/")]
+        assert set(keys) == set(got) and len(keys) == 5 * 11
+        for k in keys:
+            assert _same_bits(got[k], gold[k]), f"oracle trackNewestCoarse differs from the reference: {k} {got[k]} {gold[k]}"
+            n += 1
+        assert int(gold[f"track/{photo}/abort/ok"]) == 0 and np.isnan(gold[f"track/{photo}/abort/lastRes"][:3]).all()
+        assert int(gold[f"track/{photo}/aff_insane/ok"]) == 0 and int(gold[f"track/{photo}/aff_recovers/ok"]) == 1
+        assert int(gold[f"track/{photo}/far/ok"]) == 1
+    assert n == 110
+
+
+def test_track_new_coarse_matches_reference(gold, oracle):
+    """a11: the oracle's candidate list + sequential winner rule against the reference's own FullSystem::trackNewCoarse
+    (FullSystem.cpp:502-699, compiled verbatim with the vendored Sophus arithmetic) for six camera histories x two photometric
+    set-ups: first try wins (1 try), winner among the zero-motion candidates (3-5 tries), no early break (all 31 tries, aborts
+    active), an invalid shell (list collapses to the identity). Number of tries, camToTrackingRef, affine parameters,
+    achievedRes (= the new lastCoarseRMSE) and the returned Vec4 - bit-exact."""
+    tries_seen = set()
+    for photo in R.TRACKER_PHOTO:
+        got = R.run_candidate_cases_oracle(R.tracker_problem(photo))
+        keys = [k for k in gold if k.startswith(f"candidates/{photo}/")]
+        assert set(keys) == set(got) and len(keys) == 5 * 6
+        for k in keys:
+            assert _same_bits(got[k], gold[k]), f"oracle trackNewCoarse differs from the reference: {k} {got[k]} {gold[k]}"
+            if k.endswith("n_tries"):
+                tries_seen.add(int(gold[k]))
+    assert {1, 31} <= tries_seen and len(tries_seen) >= 3
+
+
+def test_stitch_matches_reference(gold, oracle):
+    """f2 (stitch): the oracle's stitchDoubleMT restatement (oracle/oracle_solve.cpp) against the reference's own
+    AccumulatedTopHessianSSE::stitchDoubleInternal / stitchDoubleMT and AccumulatedSCHessianSSE::stitchDoubleInternal /
+    stitchDoubleMT (AccumulatedTopHessian.cpp:241-303, .h:91-139; AccumulatedSCHessian.cpp:78-157, .h:93-133; compiled verbatim,
+    oracle/ref_ba.cpp) behind its own addPoint passes, 7 keyframes / 19 958 residuals: H (60x60) and b for the active set, the
+    linearised sets (modes 1 and 2, with camera and frame priors) and the Schur complement - bit-exact."""
+    got = R.run_stitch_cases_oracle(R.ba_problem())
+    keys = [k for k in gold if k.startswith("stitch/")]
+    assert set(keys) == set(got) and len(keys) == 8
+    for k in keys:
+        assert _same_bits(got[k], gold[k]), f"oracle stitch differs from the reference: {k}"
+    assert np.allclose(gold["stitch/top0/H"], gold["stitch/top0/H"].T) and np.abs(gold["stitch/sc/H"]).max() > 0
 
 
 def test_ba_accumulation_matches_reference(gold, oracle):
@@ -440,4 +517,111 @@ def test_gpu_immature_point_matches_reference(gold):
     finally:
         if I is not None:
             I.close()
+        ctx.close()
+
+
+def _gpu_tracker_ctx(P):
+    from nalo_slam_b200 import capi
+
+    ctx = capi.Context(P["w"], P["h"], P["L"], device=0, max_frames=2)
+    ctx.make_images(0, P["ref_img"])
+    ctx.make_images(1, P["new_img"])
+    ctx.make_k(0, *P["K"])
+    ctx.set_ref_dense(0, 0, P["idw"], P["ws"], aff=P["aff_ref"], exposure=P["exposures"][0])
+    return ctx
+
+
+@pytest.mark.gpu
+def test_gpu_track_matches_reference(gold):
+    """a8 on the device (nalo_track) against the outputs of the reference's own CoarseTracker::trackNewestCoarse in the fixture
+    (track/*): return value exact, pose within 1e-5 (north-star bar), affine parameters, lastResiduals incl. the NaN pattern of
+    aborted runs, flow indicators; an aborted run leaves pose / affine untouched."""
+    from nalo_slam_b200 import synth
+
+    n = 0
+    for photo in R.TRACKER_PHOTO:
+        P = R.tracker_problem(photo)
+        ctx = _gpu_tracker_ctx(P)
+        try:
+            for tag, mA, mB, pose0, aff0, lvl0, minres in R.track_cases(P):
+                g = f"track/{photo}/{tag}"
+                ctx.set_params(affineOptModeA=mA, affineOptModeB=mB)
+                ok, pose, aff, lr, fl, st = ctx.track(0, 1, pose0, aff0, coarsestLvl=lvl0, minRes=minres, exposure=P["exposures"][1])
+                assert int(ok) == int(gold[f"{g}/ok"]), g
+                dt, dr = synth.pose_distance(pose, gold[f"{g}/pose"])
+                assert dt < 1e-5 and dr < 1e-5, (g, dt, dr)
+                assert abs(aff[0] - gold[f"{g}/aff"][0]) < 1e-4 and abs(aff[1] - gold[f"{g}/aff"][1]) < 1e-2, (g, aff, gold[f"{g}/aff"])
+                assert np.array_equal(np.isnan(lr), np.isnan(gold[f"{g}/lastRes"])), (g, lr, gold[f"{g}/lastRes"])
+                assert np.allclose(lr, gold[f"{g}/lastRes"], rtol=1e-3, equal_nan=True), (g, lr, gold[f"{g}/lastRes"])
+                assert np.allclose(fl, gold[f"{g}/flow"], rtol=1e-3, atol=1e-6), (g, fl, gold[f"{g}/flow"])
+                if tag.startswith("abort"):
+                    assert np.array_equal(pose, np.asarray(pose0, dtype=np.float64)) and np.array_equal(aff, np.asarray(aff0, dtype=np.float64))
+                n += 1
+        finally:
+            ctx.close()
+    assert n == 22
+
+
+@pytest.mark.gpu
+def test_gpu_track_new_coarse_matches_reference(gold, oracle):
+    """a11 on the device (nalo_motion_candidates + nalo_track_multi + nalo_winner_rule) against the outputs of the reference's
+    own FullSystem::trackNewCoarse in the fixture (candidates/*): number of tries exact, winning pose within 1e-5 of
+    camToTrackingRef^-1, affine parameters, achievedRes, the returned Vec4."""
+    from nalo_slam_b200 import capi, synth
+
+    for photo in R.TRACKER_PHOTO:
+        P = R.tracker_problem(photo)
+        ctx = _gpu_tracker_ctx(P)
+        ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)
+        try:
+            for tag, spre, sl, lf, valid, aff_last, rmse in R.candidate_histories(P):
+                g = f"candidates/{photo}/{tag}"
+                tries = capi.motion_candidates(spre, sl, lf, poses_valid=all(valid))
+                res = ctx.track_multi(0, 1, tries, np.tile(np.array(aff_last, np.float64), (len(tries), 1)), exposure=P["exposures"][1])
+                got = capi.winner_rule(res, aff_last, rmse)
+                assert got["tries"] == int(gold[f"{g}/n_tries"]), (g, got["tries"], int(gold[f"{g}/n_tries"]))
+                dt, dr = synth.pose_distance(got["pose"], oracle.se3_inverse(gold[f"{g}/camToTrackingRef"]))
+                assert dt < 1e-5 and dr < 1e-5, (g, dt, dr)
+                assert abs(got["aff"][0] - gold[f"{g}/aff"][0]) < 1e-4 and abs(got["aff"][1] - gold[f"{g}/aff"][1]) < 1e-2, g
+                assert np.allclose(got["lastCoarseRMSE"], gold[f"{g}/achievedRes"], rtol=1e-3, equal_nan=True), g
+                assert np.allclose([got["achievedRes"][0], *got["flow"]], gold[f"{g}/ret4"], rtol=1e-3, atol=1e-6), g
+        finally:
+            ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_stitch_matches_reference(gold):
+    """f2 (stitch) on the device (nalo_ba_solve's stitched matrices, behind the device's own accumulation passes) against the
+    outputs of the reference's own addPoint + stitchDoubleInternal / stitchDoubleMT in the fixture (stitch/*): the device
+    accumulates in fp32 in another order, so the bar is the H / b bar, 1e-4 of sqrt(H_ii H_jj) per entry."""
+    from nalo_slam_b200 import capi
+
+    prob = R.ba_problem()
+    Wn = R.stitch_window(prob["nf"])
+    ctx = capi.Context(64, 64, 3, device=0, max_frames=2)
+    ba = capi.BA(ctx, prob["n_res"] + 16, prob["n_pts"] + 16)
+    try:
+        ba.upload(prob)
+        kw = dict(adHost=Wn["adHost"], adTarget=Wn["adTarget"], cPrior=Wn["cPrior"], frame_prior=Wn["framePrior"],
+                  frame_delta_prior=Wn["frameDeltaPrior"], lam=1e-5, want_stitched=True)
+
+        def check(H, b, key):
+            Hr, br = gold[f"stitch/{key}/H"], gold[f"stitch/{key}/b"]
+            d = np.sqrt(np.abs(np.diag(gold["stitch/top0/H"])) + np.abs(np.diag(gold["stitch/top1/H"])))
+            assert np.all(np.abs(H - Hr) <= 1e-4 * np.outer(d, d) + 1e-9 * np.abs(Hr).max()), (key, np.max(np.abs(H - Hr) / np.outer(d, d)))
+            assert np.max(np.abs(b - br)) <= 1e-4 * np.max(np.abs(br)), (key, np.max(np.abs(b - br)) / np.max(np.abs(br)))
+
+        ba.accumulate_top(0)
+        ba.accumulate_top(1)
+        ba.take_data()
+        ba.accumulate_sc(shiftPriorToZero=True, useL=True)
+        out = ba.solve(**kw)
+        check(out["HA"], out["bA"], "top0")
+        check(out["HL"], out["bL"], "top1")
+        check(out["Hsc"], out["bsc"], "sc")
+        ba.accumulate_top(2)
+        out = ba.solve(**kw)
+        check(out["HL"], out["bL"], "top2")
+    finally:
+        ba.close()
         ctx.close()
