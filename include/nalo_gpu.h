@@ -190,6 +190,20 @@ int nalo_motion_candidates(const double sprelast_c2w[7], const double slast_c2w[
 int nalo_track_multi(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, int nHyp, double* poses7_inout, double* affs2_inout,
                      int coarsestLvl, int* ok_out, double* lastRes5_out, double* flow3_out, int* pass_lvl_out, double* pass_res_out,
                      NaloTrackStats* stats);
+/* The same with static abort thresholds handed to every candidate (CoarseTracker.cpp:1225-1227): a candidate whose residual
+ * after a level pass exceeds 1.5 x minResForAbort5[level] stops there (ok = 0, pose / aff untouched, its pass log ends with
+ * level -2). Exactness against the sequential loop holds whenever the thresholds are no lower than the ones the loop would hand
+ * the candidate, e.g. achievedRes of a finished PREFIX of the tries (it only decreases along the loop, FullSystem.cpp:643-650);
+ * nalo_winner_rule returns NALO_E_STATE if a log was cut short by a threshold the loop would not have applied. */
+int nalo_track_multi_thr(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, int nHyp, double* poses7_inout, double* affs2_inout,
+                         int coarsestLvl, const double minResForAbort5[5], int* ok_out, double* lastRes5_out, double* flow3_out,
+                         int* pass_lvl_out, double* pass_res_out, NaloTrackStats* stats);
+/* FullSystem::trackNewCoarse's loop (:583-668) in one call: try 0 alone on all SMs; if the winner rule does not break after it,
+ * tries 1..n-1 concurrently in one launch with the thresholds held after try 0; then the sequential rule replayed on the pass
+ * logs. Same winner, achievedRes, lastCoarseRMSE update and number of tries as the reference's loop. aff_last = slast->aff_g2l. */
+int nalo_track_candidates(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, int nHyp, const double* tries7, const double aff_last[2],
+                          int coarsestLvl, double lastCoarseRMSE5_inout[5], float reTrackThreshold, double pose_out7[7], double aff_out2[2],
+                          double flow_out3[3], double achievedRes5[5], int* tries_used, int* haveOneGood, NaloTrackStats* stats /* nullable */);
 /* Winner rule (:583-666) replayed in index order over gathered per-candidate results (pure host function). */
 int nalo_winner_rule(int nHyp, const double* poses7, const double* affs2, const int* ok, const double* flow3, const int* pass_lvl,
                      const double* pass_res, const double aff_last[2], const double first_try_pose7[7], double lastCoarseRMSE5_inout[5],

@@ -454,6 +454,44 @@ class Context:
                     stats=st.as_dict())
 
 
+def _track_candidates(self, trk, new_slot, tries7, aff_last, lastCoarseRMSE, coarsestLvl=None, reTrackThreshold=1.5, exposure=1.0):
+    """nalo_track_candidates: FullSystem::trackNewCoarse's loop in one call (device-side aborts, at most two launches)."""
+    tries = np.ascontiguousarray(tries7, dtype=np.float64)
+    n = tries.shape[0]
+    if coarsestLvl is None:
+        coarsestLvl = min(self.levels, 5) - 1
+    rmse = np.array(lastCoarseRMSE, dtype=np.float64)
+    al = np.ascontiguousarray(aff_last, dtype=np.float64)
+    pose, aff, flow, ach = np.zeros(7), np.zeros(2), np.zeros(3), np.zeros(5)
+    used, good = C.c_int(0), C.c_int(0)
+    st = NaloTrackStats()
+    self._ck(self.L.nalo_track_candidates(self.h_, C.c_int(trk), C.c_int(new_slot), C.c_float(exposure), C.c_int(n), _ptr(tries), _ptr(al),
+                                          C.c_int(coarsestLvl), _ptr(rmse), C.c_float(reTrackThreshold), _ptr(pose), _ptr(aff), _ptr(flow), _ptr(ach),
+                                          C.byref(used), C.byref(good), C.byref(st)))
+    return dict(good=bool(good.value), pose=pose, aff=aff, flow=flow, achievedRes=ach, lastCoarseRMSE=rmse, tries=used.value, stats=st.as_dict())
+
+
+def _track_multi_thr(self, trk, new_slot, poses7, affs2, minRes5, coarsestLvl=None, exposure=1.0):
+    """nalo_track_multi_thr: track_multi with static abort thresholds for every candidate."""
+    poses = np.ascontiguousarray(poses7, dtype=np.float64).copy()
+    n = poses.shape[0]
+    affs = np.ascontiguousarray(affs2, dtype=np.float64).copy()
+    if coarsestLvl is None:
+        coarsestLvl = min(self.levels, 5) - 1
+    mr = np.ascontiguousarray(minRes5, dtype=np.float64)
+    ok = np.zeros(n, dtype=np.int32)
+    lr, fl = np.zeros((n, 5)), np.zeros((n, 3))
+    pl, pr = np.zeros((n, 6), dtype=np.int32), np.zeros((n, 6))
+    st = NaloTrackStats()
+    self._ck(self.L.nalo_track_multi_thr(self.h_, C.c_int(trk), C.c_int(new_slot), C.c_float(exposure), C.c_int(n), _ptr(poses), _ptr(affs),
+                                         C.c_int(coarsestLvl), _ptr(mr), _ptr(ok), _ptr(lr), _ptr(fl), _ptr(pl), _ptr(pr), C.byref(st)))
+    return dict(ok=ok, poses=poses, affs=affs, lastRes=lr, flow=fl, pass_lvl=pl, pass_res=pr, stats=st.as_dict())
+
+
+Context.track_candidates = _track_candidates
+Context.track_multi_thr = _track_multi_thr
+
+
 def motion_candidates(sprelast_c2w, slast_c2w, lastF_c2w, poses_valid=True):
     L = load()
     out = np.zeros((31, 7))

@@ -150,9 +150,12 @@ int nalo_motion_candidates(const double sprelast_c2w[7], const double slast_c2w[
   return NALO_OK;
 }
 
-int nalo_track_multi(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, int nHyp, double* poses7, double* affs2,
-                     int coarsestLvl, int* ok_out, double* lastRes5_out, double* flow3_out, int* pass_lvl_out, double* pass_res_out,
-                     NaloTrackStats* stats) {
+}  // extern "C"
+
+// minRes5 != nullptr: every candidate is handed these abort thresholds (CoarseTracker.cpp:1225-1227); nullptr: none.
+static int track_multi_impl(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, int nHyp, double* poses7, double* affs2,
+                            int coarsestLvl, const double* minRes5, int* ok_out, double* lastRes5_out, double* flow3_out, int* pass_lvl_out,
+                            double* pass_res_out, NaloTrackStats* stats) {
   if (!ctx || trk < 0 || trk >= NALO_MAX_TRACKERS || !poses7 || !affs2) return NALO_E_ARG;
   if (nHyp < 1 || nHyp > NALO_MAX_HYPOTHESES) return nalo_fail(ctx, NALO_E_ARG, "nHyp %d out of [1,%d]", nHyp, NALO_MAX_HYPOTHESES);
   if (coarsestLvl < 0 || coarsestLvl >= NALO_TRACK_LEVELS || coarsestLvl >= ctx->levels) return NALO_E_ARG;
@@ -169,7 +172,8 @@ int nalo_track_multi(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, i
     P->aff[0] = affs2[2 * i];
     P->aff[1] = affs2[2 * i + 1];
     P->coarsestLvl = coarsestLvl;
-    P->useAbort = 0;
+    P->useAbort = minRes5 ? 1 : 0;
+    if (minRes5) for (int l = 0; l < NALO_TRACK_LEVELS; l++) P->minRes[l] = minRes5[l];
   }
   NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_problems, ctx->h_problems, sizeof(NaloTrackProblem) * nHyp, cudaMemcpyHostToDevice, ctx->stream));
   if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evA, ctx->stream));
@@ -213,6 +217,22 @@ int nalo_track_multi(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, i
   return NALO_OK;
 }
 
+extern "C" {
+
+int nalo_track_multi(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, int nHyp, double* poses7, double* affs2,
+                     int coarsestLvl, int* ok_out, double* lastRes5_out, double* flow3_out, int* pass_lvl_out, double* pass_res_out,
+                     NaloTrackStats* stats) {
+  return track_multi_impl(ctx, trk, new_slot, exposure_new, nHyp, poses7, affs2, coarsestLvl, nullptr, ok_out, lastRes5_out, flow3_out,
+                          pass_lvl_out, pass_res_out, stats);
+}
+
+int nalo_track_multi_thr(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, int nHyp, double* poses7, double* affs2,
+                         int coarsestLvl, const double minResForAbort5[5], int* ok_out, double* lastRes5_out, double* flow3_out,
+                         int* pass_lvl_out, double* pass_res_out, NaloTrackStats* stats) {
+  return track_multi_impl(ctx, trk, new_slot, exposure_new, nHyp, poses7, affs2, coarsestLvl, minResForAbort5, ok_out, lastRes5_out, flow3_out,
+                          pass_lvl_out, pass_res_out, stats);
+}
+
 int nalo_winner_rule(int nHyp, const double* poses7, const double* affs2, const int* ok, const double* flow3, const int* pass_lvl,
                      const double* pass_res, const double aff_last[2], const double first_try_pose7[7], double lastCoarseRMSE5[5],
                      float reTrackThreshold, double pose_out7[7], double aff_out2[2], double flow_out3[3], double achievedRes5[5],
@@ -232,6 +252,7 @@ int nalo_winner_rule(int nHyp, const double* poses7, const double* affs2, const 
     bool aborted = false;
     for (int p = 0; p < 6; p++) {
       const int lvl = pass_lvl[6 * i + p];
+      if (lvl == -2) return NALO_E_STATE;  // the candidate was cut short on the device by a threshold the sequential loop would not have applied yet
       if (lvl < 0) break;
       lastRes[lvl] = pass_res[6 * i + p];
       if (lastRes[lvl] > 1.5 * achieved[lvl]) { aborted = true; break; }  // CoarseTracker.cpp:1227
@@ -265,6 +286,60 @@ int nalo_winner_rule(int nHyp, const double* poses7, const double* affs2, const 
   for (int k = 0; k < 5; k++) achievedRes5[k] = achieved[k];
   if (tries_used) *tries_used = tries;
   if (haveOneGood_out) *haveOneGood_out = haveOneGood ? 1 : 0;
+  return NALO_OK;
+}
+
+// FullSystem::trackNewCoarse (FullSystem.cpp:583-699) in one call, with the reference's aborts applied ON THE DEVICE where that is
+// provably what the sequential loop does. Try 0 (the constant-motion prediction, in a live system almost always the winner) is
+// tracked alone on all SMs. If the winner rule breaks after it (:653-654) the call is over - one try, like the reference. Otherwise
+// the remaining tries run concurrently in one launch, each handed the abort thresholds the loop holds after try 0
+// (achievedRes_1). The loop's own thresholds for try i (achievedRes_i) are a running minimum (:643-650), so
+// achievedRes_i <= achievedRes_1 level by level: a try cut short by achievedRes_1 at some level would have been cut short by the
+// sequential loop at that level or a coarser one, and what it would have computed beyond that point is never looked at. The
+// sequential rule is then replayed on the pass logs (nalo_winner_rule), which reproduces winner, achievedRes and the number of
+// tries of the sequential loop exactly.
+int nalo_track_candidates(nalo_ctx* ctx, int trk, int new_slot, float exposure_new, int nHyp, const double* tries7, const double aff_last[2],
+                          int coarsestLvl, double lastCoarseRMSE5[5], float reTrackThreshold, double pose_out7[7], double aff_out2[2],
+                          double flow_out3[3], double achievedRes5[5], int* tries_used, int* haveOneGood, NaloTrackStats* stats) {
+  if (!ctx || !tries7 || !aff_last || !lastCoarseRMSE5 || !pose_out7 || !aff_out2 || !flow_out3 || !achievedRes5) return NALO_E_ARG;
+  if (nHyp < 1 || nHyp > NALO_MAX_HYPOTHESES) return nalo_fail(ctx, NALO_E_ARG, "nHyp %d out of [1,%d]", nHyp, NALO_MAX_HYPOTHESES);
+  std::vector<double> poses(tries7, tries7 + 7 * (size_t)nHyp), affs(2 * (size_t)nHyp), flow(3 * (size_t)nHyp, 0.0), passRes(6 * (size_t)nHyp, NAN);
+  std::vector<int> ok((size_t)nHyp, 0), passLvl(6 * (size_t)nHyp, -1);
+  for (int i = 0; i < nHyp; i++) { affs[2 * i] = aff_last[0]; affs[2 * i + 1] = aff_last[1]; }
+  NaloTrackStats st0, st1;
+  memset(&st0, 0, sizeof(st0));
+  memset(&st1, 0, sizeof(st1));
+  // ---- try 0 alone (no thresholds: achievedRes is all NaN before the first try)
+  double lr[5];
+  int rc = nalo_track(ctx, trk, new_slot, exposure_new, poses.data(), affs.data(), coarsestLvl, nullptr, lr, flow.data(), &ok[0], &st0);
+  if (rc != NALO_OK) return rc;
+  for (int k = 0; k < 6; k++) { passLvl[k] = ctx->h_resMapped->passLvl[k]; passRes[k] = ctx->h_resMapped->passRes[k]; }
+  double rmse[5], thr[5];
+  int used = 0, good = 0;
+  for (int k = 0; k < 5; k++) rmse[k] = lastCoarseRMSE5[k];
+  rc = nalo_winner_rule(1, poses.data(), affs.data(), ok.data(), flow.data(), passLvl.data(), passRes.data(), aff_last, tries7, rmse, reTrackThreshold,
+                        pose_out7, aff_out2, flow_out3, thr, &used, &good);
+  if (rc != NALO_OK) return rc;
+  const bool breaks = good && thr[0] < lastCoarseRMSE5[0] * reTrackThreshold;
+  if (!breaks && nHyp > 1) {
+    // ---- tries 1..n-1 in one launch, handed achievedRes after try 0 (NaN entries never abort)
+    rc = track_multi_impl(ctx, trk, new_slot, exposure_new, nHyp - 1, poses.data() + 7, affs.data() + 2, coarsestLvl, thr, ok.data() + 1, nullptr,
+                          flow.data() + 3, passLvl.data() + 6, passRes.data() + 6, &st1);
+    if (rc != NALO_OK) return rc;
+    for (int k = 0; k < 5; k++) rmse[k] = lastCoarseRMSE5[k];
+    rc = nalo_winner_rule(nHyp, poses.data(), affs.data(), ok.data(), flow.data(), passLvl.data(), passRes.data(), aff_last, tries7, rmse,
+                          reTrackThreshold, pose_out7, aff_out2, flow_out3, thr, &used, &good);
+    if (rc != NALO_OK) return nalo_fail(ctx, rc, "nalo_track_candidates: pass logs inconsistent with the sequential winner rule");
+  }
+  for (int k = 0; k < 5; k++) { achievedRes5[k] = thr[k]; lastCoarseRMSE5[k] = rmse[k]; }
+  if (tries_used) *tries_used = used;
+  if (haveOneGood) *haveOneGood = good;
+  if (stats) {
+    *stats = st0;
+    stats->residuals += st1.residuals; stats->evals += st1.evals; stats->iters += st1.iters; stats->launches += st1.launches;
+    for (int k = 0; k < NALO_TRACK_LEVELS; k++) stats->evals_per_level[k] += st1.evals_per_level[k];
+    stats->kernel_ms += st1.kernel_ms;
+  }
   return NALO_OK;
 }
 

@@ -116,6 +116,14 @@ def test_config3_candidates_kitti(rmse0, kitti_pair, gpu_ctx_kitti, oracle):
     assert res["stats"]["launches"] == 1
     if rmse0 == 0.0:
         assert got["tries"] == 31
+    # the whole loop in one call, with the aborts applied on the device (nalo_track_candidates)
+    one = ctx.track_candidates(0, 1, tries, aff_last, rmse)
+    assert one["good"] == ref["good"] and one["tries"] == ref["tries"], (one["tries"], ref["tries"])
+    dt, dr = synth.pose_distance(one["pose"], ref["pose"])
+    assert dt < POSE_TOL and dr < POSE_TOL, (dt, dr)
+    assert np.allclose(one["achievedRes"], ref["achievedRes"], rtol=1e-3, equal_nan=True)
+    assert np.allclose(one["lastCoarseRMSE"], ref["lastCoarseRMSE"], rtol=1e-3, equal_nan=True)
+    assert one["stats"]["launches"] == (1 if ref["tries"] == 1 else 2)
 
 
 # ------------------------------------------------------------------------------------------- the benchmark's step

@@ -267,3 +267,82 @@ def test_track_frames_submit_wait(small_pair, gpu_ctx_small, oracle):
         assert np.array_equal(again["poses"], refA["poses"])
     finally:
         ctx.close()
+
+
+def _bad_tries(rng, n, scale):
+    """Candidates far from the truth: they end on a poor residual and are what the abort thresholds exist for."""
+    from oracle import oracle_py as O
+
+    return np.array([O.se3_exp(np.concatenate([rng.normal(0, 0.3 * scale, 3), rng.normal(0, 0.15 * scale, 3)])) for _ in range(n)])
+
+
+@pytest.mark.parametrize("case", ["good_first_break", "good_first_all", "bad_first", "good_in_the_middle", "all_bad", "single"])
+def test_track_candidates_equals_sequential_loop(case, small_pair, gpu_ctx_small, oracle):
+    """nalo_track_candidates (try 0 alone, the rest in one launch with the thresholds held after try 0, device-side aborts, rule
+    replayed) == the oracle's sequential trackNewCoarse loop: same winner, number of tries, achievedRes, lastCoarseRMSE - for
+    orderings in which the aborts fire (bad candidates after a good one), do not fire (bad first), and with / without the
+    early break. The pass logs the device cut short must never be needed by the replay (NALO_E_STATE otherwise)."""
+    P = small_pair
+    ctx = gpu_ctx_small
+    T = _setup(ctx, P, oracle)
+    rng = np.random.default_rng(77)
+    cand = capi.motion_candidates(*_history(P))
+    bad = _bad_tries(rng, 12, 1.0)
+    aff_last = np.array([0.0, 0.0])
+    _, _, _, good_res, _ = T.track(P["gt"], P["aff"])
+    if case == "good_first_break":
+        tries, rmse = np.concatenate([cand[:3], bad]), np.full(5, 1e9)
+    elif case == "good_first_all":
+        tries, rmse = np.concatenate([cand[:3], bad, cand[5:9]]), np.zeros(5)
+    elif case == "bad_first":
+        tries, rmse = np.concatenate([bad[:4], cand[:6], bad[4:]]), good_res.copy()
+    elif case == "good_in_the_middle":
+        tries, rmse = np.concatenate([bad[:1], cand[4:5], bad[1:6], cand[:2], bad[6:]]), np.zeros(5)
+    elif case == "all_bad":
+        tries, rmse = _bad_tries(rng, 10, 3.0), good_res.copy()
+    else:
+        tries, rmse = cand[:1], np.zeros(5)
+    ref = T.track_new_coarse(tries, aff_last, rmse)
+    got = ctx.track_candidates(0, 1, tries, aff_last, rmse)
+    assert got["good"] == ref["good"] and got["tries"] == ref["tries"], (case, got["tries"], ref["tries"])
+    dt, dr = synth.pose_distance(got["pose"], ref["pose"])
+    assert dt < 1e-5 and dr < 1e-5, (case, dt, dr)
+    assert np.allclose(got["achievedRes"], ref["achievedRes"], rtol=1e-3, equal_nan=True), (case, got["achievedRes"], ref["achievedRes"])
+    assert np.allclose(got["lastCoarseRMSE"], ref["lastCoarseRMSE"], rtol=1e-3, equal_nan=True)
+    assert np.allclose(got["flow"], ref["flow"], rtol=1e-3, atol=1e-6)
+    assert np.allclose(got["aff"], ref["aff"], atol=1e-2)
+    if case in ("good_first_break", "single"):
+        assert got["tries"] == 1 and got["stats"]["launches"] == 1          # one try, one launch: like the reference
+    else:
+        assert got["stats"]["launches"] == 2
+    if case == "good_first_all":
+        # the aborts fired on the device: the 12 bad candidates cost a fraction of a full alignment each
+        full = ctx.track_multi(0, 1, tries, np.zeros((len(tries), 2)))
+        assert got["stats"]["evals"] < 0.7 * full["stats"]["evals"], (got["stats"]["evals"], full["stats"]["evals"])
+        # and the rule replayed on the complete logs gives the same answer
+        w = capi.winner_rule(full, aff_last, rmse)
+        assert w["tries"] == got["tries"] and np.array_equal(np.isnan(w["achievedRes"]), np.isnan(got["achievedRes"]))
+        dt, dr = synth.pose_distance(w["pose"], got["pose"])
+        assert dt < 1e-6 and dr < 1e-6
+
+
+def test_track_multi_thr_marks_aborts_and_rule_rejects_wrong_thresholds(small_pair, gpu_ctx_small, oracle):
+    """nalo_track_multi_thr: a candidate above 1.5 x threshold after a level stops there (ok = 0, pose untouched, log ends with
+    -2); replaying the rule on logs cut by thresholds LOWER than the loop's own is refused, not silently accepted."""
+    P = small_pair
+    ctx = gpu_ctx_small
+    T = _setup(ctx, P, oracle)
+    cand = capi.motion_candidates(*_history(P))[:4]
+    tight = np.full(5, 1e-3)
+    res = ctx.track_multi_thr(0, 1, cand, np.zeros((4, 2)), tight)
+    assert not res["ok"].any() and np.array_equal(res["poses"], cand)
+    top = P["L"] - 1
+    for i in range(4):
+        assert res["pass_lvl"][i, 0] == top and res["pass_lvl"][i, 1] == -2
+        assert np.isnan(res["lastRes"][i, :top]).all() and np.isfinite(res["lastRes"][i, top])
+    with pytest.raises(capi.NaloError):
+        capi.winner_rule(res, [0.0, 0.0], np.zeros(5))
+    loose = np.full(5, 1e9)
+    res2 = ctx.track_multi_thr(0, 1, cand, np.zeros((4, 2)), loose)
+    full = ctx.track_multi(0, 1, cand, np.zeros((4, 2)))
+    assert res2["ok"].all() and np.array_equal(res2["poses"], full["poses"]) and np.array_equal(res2["pass_lvl"], full["pass_lvl"])
