@@ -88,3 +88,42 @@ def gpu_ctx_kitti(kitti_pair):
     ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)
     yield ctx
     ctx.close()
+
+
+# ---- LM-trace comparison: shared by tests/test_gpu_configs.py and tests/test_ref_pin.py
+def first_divergence(tg, to):
+    """Index of the first LM-trace record at which device and oracle took different branches (None: same control flow)."""
+    n = min(len(tg), len(to))
+    for k in range(n):
+        if tg[k, 0] != to[k, 0] or tg[k, 1] != to[k, 1] or tg[k, 2] != to[k, 2] or tg[k, 6] != to[k, 6]:
+            return k
+    return None if len(tg) == len(to) else n
+
+
+def knife_edge(tg, to, k):
+    """A branch difference is admissible only if the deciding quantity sits on the decision threshold to within the H/b
+    parity bar (1e-4 relative): |inc| against the 1e-3 break test (CoarseTracker.cpp:1208), or E_new/n_new against E_old/n_old
+    (:1186; E is a sequential fp32 sum of ~3.5e5 terms in the reference, ~1e-3 relative). Returns a description or None."""
+    n = min(len(tg), len(to))
+    if k == n and k > 0:  # one side left the level's loop (or finished) one iteration earlier: the |inc| > 1e-3 test
+        a, b = tg[k - 1, 7], to[k - 1, 7]
+        if min(a, b) <= 1e-3 <= max(a, b) and abs(a - b) <= 1e-4 * max(a, b):
+            return f"|inc| straddles the 1e-3 break threshold: device {a:.9g}, oracle {b:.9g}"
+        return None
+    if k < n and tg[k, 0] != to[k, 0] and k > 0:  # next level entered by one side only: same test one record earlier
+        a, b = tg[k - 1, 7], to[k - 1, 7]
+        if min(a, b) <= 1e-3 <= max(a, b) and abs(a - b) <= 1e-4 * max(a, b):
+            return f"|inc| straddles the 1e-3 break threshold: device {a:.9g}, oracle {b:.9g}"
+        return None
+    if k < n and tg[k, 2] != to[k, 2] and tg[k, 1] == 1:  # accept vs reject
+        def old_ratio(t):  # E/n of the last accepted evaluation before record k on this level
+            for j in range(k - 1, -1, -1):
+                if t[j, 2] == 1 and t[j, 0] == t[k, 0]:
+                    return t[j, 4] / t[j, 5]
+            return np.nan
+        rg, ro = (tg[k, 4] / tg[k, 5]) / old_ratio(tg), (to[k, 4] / to[k, 5]) / old_ratio(to)
+        if abs(rg - 1) <= 2e-3 and abs(ro - 1) <= 2e-3:
+            return f"accept test at the fp32 summation noise: E_new/n_new over E_old/n_old = device {rg:.7f}, oracle {ro:.7f}"
+    return None
+
+
