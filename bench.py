@@ -110,12 +110,14 @@ def make_workload(seed=synth.DEFAULT_SEED, n_frames=N_FRAMES):
     sc = synth.make_scene(W, H, seed=seed)
     rng = np.random.default_rng(seed)
     ref = synth.render_ref(sc)
-    news, gts = [], []
+    news, gts, xis = [], [], []
     for _ in range(n_frames):
         xi, aff = synth.random_motion(rng)
         gt = synth.se3_exp(xi)
         news.append(synth.render_new(sc, gt, aff))
         gts.append(gt)
+        xis.append(np.asarray(xi, dtype=np.float64))
+    make_workload.xis = xis  # (tangent vectors of the ground-truth motions: the analytic camera history of the candidate bench)
     return sc, ref, news, gts
 
 
@@ -187,6 +189,293 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+class _StreamTimer:
+    """CUDA events on the library's own stream (torch.cuda.Event only sees torch's current stream)."""
+
+    def __init__(self, ctx, local_rank):
+        import torch
+
+        self.torch = torch
+        self.ext = torch.cuda.ExternalStream(ctx.stream(), device=local_rank)
+
+    def pair(self):
+        return self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+
+    def record(self, ev):
+        with self.torch.cuda.stream(self.ext):
+            ev.record()
+
+
+def run_sharded(args, ctx, rank, world, local_rank, dist, sc, ref, news, gts, agref, idw, ws, pc_n, peak):
+    """The two paths that shard across GPUs (SURVEY.md section 8 e), STRONG scaling: the total is fixed, block-partitioned over
+    the ranks, no data-path collective, one NCCL gather of the per-unit records INSIDE the timed region.
+      pairs      : args.shard_pairs independent 1241x376 frame-pair alignments (BASELINE.json config 5)
+      candidates : the 31 motion candidates of FullSystem::trackNewCoarse (config 3), (a) all tracked to completion and
+                   (b) as the reference's loop runs them: try 0 first, the others with the abort thresholds held after it.
+    Times: CUDA events on each rank's library stream and wall clock around track + gather, max over ranks, best of 3."""
+    import torch
+
+    from nalo_slam_b200 import capi, sharding
+
+    dev = torch.device("cuda", local_rank)
+    tm = _StreamTimer(ctx, local_rank)
+
+    def max_over_ranks(x):
+        if not dist:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        v = np.asarray(v, dtype=np.float64)
+        if not dist:
+            return v
+        t = torch.from_numpy(v).to(dev)
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    out = {"scaling": "strong", "n_gpus": world,
+           "timing": "per config: barrier, then wall clock around the rank's tracking call(s) + the NCCL gather of the records, max over ranks, best of 3; kernel_ms from CUDA events on the library stream"}
+
+    # ---------------------------------------------------------------- candidates (config 3)
+    p_id = synth.pose_identity()
+    slast = synth.se3_exp(-0.5 * np.asarray(gts["xi0"]))  # previous frame half way to the new frame's camToWorld = exp(-xi)
+    tries = capi.motion_candidates(p_id, slast, p_id)
+    n = len(tries)
+    # (the batched figures synthesise their pairs through frame slots 0 / 1 and tracker 1: put the keyframe back)
+    ctx.make_images(0, ref)
+    ctx.set_ref_dense(0, 0, idw, ws)
+    ctx.make_images(1, news[0])
+    aff0 = np.zeros(2)
+    cand = {"candidates": n}
+    for mode in ("all_to_completion", "reference_loop_no_break", "reference_loop_first_try_breaks"):
+        best = None
+        for rep in range(4):
+            ctx.flush_l2()
+            ctx.sync()
+            if dist:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = tm.pair()
+            tm.record(a)
+            t0 = time.perf_counter()
+            launches0 = ctx.kernel_launches()
+            if mode == "all_to_completion":
+                lo, hi = sharding.shard_range(n, rank, world)
+                res = ctx.track_multi(0, 1, tries[lo:hi], np.zeros((hi - lo, 2))) if hi > lo else None
+                rec = sharding.pack_records(res) if res is not None else np.zeros((0, sharding.REC))
+                tm.record(b)
+                full = sharding.all_gather_records(rec, n, device=dev) if dist else rec
+                got = capi.winner_rule(sharding.unpack_records(full), aff0, np.zeros(5))
+            else:
+                # try 0 on every rank (identical, deterministic), then the share of tries 1..n-1 with the thresholds after try 0
+                rmse = np.zeros(5) if mode == "reference_loop_no_break" else np.full(5, 1e9)
+                r0 = ctx.track_multi(0, 1, tries[:1], np.zeros((1, 2)))
+                w0 = capi.winner_rule(r0, aff0, rmse)
+                rec0 = sharding.pack_records(r0)
+                if w0["good"] and w0["achievedRes"][0] < rmse[0] * 1.5:
+                    tm.record(b)
+                    full, got = rec0, w0          # the loop breaks after the first try (FullSystem.cpp:653-654): nothing to shard
+                else:
+                    lo, hi = sharding.shard_range(n - 1, rank, world)
+                    res = ctx.track_multi_thr(0, 1, tries[1 + lo : 1 + hi], np.zeros((hi - lo, 2)), w0["achievedRes"]) if hi > lo else None
+                    rec = sharding.pack_records(res) if res is not None else np.zeros((0, sharding.REC))
+                    tm.record(b)
+                    rest = sharding.all_gather_records(rec, n - 1, device=dev) if dist else rec
+                    full = np.concatenate([rec0, rest], axis=0)
+                    got = capi.winner_rule(sharding.unpack_records(full), aff0, rmse)
+            torch.cuda.synchronize()
+            wall = 1e3 * (time.perf_counter() - t0)
+            cur = dict(device_ms=max_over_ranks(a.elapsed_time(b)), wall_ms_incl_gather=max_over_ranks(wall))
+            if rep > 0 and (best is None or cur["wall_ms_incl_gather"] < best["wall_ms_incl_gather"]):
+                best = cur
+                best["tries"] = int(got["tries"])
+                best["good"] = bool(got["good"])
+                best["launches_rank0"] = int(ctx.kernel_launches() - launches0)
+                dt, dr = synth.pose_distance(got["pose"], gts["poses"][0])
+                best["pose_err_vs_gt"] = [float(dt), float(dr)]
+        cand[mode] = best
+    out["candidates"] = cand
+
+    # ---------------------------------------------------------------- batched pairs (config 5)
+    total = int(args.shard_pairs)
+    if total > 0:
+        lo, hi = sharding.shard_range(total, rank, world)
+        mine = hi - lo
+        tau = float(np.quantile(agref[: W * H], 1 - KEEP))
+        B = capi.Batch(ctx, max(mine, 1))
+        blocks = [capi.scene_param_block(synth.make_scene(W, H, seed=1000 + s_)) for s_ in range(8)]
+        t0 = time.perf_counter()
+        for k in range(mine):
+            i = lo + k
+            xi, aff = synth.random_motion(np.random.default_rng(50000 + i))  # pair i is the same whichever rank owns it
+            B.synth_pair(k, blocks[i % 8], synth.se3_exp(xi), aff, tau)
+        ctx.sync()
+        synth_s = time.perf_counter() - t0
+        best = None
+        for rep in range(3):
+            ctx.sync()
+            if dist:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = B.track(0, mine)
+            if dist:  # the packed per-pair records are gathered straight from device memory (NCCL over NVLink)
+                full = sharding.all_gather_device_records(B.results_dev_ptr(), mine, total, dev)
+            else:
+                full = sharding.pack_records(r)
+            torch.cuda.synchronize()
+            wall = 1e3 * (time.perf_counter() - t0)
+            st = r["stats"]
+            cur = dict(kernel_ms=max_over_ranks(st["kernel_ms"]), wall_ms_incl_gather=max_over_ranks(wall))
+            agg = sum_over_ranks([st["residuals"], st["evals"]] + list(st["evals_per_level"]))
+            if rep > 0 and (best is None or cur["wall_ms_incl_gather"] < best["wall_ms_incl_gather"]):
+                best = cur
+                best["pairs_ok"] = int(np.sum(full[:, 0]))
+                ab = float(algorithmic_bytes([int(x) for x in agg[2:]], pc_n))
+                best.update(pairs=total, pairs_per_rank=mine, us_per_pair=1e3 * cur["wall_ms_incl_gather"] / total,
+                            residuals_per_s=float(agg[0]) / (cur["wall_ms_incl_gather"] * 1e-3),
+                            alg_gbs_per_gpu=ab / world / (cur["kernel_ms"] * 1e-3) / 1e9,
+                            frac_hbm_peak=ab / world / (cur["kernel_ms"] * 1e-3) / 1e9 / peak, synth_s=synth_s,
+                            resident_gb_per_gpu=mine * 20e-3)
+        B.close()
+        out["pairs"] = best
+    return out
+
+
+def run_suite(args, ctx, local_rank, sc, ref, news, gts, agref, idw, ws, pc_n, peak, cpu=True):
+    """BASELINE.json configs 1 and 4 on one GPU with the CPU oracle beside them (config 3 is in `sharded.candidates`,
+    config 5 in `sharded.pairs` / `batched`). Device times: CUDA events on the library stream, L2 flushed before every call."""
+    import torch
+
+    from nalo_slam_b200 import capi
+
+    tm = _StreamTimer(ctx, local_rank)
+    O = None
+    if cpu:
+        from oracle import oracle_py as O_
+
+        O = O_
+
+    def timed(fn, reps=10, warm=2):
+        dev = []
+        for i in range(warm + reps):
+            ctx.flush_l2()
+            ctx.sync()
+            a, b = tm.pair()
+            tm.record(a)
+            fn(i)
+            tm.record(b)
+            ctx.sync()
+            b.synchronize()
+            if i >= warm:
+                dev.append(a.elapsed_time(b))
+        return float(np.median(dev))
+
+    def cpu_ms(fn, budget_s=2.0):
+        fn()
+        ts, t_end = [], time.perf_counter() + budget_s
+        while len(ts) < 3 or time.perf_counter() < t_end:
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return 1e3 * float(np.median(ts))
+
+    suite = {}
+    p0 = synth.pose_identity()
+    # ---- config 1: sparse DSO coarse tracking, ~2000 selected points (dense=0)
+    ctx.make_images(0, ref)  # (the batched figures went through frame slots 0 / 1 and tracker 1)
+    ctx.make_images(1, news[0])
+    n_sel, sel_map, _ = ctx.select_pixels(0, 2000.0, 3)
+    u, v, idp, hdi = synth.sparse_reference_points(sc, sel_map)
+    ctx.make_k(1, *sc.K)
+    ctx.set_ref_sparse(1, 0, u, v, idp, hdi)
+    pcs = [ctx.ref_count(1, l) for l in range(LEVELS)]
+    st_ = [None]
+
+    def f1(i):
+        st_[0] = ctx.track(1, 1, p0, [0.0, 0.0])
+
+    d_track = timed(f1, reps=20)
+    d_sel = timed(lambda i: ctx.select_pixels(0, 2000.0, 3, want_map=False))
+    d_ref = timed(lambda i: ctx.set_ref_sparse(1, 0, u, v, idp, hdi))
+    st = st_[0][5]
+    dt, dr = synth.pose_distance(st_[0][1], gts["poses"][0])
+    c1 = {"workload": "config 1: sparse coarse tracking, 1241x376, 5 levels: makeMaps(density 2000) -> setCoarseTrackingRef -> trackNewestCoarse",
+          "selected_points": int(n_sel), "pc_n": pcs, "track_ms": d_track, "makeMaps_ms": d_sel, "setCoarseTrackingRef_ms": d_ref,
+          "residuals_per_s": st["residuals"] / (d_track * 1e-3), "evals": st["evals"], "pose_err_vs_gt": [float(dt), float(dr)],
+          "alg_gbs": algorithmic_bytes(st["evals_per_level"], pcs) / (d_track * 1e-3) / 1e9}
+    if cpu:
+        dref, agr = O.make_images(ref, W, H, LEVELS, fast=True)
+        dnew, _ = O.make_images(news[0], W, H, LEVELS, fast=True)
+        To = O.Tracker(W, H, LEVELS, fast=True)
+        To.set_settings(affineOptModeA=0, affineOptModeB=0)
+        To.makeK(*sc.K)
+        To.set_ref_frame(dref)
+        To.set_new_frame(dnew)
+        To.make_depth_sparse(u, v, idp, hdi)
+        okc, pose_c, _, _, _ = To.track(p0, [0, 0])
+        dtc, drc = synth.pose_distance(st_[0][1], pose_c)
+        c1["cpu"] = {"track_ms": cpu_ms(lambda: To.track(p0, [0, 0])), "cores": 1, "kind": "port"}
+        c1["parity"] = {"max_dt": float(dtc), "max_dr": float(drc), "pass": bool(dtc < 1e-5 and drc < 1e-5)}
+        # config 3 on the CPU: the reference's sequential loop, 1 core (the tracker is single-threaded), both scenarios
+        To.make_depth_dense(idw.ravel(), ws.ravel())
+        slast = synth.se3_exp(-0.5 * np.asarray(gts["xi0"]))
+        tries = capi.motion_candidates(p0, slast, p0)
+        t0 = time.perf_counter()
+        rc = To.track_new_coarse(tries, np.zeros(2), np.zeros(5))
+        t_all = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        To.track_new_coarse(tries, np.zeros(2), np.full(5, 1e9))
+        t_one = 1e3 * (time.perf_counter() - t0)
+        suite["config3_cpu"] = {"sequential_loop_no_break_ms": t_all, "tries": int(rc["tries"]), "first_try_breaks_ms": t_one, "cores": 1, "kind": "port"}
+    suite["config1"] = c1
+
+    # ---- config 4: windowed BA Hessian accumulation, 7 keyframes x dense points (~1.14 M residuals)
+    prob = synth.make_ba_problem(nf=7, pts_per_frame=28571, seed=1, lin_fraction=0.2)
+    nres, npts = prob["n_res"], prob["n_pts"]
+    ba = capi.BA(ctx, nres + 16, npts + 16)
+    t0 = time.perf_counter()
+    ba.upload(prob)
+    up_ms = 1e3 * (time.perf_counter() - t0)
+    import ctypes as C
+
+    H_ = np.zeros((49, 13, 13))
+    accD, accE, accEB, accH, accb = np.zeros((343, 8, 8)), np.zeros((49, 8, 4)), np.zeros((49, 8)), np.zeros((4, 4)), np.zeros(4)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def ftop(mode):
+        def f(i):
+            nn = C.c_int(0)
+            ctx._ck(ctx.L.nalo_ba_accumulate_top(ba.h_, C.c_int(mode), vp(H_), None, C.byref(nn)))
+        return f
+
+    def fsc(i):
+        ctx._ck(ctx.L.nalo_ba_accumulate_sc(ba.h_, C.c_int(1), C.c_int(1), vp(accD), vp(accE), vp(accEB), vp(accH), vp(accb), None))
+
+    dA, dL = timed(ftop(0)), timed(ftop(1))
+    ba.take_data()
+    dS = timed(fsc)
+    c4 = {"workload": "config 4: AccumulatedTopHessian (active + linearised) + AccumulatedSCHessian, 7 keyframes x dense points",
+          "residuals": int(nres), "points": int(npts), "upload_ms_once": up_ms, "top_A_ms": dA, "top_L_ms": dL, "schur_ms": dS,
+          "iteration_ms": dA + dL + dS, "residuals_per_s": nres / ((dA + dL + dS) * 1e-3),
+          "top_A_alg_gbs": (304 * nres + 24 * npts) / (dA * 1e-3) / 1e9, "top_A_frac_hbm_peak": (304 * nres + 24 * npts) / (dA * 1e-3) / 1e9 / peak}
+    if cpu:
+        nT = 6  # NUM_THREADS, util/NumType.h:42: the reference's accumulators run on 6 worker threads
+        cA = cpu_ms(lambda: O.ba_top(prob, mode=0, nThreads=nT, fast=True))
+        cL = cpu_ms(lambda: O.ba_top(prob, mode=1, nThreads=nT, fast=True))
+        J = O.ba_take_data(prob)
+        _, ppA, _ = O.ba_top(prob, mode=0, nThreads=nT, fast=True)
+        _, ppL, _ = O.ba_top(prob, mode=1, nThreads=nT, fast=True)
+        cS = cpu_ms(lambda: O.ba_sc(prob, J, ppA, ppL, True, nThreads=nT, fast=True))
+        c4["cpu"] = {"top_A_ms": cA, "top_L_ms": cL, "schur_ms": cS, "iteration_ms": cA + cL + cS, "cores": nT, "kind": "port",
+                     "note": "6 worker threads = NUM_THREADS of the reference (util/NumType.h:42)"}
+    ba.close()
+    suite["config4"] = c4
+    return suite
 
 
 def run_b200(args, rank, world, local_rank):
@@ -418,6 +707,14 @@ def run_b200(args, rank, world, local_rank):
                                 "alg_bytes_per_launch": float(ab)}}
         B.close()
 
+    gtinfo = {"poses": gts, "xi0": make_workload.xis[0]}
+    sharded = None
+    if not args.no_sharded:
+        sharded = run_sharded(args, ctx, rank, world, local_rank, dist, sc, ref, news, gtinfo, agref, idw, ws, pc_n, peak)
+    suite = None
+    if world == 1 and not args.no_suite:
+        suite = run_suite(args, ctx, local_rank, sc, ref, news, gtinfo, agref, idw, ws, pc_n, peak, cpu=not args.no_cpu)
+
     if rank == 0:
         k_ms = float(np.mean(kern_ms))
         achieved = float(np.mean(alg_bytes)) / (k_ms * 1e-3) / 1e9
@@ -450,6 +747,10 @@ def run_b200(args, rank, world, local_rank):
         }
         if batched is not None:
             line["batched"] = batched
+        if sharded is not None:
+            line["sharded"] = sharded
+        if suite is not None:
+            line["suite"] = suite
         if world == 1 and not args.no_cpu:
             r = cpu_arm(sc, ref, news, 1, args.cpu_budget, fast=True)
             # parity of the timed step itself: every frame the device tracked in the K timed steps against the oracle's pose
@@ -488,6 +789,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--frames", type=int, default=148, help="new frames per step (tracked concurrently; 1..160; default = one per SM)")
+    ap.add_argument("--shard-pairs", type=int, default=4096, help="total frame pairs of the strong-scaling `sharded.pairs` figure (block-partitioned over the ranks; 0 = skip)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the `sharded` object (configs 3 and 5, strong scaling)")
+    ap.add_argument("--no-suite", action="store_true", help="skip the `suite` object (configs 1 and 4 at N=1)")
     ap.add_argument("--batch-pairs", type=int, default=592, help="frame pairs of the secondary batched-throughput figure (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
