@@ -51,6 +51,9 @@ WORKLOAD = ("dense=1 coarse tracking, 1241x376, 5 levels, 1 hypothesis per frame
             "against one dense reference keyframe (F independent frames in flight, like the one-frame-per-core reference arm)")
 
 
+IMAGES = "8-bit grayscale (integer valued: no photometric calibration, the reference's mode=1), 1241x376"
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -109,12 +112,16 @@ class ClockSampler:
 def make_workload(seed=synth.DEFAULT_SEED, n_frames=N_FRAMES):
     sc = synth.make_scene(W, H, seed=seed)
     rng = np.random.default_rng(seed)
-    ref = synth.render_ref(sc)
+    # 8-bit grayscale, as a camera (and KITTI) delivers it: with no photometric calibration (the reference's mode = 1)
+    # ImageAndExposure::image holds exactly these integer values as floats. Both arms get the same values; the B200 arm
+    # uploads them as uint8 (nalo_*_u8: exact, a quarter of the PCIe traffic), the CPU arm reads them as float.
+    q8 = lambda im: np.clip(np.rint(im), 0, 255).astype(np.float32)
+    ref = q8(synth.render_ref(sc))
     news, gts, xis = [], [], []
     for _ in range(n_frames):
         xi, aff = synth.random_motion(rng)
         gt = synth.se3_exp(xi)
-        news.append(synth.render_new(sc, gt, aff))
+        news.append(q8(synth.render_new(sc, gt, aff)))
         gts.append(gt)
         xis.append(np.asarray(xi, dtype=np.float64))
     make_workload.xis = xis  # (tangent vectors of the ground-truth motions: the analytic camera history of the candidate bench)
@@ -181,7 +188,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "residuals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_frame"] * cores, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pc_n": r["pc_n"], "frames_timed": r["frames"], "frames_per_step_per_gpu": cores},
+        "config": {"workload": WORKLOAD, "pc_n": r["pc_n"], "frames_timed": r["frames"], "frames_per_step_per_gpu": cores, "images": IMAGES},
         "ms_per_frame": r["ms_per_frame"], "gn_iters_per_s": r["gn_iters_per_s"],
         "cpu_baseline": {"value": r["value"], "unit": "residuals/s", "cores": cores, "kind": "port",
                          "sample": f"{r['frames']} frames ({r['seconds']:.1f} s), one frame per core at a time, oracle -O3 -march=x86-64-v3"},
@@ -522,12 +529,16 @@ def run_b200(args, rank, world, local_rank):
     # inputs: device-resident copies (value arm) and pinned host copies (e2e arm)
     # (one buffer per frame of a step, so that no two frames of a step share an input image in L2 / in the host cache)
     NB = max(F, N_FRAMES)
-    dev_imgs = [torch.from_numpy(np.ascontiguousarray(news[i % N_FRAMES])).cuda() for i in range(NB)]
-    pin_imgs = []
+    news8 = [n_.astype(np.uint8) for n_ in news]  # exact: the workload's images are integer valued
+    dev_imgs = [torch.from_numpy(np.ascontiguousarray(news8[i % N_FRAMES])).cuda() for i in range(NB)]
+    pin_imgs, pin_imgs_f32 = [], []
     for i in range(NB):
-        a = capi.pinned_array((H, W), np.float32)
-        a[...] = news[i % N_FRAMES]
+        a = capi.pinned_array((H, W), np.uint8)
+        a[...] = news8[i % N_FRAMES]
         pin_imgs.append(a)
+        a = capi.pinned_array((H, W), np.float32)  # the same values as floats: the secondary `e2e.f32_images` figure
+        a[...] = news[i % N_FRAMES]
+        pin_imgs_f32.append(a)
     p0 = synth.pose_identity()
     K, Wu = args.steps, args.warmup
     slots = list(range(1, F + 1))
@@ -536,7 +547,7 @@ def run_b200(args, rank, world, local_rank):
     # One step = the per-frame hot path of FullSystem::addActiveFrame (makeImages + trackNewestCoarse) for F new frames
     # through ONE C-ABI call; frame f of step i is input buffer (i*F + f) mod NB.
     def step_dev(i):
-        return ctx.track_frames(0, slots, p0s, a0s, colors_dev_ptrs=[dev_imgs[(i * F + f) % NB].data_ptr() for f in range(F)])
+        return ctx.track_frames(0, slots, p0s, a0s, colors_dev_ptrs=[dev_imgs[(i * F + f) % NB].data_ptr() for f in range(F)], u8=True)
 
     def step_host(i):
         return ctx.track_frames(0, slots, p0s, a0s, colors_host=[pin_imgs[(i * F + f) % NB] for f in range(F)])
@@ -624,31 +635,37 @@ def run_b200(args, rank, world, local_rank):
         sync_res += r["stats"]["residuals"]
     slots2 = [slots, list(range(F + 1, 2 * F + 1))]
 
-    def submit_host(i):
-        ctx.flush_l2()  # stream-ordered between the tracking of step i-1 and the pyramids of step i (inside the timed region)
-        return ctx.track_frames_submit(0, slots2[i & 1], p0s, a0s, colors_host=[pin_imgs[(i * F + f) % NB] for f in range(F)])
+    def stream_e2e(imgs):
+        """K steps through nalo_track_frames_submit[_u8] / _wait with two submissions in flight; wall clock, max over ranks."""
+        def submit_host(i):
+            ctx.flush_l2()  # stream-ordered between the tracking of step i-1 and the pyramids of step i (inside the timed region)
+            return ctx.track_frames_submit(0, slots2[i & 1], p0s, a0s, colors_host=[imgs[(i * F + f) % NB] for f in range(F)])
 
-    for rep in range(2):  # rep 0: warm-up (allocates the second staging set)
-        ctx.sync()
-        if dist and rep == 1:
-            dist.barrier()
-        n_steps = K if rep == 1 else min(Wu, 3) + 1
-        e2e_res, prev = 0, None
-        t0 = time.perf_counter()
-        for i in range(n_steps):
-            t = submit_host(i)
-            if prev is not None:
-                e2e_res += ctx.track_frames_wait(prev)["stats"]["residuals"]
-            prev = t
-        e2e_res += ctx.track_frames_wait(prev)["stats"]["residuals"]
-        e2e_s = time.perf_counter() - t0
-    if dist:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-        t = torch.tensor([float(e2e_res)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        e2e_res = float(t.item())
+        for rep in range(2):  # rep 0: warm-up (allocates the second staging set)
+            ctx.sync()
+            if dist and rep == 1:
+                dist.barrier()
+            n_steps = K if rep == 1 else min(Wu, 3) + 1
+            res_, prev = 0, None
+            t0 = time.perf_counter()
+            for i in range(n_steps):
+                t = submit_host(i)
+                if prev is not None:
+                    res_ += ctx.track_frames_wait(prev)["stats"]["residuals"]
+                prev = t
+            res_ += ctx.track_frames_wait(prev)["stats"]["residuals"]
+            sec_ = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([sec_], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec_ = float(t.item())
+            t = torch.tensor([float(res_)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            res_ = float(t.item())
+        return res_, sec_
+
+    e2e_res, e2e_s = stream_e2e(pin_imgs)              # 8-bit images as delivered (the workload's format)
+    f32_res, f32_s = stream_e2e(pin_imgs_f32)          # the same values uploaded as floats (ImageAndExposure::image)
 
     # ---- latency of ONE frame (the north-star "< 1 ms per frame" figure): same hot path, one frame per call
     latency = None
@@ -658,7 +675,7 @@ def run_b200(args, rank, world, local_rank):
         nl = max(10, min(K, 50))
         for i in range(3 + nl):
             ctx.flush_l2()
-            ok_, _, _, _, _, st = ctx.track_frame(0, 1, p0, [0.0, 0.0], color_dev_ptr=dev_imgs[i % N_FRAMES].data_ptr())
+            ok_, _, _, _, _, st = ctx.track_frame(0, 1, p0, [0.0, 0.0], color_dev_ptr=dev_imgs[i % N_FRAMES].data_ptr(), u8=True)
             if i >= 3:
                 lat_step.append(st["step_ms"])
                 lat_kern.append(st["kernel_ms"])
@@ -667,7 +684,7 @@ def run_b200(args, rank, world, local_rank):
             ctx.flush_l2()
             ctx.sync()
             t0 = time.perf_counter()
-            ctx.track_frame(0, 1, p0, [0.0, 0.0], color_host=pin_imgs[i % N_FRAMES])
+            ctx.track_frame(0, 1, p0, [0.0, 0.0], color_host=pin_imgs[i % N_FRAMES])  # (uint8 pinned image)
             if i >= 3:
                 lat_wall.append(1e3 * (time.perf_counter() - t0))
         latency = {"workload": "one frame per call (nalo_track_frame), all 148 SMs on it", "ms_per_frame_device": float(np.mean(lat_step)),
@@ -729,12 +746,15 @@ def run_b200(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "pc_n": pc_n, "seeded_px": int(ws.sum()),
                        "l2": "flushed between steps (256 MiB memset, untimed); the F pyramids of a step (10 MB each) exceed L2 as well",
-                       "frames_per_step_per_gpu": F, "init_pose": "identity", "frames_ok": frames_ok, "frames_total": K * F},
+                       "frames_per_step_per_gpu": F, "init_pose": "identity", "frames_ok": frames_ok, "frames_total": K * F,
+                       "images": IMAGES},
             "ms_per_frame": total_ms / (K * F), "gn_iters_per_s": job_iters / (total_ms * 1e-3),
             "residuals_per_frame": tot_res / (K * F), "evals_per_frame": tot_evals / (K * F),
             "e2e": {"value": e2e_res / e2e_s, "unit": "residuals/s", "ms_per_frame": 1e3 * e2e_s / (K * F), "ms_per_step": 1e3 * e2e_s / K,
-                    "h2d_bytes_per_step": int(F * (W * H * 4) + F * 512), "d2h_bytes_per_step": int(F * 320),
-                    "mode": "nalo_track_frames_submit/_wait, two submissions of F frames in flight; wall clock over the K steps",
+                    "h2d_bytes_per_step": int(F * (W * H) + F * 512), "d2h_bytes_per_step": int(F * 320),
+                    "mode": "nalo_track_frames_submit_u8/_wait (8-bit host images), two submissions of F frames in flight; wall clock over the K steps",
+                    "f32_images": {"value": f32_res / f32_s, "ms_per_step": 1e3 * f32_s / K, "h2d_bytes_per_step": int(F * (W * H * 4) + F * 512),
+                                   "mode": "the same images uploaded as float32 through nalo_track_frames_submit (round 1's e2e form)"},
                     "sync_call": {"value": sync_res / sync_s, "ms_per_step": 1e3 * sync_s / K,
                                   "mode": "nalo_track_frames, one blocking call per step, per-call wall time summed"}},
             "latency": latency,

@@ -111,6 +111,12 @@ int nalo_make_images_async(nalo_ctx* ctx, int slot, const float* color_host, con
                            int levels_host);
 int nalo_frame_host_wait(nalo_ctx* ctx, int slot);
 int nalo_get_frame(nalo_ctx* ctx, int slot, float* dIp_host, float* absgrad_host);
+/* 8-bit input: the camera's own samples (MinimalImageB, util/MinimalImage.h:36-99) for set-ups in which ImageAndExposure::image
+ * is integer valued anyway - no photometric calibration, i.e. the reference's mode = 1 (main_dso_pangolin.cpp:429-435: "no
+ * photometric calibration"; Undistort then passes the pixel values through, Undistort.cpp photometricUndist == 0). uint8 -> float
+ * is exact, so every output is bit-identical to nalo_make_images on the same values; the upload is a quarter of the size.
+ * The _u8 forms of the frame calls below take 8-bit images in the same way. */
+int nalo_make_images_u8(nalo_ctx* ctx, int slot, const uint8_t* color_host, const float* B256, float* dIp_host, float* absgrad_host);
 
 /* ---- a2-a4: PixelSelector (FullSystem/PixelSelector2.cpp) ---------------------------------------------- */
 /* makeMaps (:144-291). currentPotential is PixelSelector::currentPotential (state carried frame to frame,
@@ -160,6 +166,10 @@ int nalo_track_frame(nalo_ctx* ctx, int trk, int new_slot, const float* color_ho
                      float exposure_new, double pose7_inout[7], double aff2_inout[2], int coarsestLvl, const double minResForAbort5[5],
                      double lastRes5[5], double flow3[3], int* ok, NaloTrackStats* stats /* nullable */);
 
+int nalo_track_frame_u8(nalo_ctx* ctx, int trk, int new_slot, const uint8_t* color_host, const uint8_t* color_dev, const float* B256,
+                        float exposure_new, double pose7_inout[7], double aff2_inout[2], int coarsestLvl, const double minResForAbort5[5],
+                        double lastRes5[5], double flow3[3], int* ok, NaloTrackStats* stats /* nullable */);
+
 /* n NEW frames (n <= NALO_MAX_HYPOTHESES) tracked against the same reference in one submission: per frame makeImages into
  * new_slots[i] (from colors_host[i], or colors_dev[i] when colors_dev is given), then ONE tracking launch for all of
  * them. Per-frame results as nalo_track_frame (no abort thresholds). Throughput form of the per-frame hot path: a camera
@@ -177,6 +187,12 @@ int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const
 int nalo_track_frames_submit(nalo_ctx* ctx, int trk, int n, const int* new_slots, const float* const* colors_host,
                              const float* const* colors_dev, const float* B256, float exposure_new, const double* poses7,
                              const double* affs2, int coarsestLvl, unsigned* ticket_out);
+int nalo_track_frames_u8(nalo_ctx* ctx, int trk, int n, const int* new_slots, const uint8_t* const* colors_host, const uint8_t* const* colors_dev,
+                         const float* B256, float exposure_new, double* poses7_inout, double* affs2_inout, int coarsestLvl, int* ok_out,
+                         double* lastRes5_out, NaloTrackStats* stats /* nullable */);
+int nalo_track_frames_submit_u8(nalo_ctx* ctx, int trk, int n, const int* new_slots, const uint8_t* const* colors_host,
+                                const uint8_t* const* colors_dev, const float* B256, float exposure_new, const double* poses7,
+                                const double* affs2, int coarsestLvl, unsigned* ticket_out);
 int nalo_track_frames_wait(nalo_ctx* ctx, unsigned ticket, double* poses7_out, double* affs2_out, int* ok_out, double* lastRes5_out,
                            NaloTrackStats* stats /* nullable; no timings */);
 

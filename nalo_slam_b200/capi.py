@@ -237,15 +237,18 @@ class Context:
 
     # ---- a1
     def make_images(self, slot, color, B256=None, want_host=False):
-        color = np.ascontiguousarray(color, dtype=_f32).reshape(-1)
+        """nalo_make_images, or nalo_make_images_u8 when `color` is a uint8 array (8-bit camera samples)."""
+        u8 = getattr(color, "dtype", None) == np.uint8
+        color = np.ascontiguousarray(color, dtype=np.uint8 if u8 else _f32).reshape(-1)
         assert color.size == self.w * self.h
+        fn = self.L.nalo_make_images_u8 if u8 else self.L.nalo_make_images
         B = None if B256 is None else np.ascontiguousarray(B256, dtype=_f32)
         if want_host:
             dIp = np.zeros((self.tot, 3), dtype=_f32)
             ag = np.zeros(self.tot, dtype=_f32)
-            self._ck(self.L.nalo_make_images(self.h_, C.c_int(slot), _ptr(color), _ptr(B), _ptr(dIp), _ptr(ag)))
+            self._ck(fn(self.h_, C.c_int(slot), _ptr(color), _ptr(B), _ptr(dIp), _ptr(ag)))
             return dIp, ag
-        self._ck(self.L.nalo_make_images(self.h_, C.c_int(slot), _ptr(color), _ptr(B), None, None))
+        self._ck(fn(self.h_, C.c_int(slot), _ptr(color), _ptr(B), None, None))
         return None
 
     def make_images_async(self, slot, color, dIp_pinned, ag_pinned, levels_host=None, B256=None):
@@ -364,7 +367,7 @@ class Context:
         self._ck(self.L.nalo_track(self.h_, C.c_int(trk), C.c_int(new_slot), C.c_float(exposure), _ptr(pose), _ptr(aff), C.c_int(coarsestLvl), _ptr(mr), _ptr(lr), _ptr(fl), C.byref(ok), C.byref(st)))
         return bool(ok.value), pose, aff, lr, fl, st.as_dict()
 
-    def track_frame(self, trk, new_slot, pose7, aff2, color_host=None, color_dev_ptr=None, coarsestLvl=None, minRes=None, exposure=1.0, B256=None):
+    def track_frame(self, trk, new_slot, pose7, aff2, color_host=None, color_dev_ptr=None, coarsestLvl=None, minRes=None, exposure=1.0, B256=None, u8=False):
         """nalo_track_frame: makeImages + trackNewestCoarse in one call (color_host: pinned/pageable float32 image, or a device pointer)."""
         pose = np.array(pose7, dtype=np.float64)
         aff = np.array(aff2, dtype=np.float64)
@@ -375,14 +378,17 @@ class Context:
         fl = np.zeros(3)
         ok = C.c_int(0)
         st = NaloTrackStats()
-        ch = None if color_host is None else np.ascontiguousarray(color_host, dtype=_f32).reshape(-1)
+        u8 = u8 or getattr(color_host, "dtype", None) == np.uint8
+        ch = None if color_host is None else np.ascontiguousarray(color_host, dtype=np.uint8 if u8 else _f32).reshape(-1)
         B = None if B256 is None else np.ascontiguousarray(B256, dtype=_f32)
-        self._ck(self.L.nalo_track_frame(self.h_, C.c_int(trk), C.c_int(new_slot), _ptr(ch), _P(color_dev_ptr) if color_dev_ptr else None, _ptr(B),
+        fn = self.L.nalo_track_frame_u8 if u8 else self.L.nalo_track_frame
+        self._ck(fn(self.h_, C.c_int(trk), C.c_int(new_slot), _ptr(ch), _P(color_dev_ptr) if color_dev_ptr else None, _ptr(B),
                                          C.c_float(exposure), _ptr(pose), _ptr(aff), C.c_int(coarsestLvl), _ptr(mr), _ptr(lr), _ptr(fl), C.byref(ok), C.byref(st)))
         return bool(ok.value), pose, aff, lr, fl, st.as_dict()
 
-    def track_frames(self, trk, slots, poses7, affs2, colors_host=None, colors_dev_ptrs=None, coarsestLvl=None, exposure=1.0):
-        """nalo_track_frames: n new frames (host images or device pointers) against the same reference, one tracking launch."""
+    def track_frames(self, trk, slots, poses7, affs2, colors_host=None, colors_dev_ptrs=None, coarsestLvl=None, exposure=1.0, u8=False):
+        """nalo_track_frames: n new frames (host images or device pointers) against the same reference, one tracking launch.
+        uint8 host images (or u8=True with device pointers to 8-bit images) go through nalo_track_frames_u8."""
         n = len(slots)
         poses = np.ascontiguousarray(poses7, dtype=np.float64).reshape(n, 7).copy()
         affs = np.ascontiguousarray(affs2, dtype=np.float64).reshape(n, 2).copy()
@@ -396,13 +402,15 @@ class Context:
         if colors_dev_ptrs is not None:
             dp = (C.c_void_p * n)(*[int(p) for p in colors_dev_ptrs])
         else:
-            keep = [np.ascontiguousarray(c, dtype=_f32).reshape(-1) for c in colors_host]
+            u8 = u8 or getattr(colors_host[0], "dtype", None) == np.uint8
+            keep = [np.ascontiguousarray(c, dtype=np.uint8 if u8 else _f32).reshape(-1) for c in colors_host]
             hp = (C.c_void_p * n)(*[k.ctypes.data for k in keep])
-        self._ck(self.L.nalo_track_frames(self.h_, C.c_int(trk), C.c_int(n), _ptr(sl), hp, dp, None, C.c_float(exposure), _ptr(poses), _ptr(affs),
+        fn = self.L.nalo_track_frames_u8 if u8 else self.L.nalo_track_frames
+        self._ck(fn(self.h_, C.c_int(trk), C.c_int(n), _ptr(sl), hp, dp, None, C.c_float(exposure), _ptr(poses), _ptr(affs),
                                           C.c_int(coarsestLvl), _ptr(ok), _ptr(lr), C.byref(st)))
         return dict(ok=ok, poses=poses, affs=affs, lastRes=lr, stats=st.as_dict())
 
-    def track_frames_submit(self, trk, slots, poses7, affs2, colors_host=None, colors_dev_ptrs=None, coarsestLvl=None, exposure=1.0):
+    def track_frames_submit(self, trk, slots, poses7, affs2, colors_host=None, colors_dev_ptrs=None, coarsestLvl=None, exposure=1.0, u8=False):
         """nalo_track_frames_submit: enqueue one submission and return its ticket (two may be in flight). The host images
         are kept referenced until track_frames_wait returns."""
         n = len(slots)
@@ -415,10 +423,12 @@ class Context:
         if colors_dev_ptrs is not None:
             dp = (C.c_void_p * n)(*[int(p) for p in colors_dev_ptrs])
         else:
-            keep = [np.ascontiguousarray(c, dtype=_f32).reshape(-1) for c in colors_host]
+            u8 = u8 or getattr(colors_host[0], "dtype", None) == np.uint8
+            keep = [np.ascontiguousarray(c, dtype=np.uint8 if u8 else _f32).reshape(-1) for c in colors_host]
             hp = (C.c_void_p * n)(*[k.ctypes.data for k in keep])
         ticket = C.c_uint(0)
-        self._ck(self.L.nalo_track_frames_submit(self.h_, C.c_int(trk), C.c_int(n), _ptr(sl), hp, dp, None, C.c_float(exposure), _ptr(poses),
+        fn = self.L.nalo_track_frames_submit_u8 if u8 else self.L.nalo_track_frames_submit
+        self._ck(fn(self.h_, C.c_int(trk), C.c_int(n), _ptr(sl), hp, dp, None, C.c_float(exposure), _ptr(poses),
                                                  _ptr(affs), C.c_int(coarsestLvl), C.byref(ticket)))
         if not hasattr(self, "_frames_keep"):
             self._frames_keep = {}

@@ -199,9 +199,11 @@ int nalo_fail(nalo_ctx* ctx, int code, const char* fmt, ...);
   } while (0)
 
 // internal cross-file entry points
-int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float* B256_host, float* exportStage = nullptr, int exportLevels = 0);
+int nalo_images_run(nalo_ctx* ctx, int slot, const void* color_dev, const float* B256_host, float* exportStage = nullptr, int exportLevels = 0,
+                    bool u8 = false);  // u8: color_dev holds 8-bit samples instead of floats
 int nalo_images_to_host(nalo_ctx* ctx, int slot, float* dIp_host, float* absgrad_host);
-int nalo_images_run_multi(nalo_ctx* ctx, int n, const int* slots, const float* const* colors_dev, const float* B256_host, cudaStream_t stream);
+int nalo_images_run_multi(nalo_ctx* ctx, int n, const int* slots, const void* const* colors_dev, const float* B256_host, cudaStream_t stream,
+                          bool u8 = false);
 int nalo_depth_finish(nalo_ctx* ctx, int trk, int ref_slot);
 int nalo_track_init(nalo_ctx* ctx);
 void nalo_track_free(nalo_ctx* ctx);

@@ -126,10 +126,15 @@ __global__ void __launch_bounds__(256) grad_kernel(const float* __restrict__ col
 // 9.9 MB of output is written once; there is no planar intermediate and no second launch.
 // The flat-index wrap at the image's left/right border (idx-1 of x = 0 is the last pixel of the previous row) is
 // served by recomputing that one level-l value from level 0 in global memory (value_at<l>).
-template <int LVL>
-__device__ __forceinline__ float value_at(const float* __restrict__ color, int w0, int x, int y) {
+// Input pixels are float (ImageAndExposure::image, util/ImageAndExposure.h:34-74) or - for images that are integer valued
+// anyway, i.e. no photometric calibration (mode = 1) - the camera's own 8-bit samples (MinimalImageB, util/MinimalImage.h):
+// uint8 -> float is exact, so both give bit-identical pyramids, and the 8-bit form is a quarter of the PCIe traffic.
+__device__ __forceinline__ float ld_pix(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_pix(const unsigned char* p) { return (float)__ldg(p); }
+template <int LVL, class PixT>
+__device__ __forceinline__ float value_at(const PixT* __restrict__ color, int w0, int x, int y) {
   if constexpr (LVL == 0) {
-    return __ldg(color + (size_t)y * w0 + x);
+    return ld_pix(color + (size_t)y * w0 + x);
   } else {
     return box4(value_at<LVL - 1>(color, w0, 2 * x, 2 * y), value_at<LVL - 1>(color, w0, 2 * x + 1, 2 * y),
                 value_at<LVL - 1>(color, w0, 2 * x, 2 * y + 1), value_at<LVL - 1>(color, w0, 2 * x + 1, 2 * y + 1));
@@ -140,8 +145,8 @@ constexpr int FT_W = 64, FT_H = 32, FT_M = 16;             // tile and margin at
 constexpr int FR_W = FT_W + 2 * FT_M, FR_H = FT_H + 2 * FT_M;  // staged region 96 x 64
 
 // gradient + store of one pixel of level LVL: (lx, ly) inside the tile, S = staged level with margin m and pitch rw
-template <int LVL>
-__device__ __forceinline__ void fused_grad_store(const float* __restrict__ S, int lx, int ly, int tx0, int ty0, const float* __restrict__ color,
+template <int LVL, class PixT>
+__device__ __forceinline__ void fused_grad_store(const float* __restrict__ S, int lx, int ly, int tx0, int ty0, const PixT* __restrict__ color,
                                                  const float* __restrict__ B, int useB, float4* __restrict__ pix, const PyrLevels& L,
                                                  float* __restrict__ exportStage, int exportLevels) {
   constexpr int m = FT_M >> LVL, rw = FR_W >> LVL;
@@ -182,12 +187,13 @@ __device__ __forceinline__ void fused_grad_store(const float* __restrict__ S, in
 
 // frameTable != nullptr: blockIdx.z selects a frame; frameTable[2z] = its input image, frameTable[2z+1] = its float4 pyramid
 // (many frames in ONE launch: nalo_track_frames).
-__global__ void __launch_bounds__(512, 3) make_images_fused_kernel(const float* __restrict__ color, const float* __restrict__ B, int useB,
+template <class PixT>
+__global__ void __launch_bounds__(512, 3) make_images_fused_kernel(const PixT* __restrict__ color, const float* __restrict__ B, int useB,
                                                                 float4* __restrict__ pix, const __grid_constant__ PyrLevels L,
                                                                 float* __restrict__ exportStage, int exportLevels,
                                                                 const void* const* __restrict__ frameTable) {
   if (frameTable != nullptr) {
-    color = static_cast<const float*>(frameTable[2 * blockIdx.z]);
+    color = static_cast<const PixT*>(frameTable[2 * blockIdx.z]);
     pix = static_cast<float4*>(const_cast<void*>(frameTable[2 * blockIdx.z + 1]));
   }
   __shared__ float s0[FR_H * FR_W];
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(512, 3) make_images_fused_kernel(const float* 
 #pragma unroll
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-      for (int q = 0; q < 3; q++) v[3 * r + q] = (xok[q] && yok[r]) ? __ldg(color + (unsigned)(off0 + 16 * r * w0 + 32 * q)) : 0.f;
+      for (int q = 0; q < 3; q++) v[3 * r + q] = (xok[q] && yok[r]) ? ld_pix(color + (unsigned)(off0 + 16 * r * w0 + 32 * q)) : 0.f;
     }
 #pragma unroll
     for (int r = 0; r < 4; r++)
@@ -285,6 +291,11 @@ __global__ void __launch_bounds__(256) export_kernel(const float4* __restrict__ 
   stage[3 * (size_t)L.total + g] = p.w;
 }
 
+__global__ void u8_to_float_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)__ldg(src + i);
+}
+
 PyrLevels make_levels(const nalo_ctx* ctx) {
   PyrLevels L;
   L.levels = ctx->levels;
@@ -307,9 +318,18 @@ PyrLevels make_levels(const nalo_ctx* ctx) {
 }  // namespace
 
 // color_dev: w0*h0 floats on the device. Planar scratch lives in ctx->d_stage (>= sum_{l>=1} w_l h_l floats).
-int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float* B256_host, float* exportStage, int exportLevels) {
+int nalo_images_run(nalo_ctx* ctx, int slot, const void* color_dev_any, const float* B256_host, float* exportStage, int exportLevels, bool u8) {
   if (slot < 0 || slot >= ctx->maxFrames) return nalo_fail(ctx, NALO_E_ARG, "frame slot %d out of range", slot);
   NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const float* color_dev = static_cast<const float*>(color_dev_any);
+  if (u8 && ctx->levels > 5) {  // the two-kernel path of 6-level pyramids reads float: convert first (scratch: the frame's own level-0 plane is not free yet)
+    const int n0 = ctx->w0 * ctx->h0;
+    float* tmp = ctx->d_stage + 3 * (size_t)ctx->totPixDense;  // last quarter of the host-layout staging buffer (>= w0*h0 floats), unused by this path
+    u8_to_float_kernel<<<(n0 + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const unsigned char*>(color_dev_any), tmp, n0);
+    NALO_CHECK_LAUNCH(ctx);
+    color_dev = tmp;
+    u8 = false;
+  }
   PyrLevels L = make_levels(ctx);
   if (ctx->frames[slot].hostPending) {  // an asynchronous export still reads this slot: order the overwrite after it
     NALO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->frames[slot].hostReady, 0));
@@ -322,7 +342,11 @@ int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float
   }
   if (ctx->levels <= 5) {
     dim3 fgrid((ctx->w0 + FT_W - 1) / FT_W, (ctx->h0 + FT_H - 1) / FT_H);
-    make_images_fused_kernel<<<fgrid, 512, 0, ctx->stream>>>(color_dev, ctx->d_B, useB, ctx->frames[slot].pix, L, exportStage, exportLevels, nullptr);
+    if (u8)
+      make_images_fused_kernel<unsigned char><<<fgrid, 512, 0, ctx->stream>>>(static_cast<const unsigned char*>(color_dev_any), ctx->d_B, useB,
+                                                                              ctx->frames[slot].pix, L, exportStage, exportLevels, nullptr);
+    else
+      make_images_fused_kernel<float><<<fgrid, 512, 0, ctx->stream>>>(color_dev, ctx->d_B, useB, ctx->frames[slot].pix, L, exportStage, exportLevels, nullptr);
     NALO_CHECK_LAUNCH(ctx);
     NALO_CUDA(ctx, cudaEventRecord(ctx->frames[slot].built, ctx->stream));
     ctx->frames[slot].valid = true;
@@ -356,11 +380,11 @@ int nalo_images_run(nalo_ctx* ctx, int slot, const float* color_dev, const float
 
 // Pyramids of n frames in ONE launch (levels <= 5): colors_dev[i] -> frame slot slots[i]. `stream` lets the caller place
 // the launch (nalo_track_frames pipelines uploads against tracking); the pointer table is staged in pinned memory.
-int nalo_images_run_multi(nalo_ctx* ctx, int n, const int* slots, const float* const* colors_dev, const float* B256_host, cudaStream_t stream) {
+int nalo_images_run_multi(nalo_ctx* ctx, int n, const int* slots, const void* const* colors_dev, const float* B256_host, cudaStream_t stream, bool u8) {
   if (n < 1 || n > NALO_MAX_HYPOTHESES) return nalo_fail(ctx, NALO_E_ARG, "nalo_images_run_multi: n = %d", n);
   if (ctx->levels > 5) {  // 6-level pyramids: frame by frame on the two-kernel path
     for (int i = 0; i < n; i++) {
-      int rc = nalo_images_run(ctx, slots[i], colors_dev[i], B256_host, nullptr, 0);
+      int rc = nalo_images_run(ctx, slots[i], colors_dev[i], B256_host, nullptr, 0, u8);
       if (rc != NALO_OK) return rc;
     }
     return NALO_OK;
@@ -393,7 +417,10 @@ int nalo_images_run_multi(nalo_ctx* ctx, int n, const int* slots, const float* c
   }
   NALO_CUDA(ctx, cudaMemcpyAsync(dt, ht, sizeof(void*) * 2 * n, cudaMemcpyHostToDevice, stream));
   dim3 fgrid((ctx->w0 + FT_W - 1) / FT_W, (ctx->h0 + FT_H - 1) / FT_H, n);
-  make_images_fused_kernel<<<fgrid, 512, 0, stream>>>(nullptr, ctx->d_B, useB, nullptr, L, nullptr, 0, reinterpret_cast<const void* const*>(dt));
+  if (u8)
+    make_images_fused_kernel<unsigned char><<<fgrid, 512, 0, stream>>>(nullptr, ctx->d_B, useB, nullptr, L, nullptr, 0, reinterpret_cast<const void* const*>(dt));
+  else
+    make_images_fused_kernel<float><<<fgrid, 512, 0, stream>>>(nullptr, ctx->d_B, useB, nullptr, L, nullptr, 0, reinterpret_cast<const void* const*>(dt));
   NALO_CHECK_LAUNCH(ctx);
   for (int i = 0; i < n; i++) {
     ctx->frames[slots[i]].valid = true;
@@ -467,6 +494,16 @@ int nalo_frame_host_wait(nalo_ctx* ctx, int slot) {
   if (!ctx->frames[slot].hostPending) return NALO_OK;
   NALO_CUDA(ctx, cudaEventSynchronize(ctx->frames[slot].hostReady));
   return NALO_OK;  // hostPending stays set until the slot is rebuilt: a later overwrite still orders itself after the event
+}
+
+int nalo_make_images_u8(nalo_ctx* ctx, int slot, const uint8_t* color_host, const float* B256, float* dIp_host, float* absgrad_host) {
+  if (!ctx || !color_host) return NALO_E_ARG;
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_color, color_host, (size_t)ctx->w0 * ctx->h0, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = nalo_images_run(ctx, slot, ctx->d_color, B256, nullptr, 0, true);
+  if (rc != NALO_OK) return rc;
+  if (dIp_host || absgrad_host) return nalo_images_to_host(ctx, slot, dIp_host, absgrad_host);
+  return NALO_OK;
 }
 
 int nalo_make_images_dev(nalo_ctx* ctx, int slot, const float* color_dev, const float* B256_host) {

@@ -364,9 +364,10 @@ static int frames_buf_alloc(nalo_ctx* ctx, nalo_ctx::FramesBuf& B) {
   return NALO_OK;
 }
 
-static int frames_enqueue(nalo_ctx* ctx, nalo_ctx::FramesBuf& B, int trk, int n, const int* new_slots, const float* const* colors_host,
-                          const float* const* colors_dev, const float* B256, float exposure_new, const double* poses7, const double* affs2,
-                          int coarsestLvl, bool timing) {
+// pixBytes: 4 = float images, 1 = 8-bit images (see nalo_images.cu: uint8 -> float is exact, a quarter of the PCIe traffic)
+static int frames_enqueue(nalo_ctx* ctx, nalo_ctx::FramesBuf& B, int trk, int n, const int* new_slots, const void* const* colors_host,
+                          const void* const* colors_dev, const float* B256, float exposure_new, const double* poses7, const double* affs2,
+                          int coarsestLvl, bool timing, int pixBytes = 4) {
   if (trk < 0 || trk >= NALO_MAX_TRACKERS || !new_slots || !poses7 || !affs2 || (!colors_host && !colors_dev)) return NALO_E_ARG;
   if (n < 1 || n > NALO_MAX_HYPOTHESES) return nalo_fail(ctx, NALO_E_ARG, "n %d out of [1,%d]", n, NALO_MAX_HYPOTHESES);
   if (coarsestLvl < 0 || coarsestLvl >= NALO_TRACK_LEVELS || coarsestLvl >= ctx->levels) return NALO_E_ARG;
@@ -409,13 +410,17 @@ static int frames_enqueue(nalo_ctx* ctx, nalo_ctx::FramesBuf& B, int trk, int n,
   // the frames' pyramids (10 MB each) exceed L2 from ~10 frames on: the evaluation then streams texels from HBM
   const bool streamed = (size_t)n * ctx->totPix * sizeof(float4) > ((size_t)96 << 20);
   const size_t n0 = (size_t)ctx->w0 * ctx->h0;
-  const float* srcs[NALO_MAX_HYPOTHESES];
+  const void* srcs[NALO_MAX_HYPOTHESES];
   // Host images: the submission is cut into parts of ~37 frames (4 CTAs per frame on 148 SMs); the upload of part p+1
   // (copy stream; a second DMA queue was measured slower) overlaps pyramids + tracking of part p. At 1241x376 the H2D copy of a frame (1.87 MB, ~40 us) costs
   // more than tracking it (~30-40 us), so the call is PCIe-bound and finer parts only shorten the un-overlapped head/tail.
   constexpr int kMaxParts = nalo_ctx::kMaxUploadParts;
   static const char* envP = getenv("NALO_FRAMES_PART");  // measurement switch: frames per part
-  const int partTarget = (envP && atoi(envP) > 0) ? atoi(envP) : 37;
+  // 8-bit images: the whole submission's upload (69 MB for 148 frames, 1.4 ms) is shorter than one tracking launch and a
+  // launch of all frames (one CTA per frame) tracks faster than four launches of 37 (latency-bound 4-CTA groups: 4 x ~1.05 ms
+  // against 3.07 ms), so the submission is ONE part; with two submissions in flight its upload hides behind the previous
+  // submission's tracking (measured: 4.37 -> see profiles/r02_suite.md).
+  const int partTarget = (envP && atoi(envP) > 0) ? atoi(envP) : (pixBytes == 1 ? NALO_MAX_HYPOTHESES : 37);
   int nParts = 1;
   if (!colors_dev && n >= 8) nParts = std::min(kMaxParts, std::max(1, (n + partTarget / 2) / partTarget));
   if (nParts > n) nParts = n;
@@ -428,8 +433,9 @@ static int frames_enqueue(nalo_ctx* ctx, nalo_ctx::FramesBuf& B, int trk, int n,
     for (int part = 0; part < nParts; part++) {
       const int lo = partLo(part), hi = partLo(part + 1);
       for (int i = lo; i < hi; i++) {
-        NALO_CUDA(ctx, cudaMemcpyAsync(B.d_color + n0 * i, colors_host[i], sizeof(float) * n0, cudaMemcpyHostToDevice, ctx->copyStream));
-        srcs[i] = B.d_color + n0 * i;
+        unsigned char* dst = reinterpret_cast<unsigned char*>(B.d_color) + (size_t)pixBytes * n0 * i;
+        NALO_CUDA(ctx, cudaMemcpyAsync(dst, colors_host[i], (size_t)pixBytes * n0, cudaMemcpyHostToDevice, ctx->copyStream));
+        srcs[i] = dst;
       }
       NALO_CUDA(ctx, cudaEventRecord(B.evUpload[part], ctx->copyStream));
     }
@@ -439,7 +445,7 @@ static int frames_enqueue(nalo_ctx* ctx, nalo_ctx::FramesBuf& B, int trk, int n,
   for (int part = 0; part < nParts; part++) {
     const int lo = partLo(part), cnt = partLo(part + 1) - lo;
     if (!colors_dev) NALO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, B.evUpload[part], 0));
-    rc = nalo_images_run_multi(ctx, cnt, new_slots + lo, srcs + lo, B256, ctx->stream);
+    rc = nalo_images_run_multi(ctx, cnt, new_slots + lo, srcs + lo, B256, ctx->stream, pixBytes == 1);
     if (rc != NALO_OK) return rc;
     if (timing && part == 0) NALO_CUDA(ctx, cudaEventRecord(ctx->evA, ctx->stream));
     int G = ctx->maxGroups / cnt;
@@ -489,22 +495,54 @@ static int frames_collect(nalo_ctx* ctx, nalo_ctx::FramesBuf& B, double* poses7,
 
 extern "C" {
 
-int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const float* const* colors_host, const float* const* colors_dev,
-                      const float* B256, float exposure_new, double* poses7, double* affs2, int coarsestLvl, int* ok_out, double* lastRes5_out,
-                      NaloTrackStats* stats) {
+static int track_frames_sync(nalo_ctx* ctx, int trk, int n, const int* new_slots, const void* const* colors_host, const void* const* colors_dev,
+                             const float* B256, float exposure_new, double* poses7, double* affs2, int coarsestLvl, int* ok_out, double* lastRes5_out,
+                             NaloTrackStats* stats, int pixBytes) {
   if (!ctx) return NALO_E_ARG;
   if (ctx->fb[0].pending || ctx->fb[1].pending)
     return nalo_fail(ctx, NALO_E_STATE, "nalo_track_frames: a submission of nalo_track_frames_submit has not been waited for");
   nalo_ctx::FramesBuf& B = ctx->fb[0];
   int rc = frames_enqueue(ctx, B, trk, n, new_slots, colors_host, colors_dev, B256, exposure_new, poses7, affs2, coarsestLvl,
-                          stats && ctx->profiling);
+                          stats && ctx->profiling, pixBytes);
   if (rc != NALO_OK) { B.pending = false; return rc; }
   return frames_collect(ctx, B, poses7, affs2, ok_out, lastRes5_out, stats);
 }
 
+int nalo_track_frames(nalo_ctx* ctx, int trk, int n, const int* new_slots, const float* const* colors_host, const float* const* colors_dev,
+                      const float* B256, float exposure_new, double* poses7, double* affs2, int coarsestLvl, int* ok_out, double* lastRes5_out,
+                      NaloTrackStats* stats) {
+  return track_frames_sync(ctx, trk, n, new_slots, reinterpret_cast<const void* const*>(colors_host), reinterpret_cast<const void* const*>(colors_dev),
+                           B256, exposure_new, poses7, affs2, coarsestLvl, ok_out, lastRes5_out, stats, 4);
+}
+
+int nalo_track_frames_u8(nalo_ctx* ctx, int trk, int n, const int* new_slots, const uint8_t* const* colors_host, const uint8_t* const* colors_dev,
+                         const float* B256, float exposure_new, double* poses7, double* affs2, int coarsestLvl, int* ok_out, double* lastRes5_out,
+                         NaloTrackStats* stats) {
+  return track_frames_sync(ctx, trk, n, new_slots, reinterpret_cast<const void* const*>(colors_host), reinterpret_cast<const void* const*>(colors_dev),
+                           B256, exposure_new, poses7, affs2, coarsestLvl, ok_out, lastRes5_out, stats, 1);
+}
+
+static int track_frames_submit_impl(nalo_ctx* ctx, int trk, int n, const int* new_slots, const void* const* colors_host,
+                                    const void* const* colors_dev, const float* B256, float exposure_new, const double* poses7,
+                                    const double* affs2, int coarsestLvl, unsigned* ticket_out, int pixBytes);
+
 int nalo_track_frames_submit(nalo_ctx* ctx, int trk, int n, const int* new_slots, const float* const* colors_host,
                              const float* const* colors_dev, const float* B256, float exposure_new, const double* poses7,
                              const double* affs2, int coarsestLvl, unsigned* ticket_out) {
+  return track_frames_submit_impl(ctx, trk, n, new_slots, reinterpret_cast<const void* const*>(colors_host),
+                                  reinterpret_cast<const void* const*>(colors_dev), B256, exposure_new, poses7, affs2, coarsestLvl, ticket_out, 4);
+}
+
+int nalo_track_frames_submit_u8(nalo_ctx* ctx, int trk, int n, const int* new_slots, const uint8_t* const* colors_host,
+                                const uint8_t* const* colors_dev, const float* B256, float exposure_new, const double* poses7,
+                                const double* affs2, int coarsestLvl, unsigned* ticket_out) {
+  return track_frames_submit_impl(ctx, trk, n, new_slots, reinterpret_cast<const void* const*>(colors_host),
+                                  reinterpret_cast<const void* const*>(colors_dev), B256, exposure_new, poses7, affs2, coarsestLvl, ticket_out, 1);
+}
+
+static int track_frames_submit_impl(nalo_ctx* ctx, int trk, int n, const int* new_slots, const void* const* colors_host,
+                                    const void* const* colors_dev, const float* B256, float exposure_new, const double* poses7,
+                                    const double* affs2, int coarsestLvl, unsigned* ticket_out, int pixBytes) {
   if (!ctx || !ticket_out) return NALO_E_ARG;
   nalo_ctx::FramesBuf* B = !ctx->fb[0].pending ? &ctx->fb[0] : (!ctx->fb[1].pending ? &ctx->fb[1] : nullptr);
   if (!B) return nalo_fail(ctx, NALO_E_STATE, "nalo_track_frames_submit: two submissions are already in flight");
@@ -515,7 +553,7 @@ int nalo_track_frames_submit(nalo_ctx* ctx, int trk, int n, const int* new_slots
       for (int k = 0; k < O.n; k++)
         if (O.slots[k] == new_slots[i])
           return nalo_fail(ctx, NALO_E_ARG, "frame slot %d belongs to the submission still in flight", new_slots[i]);
-  int rc = frames_enqueue(ctx, *B, trk, n, new_slots, colors_host, colors_dev, B256, exposure_new, poses7, affs2, coarsestLvl, false);
+  int rc = frames_enqueue(ctx, *B, trk, n, new_slots, colors_host, colors_dev, B256, exposure_new, poses7, affs2, coarsestLvl, false, pixBytes);
   if (rc != NALO_OK) { B->pending = false; return rc; }
   B->ticket = ctx->framesTicketNext++;
   if (ctx->framesTicketNext == 0) ctx->framesTicketNext = 1;

@@ -103,3 +103,52 @@ def test_empty_reference(small_pair, gpu_ctx_small):
     z = np.zeros(0, dtype=np.float32)
     ctx.set_ref_sparse(0, 0, z, z, z, z)
     assert all(ctx.ref_count(0, l) == 0 for l in range(P["L"]))
+
+
+@pytest.mark.parametrize("which,L", [("small", 4), ("kitti", 5), ("small6", 6)])
+def test_u8_images_bit_identical_to_float(which, L, request, oracle):
+    """8-bit input (nalo_make_images_u8 and the _u8 frame calls): uint8 -> float is exact, so pyramids, tracking results
+    and everything downstream are bit-identical to the float entry on the same (integer) values - incl. the 6-level path."""
+    import torch
+
+    from nalo_slam_b200 import capi, synth
+
+    P = request.getfixturevalue("kitti_pair" if which == "kitti" else "small_pair")
+    w, h = P["w"], P["h"]
+    ref8 = np.clip(np.rint(P["ref"]), 0, 255).astype(np.uint8)
+    new8 = np.clip(np.rint(P["new"]), 0, 255).astype(np.uint8)
+    ctx = capi.Context(w, h, L, device=0, max_frames=8)
+    ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)
+    try:
+        a = ctx.make_images(0, ref8.astype(np.float32), want_host=True)
+        b = ctx.make_images(1, ref8, want_host=True)
+        assert np.array_equal(_bits(a[0]), _bits(b[0])) and np.array_equal(_bits(a[1]), _bits(b[1]))
+        o_d, o_ag = oracle.make_images(ref8.astype(np.float32), w, h, L)
+        assert np.array_equal(_bits(b[0]), _bits(o_d)) and np.array_equal(_bits(b[1]), _bits(o_ag))
+        if L > 5:
+            return
+        idw, ws = synth.dense_reference_maps(P["scene"], a[1][: w * h])
+        ctx.make_k(0, *P["scene"].K)
+        ctx.set_ref_dense(0, 0, idw, ws)
+        p0 = synth.pose_identity()
+        rf = ctx.track_frame(0, 2, p0, [0, 0], color_host=new8.astype(np.float32))
+        r8 = ctx.track_frame(0, 3, p0, [0, 0], color_host=new8)
+        assert rf[0] and r8[0] and np.array_equal(rf[1], r8[1]) and np.array_equal(rf[2], r8[2]) and np.array_equal(rf[3], r8[3], equal_nan=True)
+        dev8 = torch.from_numpy(new8.copy()).cuda()
+        rd = ctx.track_frame(0, 3, p0, [0, 0], color_dev_ptr=dev8.data_ptr(), u8=True)
+        assert np.array_equal(rd[1], rf[1])
+        n = 5
+        pins = []
+        for i in range(n):
+            pa = capi.pinned_array((h, w), np.uint8)
+            pa[...] = new8
+            pins.append(pa)
+        slots = list(range(2, 2 + n))
+        out = ctx.track_frames(0, slots, np.tile(p0, (n, 1)), np.zeros((n, 2)), colors_host=pins)
+        outf = ctx.track_frames(0, slots, np.tile(p0, (n, 1)), np.zeros((n, 2)), colors_host=[new8.astype(np.float32)] * n)
+        assert np.array_equal(out["poses"], outf["poses"]) and np.array_equal(out["lastRes"], outf["lastRes"], equal_nan=True)
+        t = ctx.track_frames_submit(0, slots, np.tile(p0, (n, 1)), np.zeros((n, 2)), colors_host=pins)
+        o2 = ctx.track_frames_wait(t)
+        assert np.array_equal(o2["poses"][:n], out["poses"])
+    finally:
+        ctx.close()
