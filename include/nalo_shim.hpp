@@ -193,7 +193,10 @@ struct TrackNewCoarseResult {
   bool haveOneGood = false;
 };
 
-// FullSystem::trackNewCoarse: candidate list + all candidates in one launch + sequential winner rule replayed.
+// FullSystem::trackNewCoarse (FullSystem.cpp:502-699): candidate list (:516-580), then the loop :583-668 through
+// nalo_track_candidates - try 0 alone on all SMs; if the winner rule does not break after it, the remaining tries in ONE
+// launch with the abort thresholds held after try 0 (never lower than the sequential loop's own), rule replayed on the pass
+// logs. Same winner / achievedRes / lastCoarseRMSE / tryIterations as the reference's loop.
 inline TrackNewCoarseResult trackNewCoarse(CoarseTracker& tracker, FrameHessian* fh, const SE3& sprelast_c2w, const SE3& slast_c2w,
                                            const SE3& lastF_c2w, bool posesValid, const AffLight& aff_last, Vec5& lastCoarseRMSE,
                                            float reTrackThreshold = 1.5f) {
@@ -201,20 +204,15 @@ inline TrackNewCoarseResult trackNewCoarse(CoarseTracker& tracker, FrameHessian*
   int n = 0;
   if (nalo_motion_candidates(sprelast_c2w.data, slast_c2w.data, lastF_c2w.data, posesValid ? 1 : 0, tries, &n) != NALO_OK)
     throw std::runtime_error("nalo_motion_candidates");
-  std::vector<double> poses(tries, tries + 7 * n), affs(2 * n), lastRes(5 * n), flow(3 * n), passRes(6 * n);
-  std::vector<int> ok(n), passLvl(6 * n);
-  for (int i = 0; i < n; i++) { affs[2 * i] = aff_last.a; affs[2 * i + 1] = aff_last.b; }
   nalo_ctx* c = tracker.ctx.get();
-  check(c, nalo_track_multi(c, tracker.trk, fh->slot, fh->ab_exposure, n, poses.data(), affs.data(), tracker.ctx.levels() - 1, ok.data(), lastRes.data(),
-                            flow.data(), passLvl.data(), passRes.data(), &tracker.lastStats),
-        "nalo_track_multi");
   TrackNewCoarseResult r;
   const double affl[2] = {aff_last.a, aff_last.b};
   double aff_out[2];
   int used = 0, good = 0;
-  if (nalo_winner_rule(n, poses.data(), affs.data(), ok.data(), flow.data(), passLvl.data(), passRes.data(), affl, tries, lastCoarseRMSE.data(),
-                       reTrackThreshold, r.lastF_2_fh.data, aff_out, r.flowVecs.data(), r.achievedRes.data(), &used, &good) != NALO_OK)
-    throw std::runtime_error("nalo_winner_rule");
+  check(c, nalo_track_candidates(c, tracker.trk, fh->slot, fh->ab_exposure, n, tries, affl, tracker.ctx.levels() - 1, lastCoarseRMSE.data(),
+                                 reTrackThreshold, r.lastF_2_fh.data, aff_out, r.flowVecs.data(), r.achievedRes.data(), &used, &good,
+                                 &tracker.lastStats),
+        "nalo_track_candidates");
   r.aff_g2l.a = aff_out[0];
   r.aff_g2l.b = aff_out[1];
   r.tryIterations = used;

@@ -48,6 +48,16 @@ int main(int argc, char** argv) {
     std::vector<float> map(n);
     const int nsel = sel.makeMaps(&refFH, map.data(), 1500.f);
     printf("\nsel %d %d\n", nsel, sel.currentPotential);
+    // FullSystem::trackNewCoarse through the shim: a stationary history (the prediction is the identity), no early break
+    nalo::SE3 ident;
+    nalo::Vec5 rmse;
+    rmse.fill(0.0);
+    const nalo::TrackNewCoarseResult r = nalo::trackNewCoarse(tracker, &newFH, ident, ident, ident, true, nalo::AffLight(), rmse);
+    printf("tnc %d %d", r.tryIterations, r.haveOneGood ? 1 : 0);
+    for (int i = 0; i < 7; i++) printf(" %.17g", r.lastF_2_fh.data[i]);
+    printf("\ntncres");
+    for (int i = 0; i < 5; i++) printf(" %.9g", rmse[i]);
+    printf("\n");
   } catch (const std::exception& e) {
     fprintf(stderr, "shim_smoke failed: %s\n", e.what());
     return 1;

@@ -44,3 +44,11 @@ def test_cpp_shim_smoke(small_pair, gpu_ctx_small, oracle, tmp_path):
     off = np.cumsum([0] + [(P["w"] >> l) * (P["h"] >> l) for l in range(P["L"])])[:-1].tolist()
     n_o, _ = S.make_maps(P["dref"], P["agref"], off, 1500)
     assert [int(x) for x in kv["sel"]] == [n_o, S.currentPotential]
+    # FullSystem::trackNewCoarse through the shim (nalo_motion_candidates + nalo_track_candidates) == the oracle's sequential loop
+    ident = synth.pose_identity()
+    tries = oracle.motion_candidates(ident, ident, ident)
+    ref = T.track_new_coarse(tries, np.zeros(2), np.zeros(5))
+    assert [int(x) for x in kv["tnc"][:2]] == [ref["tries"], int(ref["good"])]
+    dt, dr = synth.pose_distance(np.array(kv["tnc"][2:], dtype=np.float64), ref["pose"])
+    assert dt < 1e-5 and dr < 1e-5
+    assert np.allclose(np.array(kv["tncres"], dtype=np.float64), ref["lastCoarseRMSE"], rtol=1e-3, equal_nan=True)
