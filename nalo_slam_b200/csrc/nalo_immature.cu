@@ -45,21 +45,30 @@ __constant__ int kPat[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 
 #define D_ __fdiv_rn
 
 // getInterpolatedElement31 (globalFuncs.h:126-140) on a float4 {I,dx,dy,ag} level
-__device__ __forceinline__ float interp31(const float4* __restrict__ img, float x, float y, int w) {
+// Texel base address of a bilinear lookup, clamped into the level: the reference reads wherever (int)x + (int)y*w points
+// (undefined outside the image; it can get there when the rotated pattern or a Gauss-Newton step leaves the 4-pixel margin
+// its range tests keep, or when a coordinate is not finite). Here such a lookup reads the nearest in-image texels instead
+// of unmapped memory; in-image lookups are unaffected.
+__device__ __forceinline__ int texel_base(int ix, int iy, int w, int h) {
+  const long long i = (long long)ix + (long long)iy * w;
+  const long long hi = (long long)w * h - w - 2;
+  return (int)(i < 0 ? 0 : (i > hi ? hi : i));
+}
+__device__ __forceinline__ float interp31(const float4* __restrict__ img, float x, float y, int w, int h) {
   const int ix = (int)x, iy = (int)y;
   const float dx = S_(x, (float)ix), dy = S_(y, (float)iy);
   const float dxdy = M_(dx, dy);
-  const float4* bp = img + (ix + iy * w);
+  const float4* bp = img + texel_base(ix, iy, w, h);
   const float q00 = __ldg(bp).x, q10 = __ldg(bp + 1).x, q01 = __ldg(bp + w).x, q11 = __ldg(bp + w + 1).x;
   return A_(A_(A_(M_(dxdy, q11), M_(S_(dy, dxdy), q01)), M_(S_(dx, dxdy), q10)), M_(A_(S_(S_(1.f, dx), dy), dxdy), q00));
 }
 // getInterpolatedElement33 (globalFuncs.h:75-89)
-__device__ __forceinline__ void interp33(const float4* __restrict__ img, float x, float y, int w, float& h0, float& h1, float& h2) {
+__device__ __forceinline__ void interp33(const float4* __restrict__ img, float x, float y, int w, int h, float& h0, float& h1, float& h2) {
   const int ix = (int)x, iy = (int)y;
   const float dx = S_(x, (float)ix), dy = S_(y, (float)iy);
   const float dxdy = M_(dx, dy);
   const float w11 = dxdy, w01 = S_(dy, dxdy), w10 = S_(dx, dxdy), w00 = A_(S_(S_(1.f, dx), dy), dxdy);
-  const float4* bp = img + (ix + iy * w);
+  const float4* bp = img + texel_base(ix, iy, w, h);
   const float4 p00 = __ldg(bp), p10 = __ldg(bp + 1), p01 = __ldg(bp + w), p11 = __ldg(bp + w + 1);
   h0 = A_(A_(A_(M_(w11, p11.x), M_(w01, p01.x)), M_(w10, p10.x)), M_(w00, p00.x));
   h1 = A_(A_(A_(M_(w11, p11.y), M_(w01, p01.y)), M_(w10, p10.y)), M_(w00, p00.y));
@@ -74,7 +83,7 @@ struct ImmSettings {
 
 struct ImmInitArgs {
   const float4* img;  // host frame, level 0
-  int w, n;
+  int w, h, n;
   const int* nDev;    // non-null: the number of points comes from the device (map-driven construction), n is the capacity
   const float *u, *v;
   float *color, *weights, *gradH, *energyTH, *idMin, *idMax, *quality, *uv, *interval;
@@ -94,7 +103,7 @@ __global__ void __launch_bounds__(MT) immature_init_kernel(const __grid_constant
     // getInterpolatedElement33BiLin (globalFuncs.h:166-188)
     const float x = A_(u, (float)kPat[idx][0]), y = A_(v, (float)kPat[idx][1]);
     const int ix = (int)x, iy = (int)y;
-    const float4* bp = a.img + (ix + iy * a.w);
+    const float4* bp = a.img + texel_base(ix, iy, a.w, a.h);
     const float tl = __ldg(bp).x, tr = __ldg(bp + 1).x, bl = __ldg(bp + a.w).x, br = __ldg(bp + a.w + 1).x;
     const float dx = S_(x, (float)ix), dy = S_(y, (float)iy);
     const float topInt = A_(M_(dx, tr), M_(S_(1.f, dx), tl));
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(TT) immature_trace_kernel(const __grid_constan
         if (numSteps >= 100) numSteps = 99;
         float* err = sErr[pl];
         for (int i = 0; i < numSteps; i++) {
-          const float hit = interp31(a.img, A_(ptx, rx), A_(pty, ry), w);
+          const float hit = interp31(a.img, A_(ptx, rx), A_(pty, ry), w, h);
           float term = 1e5f;
           if (isfinite(hit)) {
             const float residual = S_(hit, tcol);
@@ -345,7 +354,7 @@ __global__ void __launch_bounds__(TT) immature_trace_kernel(const __grid_constan
         if (S.GNIterations > 0) bestEnergy = 1e5f;
         for (int it = 0; it < S.GNIterations; it++) {
           float h0, h1, h2;
-          interp33(a.img, A_(bestU, rx), A_(bestV, ry), w, h0, h1, h2);
+          interp33(a.img, A_(bestU, rx), A_(bestV, ry), w, h, h0, h1, h2);
           const bool fin = isfinite(h0);
           const float residual = S_(h0, tcol);
           const float dRes = A_(M_(dx, h1), M_(dy, h2));
@@ -511,7 +520,7 @@ int nalo_immature_init(nalo_immature* im, int host_slot, int n, const float* u, 
   NALO_CUDA(ctx, cudaMemcpyAsync(im->d_v, v, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
   ImmInitArgs a;
   a.img = ctx->frames[host_slot].pix + ctx->loff[0];
-  a.w = ctx->w0; a.n = n; a.nDev = nullptr; a.u = im->d_u; a.v = im->d_v;
+  a.w = ctx->w0; a.h = ctx->h0; a.n = n; a.nDev = nullptr; a.u = im->d_u; a.v = im->d_v;
   a.color = im->d_color; a.weights = im->d_weights; a.gradH = im->d_gradH; a.energyTH = im->d_energyTH; a.idMin = im->d_idMin; a.idMax = im->d_idMax;
   a.quality = im->d_quality; a.uv = im->d_uv; a.interval = im->d_interval; a.status = im->d_status;
   a.S = make_settings(ctx, tp);
@@ -541,7 +550,7 @@ int nalo_immature_init_from_map(nalo_immature* im, int host_slot, const NaloTrac
   NALO_CHECK_LAUNCH(ctx);
   ImmInitArgs a;
   a.img = img;
-  a.w = w; a.n = im->maxPts; a.nDev = im->d_counts + 6; a.u = im->d_u; a.v = im->d_v;
+  a.w = w; a.h = h; a.n = im->maxPts; a.nDev = im->d_counts + 6; a.u = im->d_u; a.v = im->d_v;
   a.color = im->d_color; a.weights = im->d_weights; a.gradH = im->d_gradH; a.energyTH = im->d_energyTH; a.idMin = im->d_idMin; a.idMax = im->d_idMax;
   a.quality = im->d_quality; a.uv = im->d_uv; a.interval = im->d_interval; a.status = im->d_status;
   a.S = make_settings(ctx, tp);
