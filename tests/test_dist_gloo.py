@@ -64,6 +64,46 @@ def _worker(rank, world, port, tmpdir):
         assert np.allclose(got["pose"], ref_out["pose"], atol=1e-12)
         assert np.allclose(got["achievedRes"], ref_out["achievedRes"], equal_nan=True)
         np.save(os.path.join(tmpdir, f"rank{rank}.npy"), got["pose"])
+
+        # ---- the reference-loop form of bench.py's `sharded.candidates` (nalo_track_candidates across ranks): try 0 on every
+        # rank, then this rank's share of tries 1..n-1 handed the abort thresholds held after try 0 (device-side aborts: the
+        # pass log of an aborted try ends with level -2); gathered; the sequential rule replayed. Bad candidates are mixed in so
+        # that the aborts fire. Must equal the sequential loop over the same list.
+        def record(pose0, thr):
+            ok, pose, a2, lr, fl = T.track(pose0, [0, 0], minRes=thr)
+            r = np.zeros(sharding.REC)
+            r[0], r[1:8], r[8:10], r[10:15], r[15:18] = ok, pose, a2, lr, fl
+            r[18:24] = -1
+            k = 0
+            for l in range(L - 1, -1, -1):
+                if np.isfinite(lr[l]):
+                    r[18 + k], r[24 + k] = l, lr[l]
+                    k += 1
+            aborted = thr is not None and any(np.isfinite(lr[l]) and lr[l] > 1.5 * thr[l] for l in range(L))
+            if aborted and k < 6:
+                r[18 + k] = -2
+            return r
+
+        rngb = np.random.default_rng(5)
+        bad = np.array([O.se3_exp(np.concatenate([rngb.normal(0, 0.3, 3), rngb.normal(0, 0.15, 3)])) for _ in range(9)])
+        for rmse0 in (0.0, 1e9):
+            tries2 = np.concatenate([tries[:2], bad[:5], tries[5:8], bad[5:]])
+            n2 = len(tries2)
+            rmse = np.full(5, rmse0)
+            rec0 = record(tries2[0], None)[None, :]
+            w0 = capi.winner_rule(sharding.unpack_records(rec0), [0, 0], rmse, first_try=tries2[0])
+            if w0["good"] and w0["achievedRes"][0] < rmse0 * 1.5:
+                got2 = w0
+            else:
+                lo2, hi2 = sharding.shard_range(n2 - 1, rank, world)
+                mine = np.array([record(tries2[1 + i], w0["achievedRes"]) for i in range(lo2, hi2)]).reshape(-1, sharding.REC)
+                rest = sharding.all_gather_records(mine, n2 - 1)
+                got2 = capi.winner_rule(sharding.unpack_records(np.concatenate([rec0, rest], axis=0)), [0, 0], rmse, first_try=tries2[0])
+                assert (rest[:, 18:24] == -2).any()  # some tries were cut short by the thresholds
+            ref2 = T.track_new_coarse(tries2, [0, 0], rmse)
+            assert got2["good"] == ref2["good"] and got2["tries"] == ref2["tries"], (rmse0, got2["tries"], ref2["tries"])
+            assert np.allclose(got2["pose"], ref2["pose"], atol=1e-12)
+            assert np.allclose(got2["achievedRes"], ref2["achievedRes"], equal_nan=True)
     finally:
         dist.destroy_process_group()
 
