@@ -11,6 +11,8 @@
 //                      non-finite -> 0, absSquaredGrad (* gw^2 when B is given, :181-187), one 16-byte
 //                      coalesced store per pixel.
 // Arithmetic is exact-op fp32 without contraction, so results are bit-identical to the CPU oracle.
+#include <type_traits>
+
 #include "nalo_common.cuh"
 
 namespace {
@@ -118,47 +120,59 @@ __global__ void __launch_bounds__(256) grad_kernel(const float* __restrict__ col
   pix[L.pixOff[lvl] + idx] = make_float4(I, dx, dy, ag);
 }
 
-// ---- fused single-launch version (levels <= 5): pyramid + gradients of one 64x32 level-0 tile per CTA -------------
-// The CTA stages the 96x64 level-0 neighbourhood of its tile (16-pixel margin = one level-4 pixel) in shared memory,
-// cascades the 2x2 box means down to level 4 over the whole neighbourhood (so every level has a >= 1 pixel halo; the
-// halo values are recomputed, bit-identically, instead of exchanged), then evaluates the reference's flat-index central
-// differences of all levels for its own tile and writes one float4 per pixel. Level-0 data is read ~3x (from L2), the
-// 9.9 MB of output is written once; there is no planar intermediate and no second launch.
-// The flat-index wrap at the image's left/right border (idx-1 of x = 0 is the last pixel of the previous row) is
-// served by recomputing that one level-l value from level 0 in global memory (value_at<l>).
-// Input pixels are float (ImageAndExposure::image, util/ImageAndExposure.h:34-74) or - for images that are integer valued
-// anyway, i.e. no photometric calibration (mode = 1) - the camera's own 8-bit samples (MinimalImageB, util/MinimalImage.h):
-// uint8 -> float is exact, so both give bit-identical pyramids, and the 8-bit form is a quarter of the PCIe traffic.
-__device__ __forceinline__ float ld_pix(const float* p) { return __ldg(p); }
-__device__ __forceinline__ float ld_pix(const unsigned char* p) { return (float)__ldg(p); }
-template <int LVL, class PixT>
-__device__ __forceinline__ float value_at(const PixT* __restrict__ color, int w0, int x, int y) {
-  if constexpr (LVL == 0) {
-    return ld_pix(color + (size_t)y * w0 + x);
+// ---- staged version (levels <= 5): pyramid + gradients in one or two launches ----------------------------------------
+// Stage A builds levels 0..2 from the input image, stage B levels 3..4 from the level-2 intensities stage A left in the
+// frame (pix.x): the SAME kernel, whose input plane is either the image or that level (the 2x2 box means cascade the same
+// way and read the same floats, so every level is bit-identical to a cascade from level 0).
+// A CTA owns a 64x32 tile of its input plane and produces up to three levels for it. It stages the tile plus a margin of
+// 2^(NL-1) pixels (NL = levels the stage produces: one pixel of its coarsest level, the halo that level's gradient needs;
+// halos are recomputed, bit-identically, not exchanged), cascades the box means over the staged region, then evaluates the
+// reference's flat-index central differences for its own tile and writes one float4 per pixel.
+// Round 1 did all five levels in one stage, which takes a 16-pixel margin: 96x64 staged for a 64x32 tile (3x re-read, 3x
+// re-computed cascade; 134 warp-instructions per 32 level-0 pixels, 3.6 TB/s for 148 frames). With a 4-pixel margin the
+// staged region is 72x40 (1.4x), and stage B touches 1/16 of the pixels.
+// The flat-index wrap at the plane's left/right border (idx-1 of x = 0 is the last pixel of the previous row) is served by
+// recomputing that one value from the input plane in global memory (value_at<r>).
+struct InF32 { const float* p; __device__ __forceinline__ float ld(int i) const { return __ldg(p + i); } };
+struct InU8 { const unsigned char* p; __device__ __forceinline__ float ld(int i) const { return (float)__ldg(p + i); } };  // exact
+struct InPix { const float4* p; __device__ __forceinline__ float ld(int i) const { return __ldg(reinterpret_cast<const float*>(p + i)); } };  // .x of a built level
+
+template <int R, class In>
+__device__ __forceinline__ float value_at(const In& in, int w0, int x, int y) {
+  if constexpr (R == 0) {
+    return in.ld(y * w0 + x);
   } else {
-    return box4(value_at<LVL - 1>(color, w0, 2 * x, 2 * y), value_at<LVL - 1>(color, w0, 2 * x + 1, 2 * y),
-                value_at<LVL - 1>(color, w0, 2 * x, 2 * y + 1), value_at<LVL - 1>(color, w0, 2 * x + 1, 2 * y + 1));
+    return box4(value_at<R - 1>(in, w0, 2 * x, 2 * y), value_at<R - 1>(in, w0, 2 * x + 1, 2 * y),
+                value_at<R - 1>(in, w0, 2 * x, 2 * y + 1), value_at<R - 1>(in, w0, 2 * x + 1, 2 * y + 1));
   }
 }
 
-constexpr int FT_W = 64, FT_H = 32, FT_M = 16;             // tile and margin at level 0
-constexpr int FR_W = FT_W + 2 * FT_M, FR_H = FT_H + 2 * FT_M;  // staged region 96 x 64
+constexpr int FT_W = 64, FT_H = 32;  // tile of the stage's input plane
 
-// gradient + store of one pixel of level LVL: (lx, ly) inside the tile, S = staged level with margin m and pitch rw
-template <int LVL, class PixT>
-__device__ __forceinline__ void fused_grad_store(const float* __restrict__ S, int lx, int ly, int tx0, int ty0, const PixT* __restrict__ color,
-                                                 const float* __restrict__ B, int useB, float4* __restrict__ pix, const PyrLevels& L,
-                                                 float* __restrict__ exportStage, int exportLevels) {
-  constexpr int m = FT_M >> LVL, rw = FR_W >> LVL;
-  const int X = (tx0 >> LVL) + lx, Y = (ty0 >> LVL) + ly;
-  const int w = L.w[LVL], h = L.h[LVL];
+// Per-level constants of a stage, read once from the kernel parameters.
+struct StageLevel {
+  int w, h;
+  float4* pix;       // first pixel of the level in the frame
+  size_t dense;      // offset of the level in the reference's dense concatenation (export only)
+};
+
+// The wrap value of a border pixel: the flat-index neighbour of (0, Y) is (w-1, Y-1), of (w-1, Y) it is (0, Y+1). Kept out of
+// line so the two in 72 tile columns that need it do not cost the others predicated instructions.
+template <int R, class In>
+__device__ __noinline__ float wrap_value(const In in, int w0, int x, int y) { return value_at<R>(in, w0, x, y); }
+
+// gradient + store of one pixel of relative level R: c = its staged intensity (pitch rw), (X, Y) its position in the level
+template <int R, class In>
+__device__ __forceinline__ void staged_grad_store(const float* __restrict__ c, int rw, int X, int Y, const StageLevel& lv, const In& in, int w0,
+                                                  const float* __restrict__ B, int useB, float* __restrict__ exportStage, size_t exportTotal) {
+  const int w = lv.w, h = lv.h;
   if (X >= w || Y >= h) return;
-  const float* c = S + (ly + m) * rw + (lx + m);
   const float I = c[0];
   float dx = 0.f, dy = 0.f, ag = 0.f;
   if (Y >= 1 && Y < h - 1) {  // idx in [w, w(h-1))
-    const float left = (X > 0) ? c[-1] : value_at<LVL>(color, L.w[0], w - 1, Y - 1);
-    const float right = (X < w - 1) ? c[1] : value_at<LVL>(color, L.w[0], 0, Y + 1);
+    float left = c[-1], right = c[1];
+    if (__builtin_expect(X == 0, 0)) left = wrap_value<R>(in, w0, w - 1, Y - 1);
+    if (__builtin_expect(X == w - 1, 0)) right = wrap_value<R>(in, w0, 0, Y + 1);
     dx = __fmul_rn(0.5f, __fsub_rn(right, left));
     dy = __fmul_rn(0.5f, __fsub_rn(c[rw], c[-rw]));
     if (!isfinite(dx)) dx = 0.f;
@@ -172,107 +186,134 @@ __device__ __forceinline__ void fused_grad_store(const float* __restrict__ S, in
       ag = __fmul_rn(ag, __fmul_rn(gw, gw));
     }
   }
-  pix[L.pixOff[LVL] + (size_t)Y * w + X] = make_float4(I, dx, dy, ag);
-  if (exportStage != nullptr && LVL < exportLevels) {
+  const int idx = Y * w + X;
+  lv.pix[idx] = make_float4(I, dx, dy, ag);
+  if (exportStage != nullptr) {
     // reference host layout (AoS Vector3f {I,dx,dy}, levels concatenated; absSquaredGrad behind it) written in the same
     // pass, so the asynchronous D2H of nalo_make_images_async needs no kernel of its own (which could not run beside
     // the all-SM tracking kernel anyway)
-    const size_t g = (size_t)L.denseOff[LVL] + (size_t)Y * w + X;
+    const size_t g = lv.dense + (size_t)idx;
     exportStage[3 * g + 0] = I;
     exportStage[3 * g + 1] = dx;
     exportStage[3 * g + 2] = dy;
-    exportStage[3 * (size_t)L.total + g] = ag;
+    exportStage[3 * exportTotal + g] = ag;
   }
 }
 
+// In: the stage's input plane type. NL: levels the stage produces (1..3), absolute levels base .. base+NL-1. FIRST: first
+// relative level whose float4 pixels are written (stage B: 1, its input level already has them).
 // frameTable != nullptr: blockIdx.z selects a frame; frameTable[2z] = its input image, frameTable[2z+1] = its float4 pyramid
-// (many frames in ONE launch: nalo_track_frames).
-template <class PixT>
-__global__ void __launch_bounds__(512, 3) make_images_fused_kernel(const PixT* __restrict__ color, const float* __restrict__ B, int useB,
-                                                                float4* __restrict__ pix, const __grid_constant__ PyrLevels L,
-                                                                float* __restrict__ exportStage, int exportLevels,
-                                                                const void* const* __restrict__ frameTable) {
+// (many frames in ONE launch: nalo_track_frames). A stage whose input is the pyramid itself (InPix) reads frameTable[2z+1].
+template <class In, int NL, int FIRST>
+__global__ void __launch_bounds__(512, 3) pyr_stage_kernel(const void* __restrict__ input, int base, const float* __restrict__ B, int useB,
+                                                           float4* __restrict__ pix, const __grid_constant__ PyrLevels L,
+                                                           float* __restrict__ exportStage, int exportLevels,
+                                                           const void* const* __restrict__ frameTable) {
+  constexpr bool kFromPix = std::is_same<In, InPix>::value;
   if (frameTable != nullptr) {
-    color = static_cast<const PixT*>(frameTable[2 * blockIdx.z]);
     pix = static_cast<float4*>(const_cast<void*>(frameTable[2 * blockIdx.z + 1]));
+    input = kFromPix ? static_cast<const void*>(pix) : frameTable[2 * blockIdx.z];
   }
-  __shared__ float s0[FR_H * FR_W];
-  __shared__ float s1[(FR_H / 2) * (FR_W / 2)];
-  __shared__ float s2[(FR_H / 4) * (FR_W / 4)];
-  __shared__ float s3[(FR_H / 8) * (FR_W / 8)];
-  __shared__ float s4[(FR_H / 16) * (FR_W / 16)];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  In in;
+  if constexpr (kFromPix) in.p = static_cast<const float4*>(input) + L.pixOff[base];
+  else in.p = static_cast<decltype(in.p)>(input);
+  constexpr int M0 = 1 << (NL - 1);
+  constexpr int RW = FT_W + 2 * M0, RH = FT_H + 2 * M0;
+  __shared__ float s0[RH * RW];
+  __shared__ float s1[NL > 1 ? (RH / 2) * (RW / 2) : 1];
+  __shared__ float s2[NL > 2 ? (RH / 4) * (RW / 4) : 1];
+  const int tid = threadIdx.x;
   const int tx0 = blockIdx.x * FT_W, ty0 = blockIdx.y * FT_H;
-  const int rx0 = tx0 - FT_M, ry0 = ty0 - FT_M;
-  const int w0 = L.w[0], h0 = L.h[0];
-  // stage the 96 x 64 neighbourhood: warp `wid` takes rows wid, wid+16, wid+32, wid+48; 3 coalesced loads per row.
-  // All 12 loads of a thread are issued before the first store (one DRAM round trip, not twelve).
+  const int w0 = L.w[base], h0 = L.h[base];
+  // stage the RW x RH neighbourhood, element e = tid + 512 q (consecutive threads, consecutive columns). The position of
+  // e advances by (512 / RW rows, 512 % RW columns) per step: no division in the loop. All loads of a thread are issued
+  // before its first store (one memory round trip, not several).
   {
-    float v[12];
-    // 32-bit offsets from one base, validity as 3 column x 4 row predicates (the first version spent ~45 % of the kernel's
-    // issue slots on per-load bounds tests and 64-bit index arithmetic)
-    const int gx0 = rx0 + lane, gy0 = ry0 + wid;
-    const int off0 = gy0 * w0 + gx0;
-    bool xok[3], yok[4];
+    constexpr int kN = RW * RH, kPer = (kN + 511) / 512, kDy = 512 / RW, kDx = 512 % RW;
+    float v[kPer];
+    int ry = tid / RW, rx = tid - ry * RW;
+    int g = (ty0 - M0 + ry) * w0 + (tx0 - M0 + rx);
 #pragma unroll
-    for (int q = 0; q < 3; q++) xok[q] = (unsigned)(gx0 + 32 * q) < (unsigned)w0;
-#pragma unroll
-    for (int r = 0; r < 4; r++) yok[r] = (unsigned)(gy0 + 16 * r) < (unsigned)h0;
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-      for (int q = 0; q < 3; q++) v[3 * r + q] = (xok[q] && yok[r]) ? ld_pix(color + (unsigned)(off0 + 16 * r * w0 + 32 * q)) : 0.f;
+    for (int q = 0; q < kPer; q++) {
+      const int gx = tx0 - M0 + rx, gy = ty0 - M0 + ry;
+      v[q] = ((tid + 512 * q < kN) && (unsigned)gx < (unsigned)w0 && (unsigned)gy < (unsigned)h0) ? in.ld(g) : 0.f;
+      rx += kDx; ry += kDy; g += kDy * w0 + kDx;
+      if (rx >= RW) { rx -= RW; ry += 1; g += w0 - RW; }
     }
 #pragma unroll
-    for (int r = 0; r < 4; r++)
-#pragma unroll
-      for (int q = 0; q < 3; q++) s0[(wid + 16 * r) * FR_W + lane + 32 * q] = v[3 * r + q];
+    for (int q = 0; q < kPer; q++)
+      if (tid + 512 * q < kN) s0[tid + 512 * q] = v[q];
   }
   __syncthreads();
-  if (L.levels > 1) {  // 48 x 32 = 1536 = 3 per thread: row = tid / 16 (+32 rows? no: 32 rows x 48 cols) -> x = k % 48 via 3 x 16 columns
-    const int y = tid >> 4, xb = tid & 15;  // 32 rows x 16 threads, each thread 3 columns xb, xb+16, xb+32
+  if constexpr (NL > 1) {
+    constexpr int W1 = RW / 2, H1 = RH / 2, kDy = 512 / W1, kDx = 512 % W1;
+    int y = tid / W1, x = tid - y * W1;
 #pragma unroll
-    for (int q = 0; q < 3; q++) {
-      const int x = xb + 16 * q;
-      const float* p = s0 + (2 * y) * FR_W + 2 * x;
-      s1[y * (FR_W / 2) + x] = box4(p[0], p[1], p[FR_W], p[FR_W + 1]);
+    for (int e = 0; e < W1 * H1; e += 512) {
+      if (tid + e < W1 * H1) {
+        const float* p = s0 + (2 * y) * RW + 2 * x;
+        s1[tid + e] = box4(p[0], p[1], p[RW], p[RW + 1]);
+      }
+      x += kDx; y += kDy;
+      if (x >= W1) { x -= W1; y += 1; }
     }
     __syncthreads();
   }
-  if (L.levels > 2) {  // 24 x 16 = 384
-    if (tid < 384) {
-      const int y = tid / 24, x = tid - 24 * y;
-      const float* p = s1 + (2 * y) * (FR_W / 2) + 2 * x;
-      s2[tid] = box4(p[0], p[1], p[FR_W / 2], p[FR_W / 2 + 1]);
+  if constexpr (NL > 2) {
+    constexpr int W1 = RW / 2, W2 = RW / 4, H2 = RH / 4;
+    static_assert(W2 * H2 <= 512, "one pass");
+    if (tid < W2 * H2) {
+      const int y = tid / W2, x = tid - y * W2;
+      const float* p = s1 + (2 * y) * W1 + 2 * x;
+      s2[tid] = box4(p[0], p[1], p[W1], p[W1 + 1]);
     }
     __syncthreads();
   }
-  if (L.levels > 3) {  // 12 x 8 = 96
-    if (tid < 96) {
-      const int y = tid / 12, x = tid - 12 * y;
-      const float* p = s2 + (2 * y) * (FR_W / 4) + 2 * x;
-      s3[tid] = box4(p[0], p[1], p[FR_W / 4], p[FR_W / 4 + 1]);
-    }
-    __syncthreads();
-  }
-  if (L.levels > 4) {  // 6 x 4 = 24
-    if (tid < 24) {
-      const int y = tid / 6, x = tid - 6 * y;
-      const float* p = s3 + (2 * y) * (FR_W / 8) + 2 * x;
-      s4[tid] = box4(p[0], p[1], p[FR_W / 8], p[FR_W / 8 + 1]);
-    }
-    __syncthreads();
-  }
-  // gradients of every level for this tile: level 0 = 64 x 32 (4 rows per thread), level 1 = 32 x 16 (1 per thread), ...
-  {
+  float* ex = nullptr;  // (export: single-frame asynchronous host copies only)
+  // gradients of every produced level for this tile: relative level 0 = 64 x 32 (4 rows per thread), 1 = 32 x 16 (1 per
+  // thread), 2 = 16 x 8
+  if constexpr (FIRST == 0) {
+    const StageLevel lv{L.w[base], L.h[base], pix + L.pixOff[base], (size_t)L.denseOff[base]};
+    ex = (exportStage != nullptr && base < exportLevels) ? exportStage : nullptr;
     const int lx = tid & 63, lyb = tid >> 6;
+    const float* c = s0 + (lyb + M0) * RW + (lx + M0);
 #pragma unroll
-    for (int r = 0; r < 4; r++) fused_grad_store<0>(s0, lx, lyb + 8 * r, tx0, ty0, color, B, useB, pix, L, exportStage, exportLevels);
+    for (int r = 0; r < 4; r++) staged_grad_store<0>(c + 8 * r * RW, RW, tx0 + lx, ty0 + lyb + 8 * r, lv, in, w0, B, useB, ex, (size_t)L.total);
   }
-  if (L.levels > 1) fused_grad_store<1>(s1, tid & 31, tid >> 5, tx0, ty0, color, B, useB, pix, L, exportStage, exportLevels);
-  if (L.levels > 2 && tid < 128) fused_grad_store<2>(s2, tid & 15, tid >> 4, tx0, ty0, color, B, useB, pix, L, exportStage, exportLevels);
-  if (L.levels > 3 && tid < 32) fused_grad_store<3>(s3, tid & 7, tid >> 3, tx0, ty0, color, B, useB, pix, L, exportStage, exportLevels);
-  if (L.levels > 4 && tid < 8) fused_grad_store<4>(s4, tid & 3, tid >> 2, tx0, ty0, color, B, useB, pix, L, exportStage, exportLevels);
+  if constexpr (NL > 1) {
+    const StageLevel lv{L.w[base + 1], L.h[base + 1], pix + L.pixOff[base + 1], (size_t)L.denseOff[base + 1]};
+    ex = (exportStage != nullptr && base + 1 < exportLevels) ? exportStage : nullptr;
+    constexpr int rw = RW / 2, m = M0 / 2;
+    const int lx = tid & 31, ly = tid >> 5;
+    staged_grad_store<1>(s1 + (ly + m) * rw + (lx + m), rw, (tx0 >> 1) + lx, (ty0 >> 1) + ly, lv, in, w0, B, useB, ex, (size_t)L.total);
+  }
+  if constexpr (NL > 2) {
+    if (tid < 128) {
+      const StageLevel lv{L.w[base + 2], L.h[base + 2], pix + L.pixOff[base + 2], (size_t)L.denseOff[base + 2]};
+      ex = (exportStage != nullptr && base + 2 < exportLevels) ? exportStage : nullptr;
+      constexpr int rw = RW / 4, m = M0 / 4;
+      const int lx = tid & 15, ly = tid >> 4;
+      staged_grad_store<2>(s2 + (ly + m) * rw + (lx + m), rw, (tx0 >> 2) + lx, (ty0 >> 2) + ly, lv, in, w0, B, useB, ex, (size_t)L.total);
+    }
+  }
+}
+
+// Launches stage A (and stage B for 4- and 5-level pyramids) on `stream`. nFrames = 0: single frame (input / pix given);
+// else blockIdx.z = frame through frameTable.
+template <class In>
+static void launch_stages(const nalo_ctx* ctx, const void* input, const float* d_B, int useB, float4* pix, const PyrLevels& L, float* exportStage,
+                          int exportLevels, const void* const* frameTable, int nFrames, cudaStream_t stream) {
+  const int z = nFrames > 0 ? nFrames : 1;
+  const dim3 gA((ctx->w0 + FT_W - 1) / FT_W, (ctx->h0 + FT_H - 1) / FT_H, z);
+  const int nA = L.levels < 3 ? L.levels : 3;
+  if (nA == 1) pyr_stage_kernel<In, 1, 0><<<gA, 512, 0, stream>>>(input, 0, d_B, useB, pix, L, exportStage, exportLevels, frameTable);
+  else if (nA == 2) pyr_stage_kernel<In, 2, 0><<<gA, 512, 0, stream>>>(input, 0, d_B, useB, pix, L, exportStage, exportLevels, frameTable);
+  else pyr_stage_kernel<In, 3, 0><<<gA, 512, 0, stream>>>(input, 0, d_B, useB, pix, L, exportStage, exportLevels, frameTable);
+  if (L.levels > 3) {  // stage B: levels 3.. from the level-2 plane of the frame
+    const dim3 gB((L.w[2] + FT_W - 1) / FT_W, (L.h[2] + FT_H - 1) / FT_H, z);
+    if (L.levels == 4) pyr_stage_kernel<InPix, 2, 1><<<gB, 512, 0, stream>>>(pix, 2, d_B, useB, pix, L, exportStage, exportLevels, frameTable);
+    else pyr_stage_kernel<InPix, 3, 1><<<gB, 512, 0, stream>>>(pix, 2, d_B, useB, pix, L, exportStage, exportLevels, frameTable);
+  }
 }
 
 // float4 frame -> reference host layout: stage[0 .. 3*total) = AoS {I,dx,dy}, stage[3*total ..) = absgrad
@@ -341,13 +382,10 @@ int nalo_images_run(nalo_ctx* ctx, int slot, const void* color_dev_any, const fl
     useB = 1;
   }
   if (ctx->levels <= 5) {
-    dim3 fgrid((ctx->w0 + FT_W - 1) / FT_W, (ctx->h0 + FT_H - 1) / FT_H);
-    if (u8)
-      make_images_fused_kernel<unsigned char><<<fgrid, 512, 0, ctx->stream>>>(static_cast<const unsigned char*>(color_dev_any), ctx->d_B, useB,
-                                                                              ctx->frames[slot].pix, L, exportStage, exportLevels, nullptr);
-    else
-      make_images_fused_kernel<float><<<fgrid, 512, 0, ctx->stream>>>(color_dev, ctx->d_B, useB, ctx->frames[slot].pix, L, exportStage, exportLevels, nullptr);
+    if (u8) launch_stages<InU8>(ctx, color_dev_any, ctx->d_B, useB, ctx->frames[slot].pix, L, exportStage, exportLevels, nullptr, 0, ctx->stream);
+    else launch_stages<InF32>(ctx, color_dev, ctx->d_B, useB, ctx->frames[slot].pix, L, exportStage, exportLevels, nullptr, 0, ctx->stream);
     NALO_CHECK_LAUNCH(ctx);
+    if (ctx->levels > 3) ctx->launches++;  // (stage B)
     NALO_CUDA(ctx, cudaEventRecord(ctx->frames[slot].built, ctx->stream));
     ctx->frames[slot].valid = true;
     if (ctx->histFrameSlot == slot) ctx->histFrameSlot = -1;
@@ -416,12 +454,10 @@ int nalo_images_run_multi(nalo_ctx* ctx, int n, const int* slots, const void* co
     ht[2 * i + 1] = ctx->frames[slot].pix;
   }
   NALO_CUDA(ctx, cudaMemcpyAsync(dt, ht, sizeof(void*) * 2 * n, cudaMemcpyHostToDevice, stream));
-  dim3 fgrid((ctx->w0 + FT_W - 1) / FT_W, (ctx->h0 + FT_H - 1) / FT_H, n);
-  if (u8)
-    make_images_fused_kernel<unsigned char><<<fgrid, 512, 0, stream>>>(nullptr, ctx->d_B, useB, nullptr, L, nullptr, 0, reinterpret_cast<const void* const*>(dt));
-  else
-    make_images_fused_kernel<float><<<fgrid, 512, 0, stream>>>(nullptr, ctx->d_B, useB, nullptr, L, nullptr, 0, reinterpret_cast<const void* const*>(dt));
+  if (u8) launch_stages<InU8>(ctx, nullptr, ctx->d_B, useB, nullptr, L, nullptr, 0, reinterpret_cast<const void* const*>(dt), n, stream);
+  else launch_stages<InF32>(ctx, nullptr, ctx->d_B, useB, nullptr, L, nullptr, 0, reinterpret_cast<const void* const*>(dt), n, stream);
   NALO_CHECK_LAUNCH(ctx);
+  if (ctx->levels > 3) ctx->launches++;  // (stage B)
   for (int i = 0; i < n; i++) {
     ctx->frames[slots[i]].valid = true;
     if (ctx->histFrameSlot == slots[i]) ctx->histFrameSlot = -1;

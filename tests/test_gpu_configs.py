@@ -172,7 +172,7 @@ def test_track_frames_148_kitti_vs_single_and_oracle(kitti_pair, oracle):
         p0s, a0s = np.tile(p0, (F, 1)), np.zeros((F, 2))
         out_dev = ctx.track_frames(0, slots, p0s, a0s, colors_dev_ptrs=[dev[i % ND].data_ptr() for i in range(F)])
         out_host = ctx.track_frames(0, slots, p0s, a0s, colors_host=pins)
-        assert out_dev["stats"]["launches"] == 2
+        assert out_dev["stats"]["launches"] == 3  # pyramids of all frames (stage A: levels 0-2, stage B: 3-4) + one tracking launch
         for name, out in (("dev", out_dev), ("host", out_host)):
             assert out["ok"].all(), name
             for i in range(F):

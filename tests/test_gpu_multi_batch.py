@@ -176,7 +176,7 @@ def test_track_frames_equals_single_frames(small_pair, gpu_ctx_small, oracle):
                 assert dt < 1e-6 and dr < 1e-6, (i, dt, dr)
                 dt, dr = synth.pose_distance(out["poses"][i], gts[i])
                 assert dt < 3e-3 and dr < 3e-4
-        assert outs[0]["stats"]["launches"] == 2  # one pyramid launch for all frames + one tracking launch
+        assert outs[0]["stats"]["launches"] == 3  # pyramids of all frames (two stages) + one tracking launch
     finally:
         ctx.close()
 
@@ -208,7 +208,7 @@ def test_track_frames_pipelined_parts(small_pair, gpu_ctx_small, oracle):
             pins.append(a)
         for rep in range(2):  # second call reuses the staging area while nothing of the first is pending
             out = ctx.track_frames(0, list(range(1, n + 1)), np.tile(p0, (n, 1)), np.zeros((n, 2)), colors_host=pins)
-            assert out["stats"]["launches"] == 4  # two parts x (pyramids + tracking)
+            assert out["stats"]["launches"] == 6  # two parts x (pyramid stages A, B + tracking)
             for i in range(n):
                 assert out["ok"][i] == 1
                 dt, dr = synth.pose_distance(out["poses"][i], singles[i % 6][1])
