@@ -205,7 +205,7 @@ __device__ __forceinline__ void staged_grad_store(const float* __restrict__ c, i
 // frameTable != nullptr: blockIdx.z selects a frame; frameTable[2z] = its input image, frameTable[2z+1] = its float4 pyramid
 // (many frames in ONE launch: nalo_track_frames). A stage whose input is the pyramid itself (InPix) reads frameTable[2z+1].
 template <class In, int NL, int FIRST>
-__global__ void __launch_bounds__(512, 3) pyr_stage_kernel(const void* __restrict__ input, int base, const float* __restrict__ B, int useB,
+__global__ void __launch_bounds__(512, 4) pyr_stage_kernel(const void* __restrict__ input, int base, const float* __restrict__ B, int useB,
                                                            float4* __restrict__ pix, const __grid_constant__ PyrLevels L,
                                                            float* __restrict__ exportStage, int exportLevels,
                                                            const void* const* __restrict__ frameTable) {
