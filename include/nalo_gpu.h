@@ -336,6 +336,12 @@ typedef struct NaloLinInput {
   const float* rec_init;
   float fx, fy, cx, cy;          /* HCalib->fxl(), fyl(), cxl(), cyl() */
   float outlierTHSumComponent;   /* setting_outlierTHSumComponent = 50*50 */
+  /* Alternative to pt4 (then pt4 may be NULL): the same four values once per POINT, [n_pts][4], indexed through `point`.
+   * A point has ~6 residuals, so the per-iteration upload shrinks from 16 B per residual to ~2.8 B. With pinned host buffers
+   * (nalo_host_alloc) for this, state_in / energy_in and the outputs, a call moves ~8 B per residual up and 5 B down at the
+   * PCIe rate instead of 21 + 5 B through pageable staging. */
+  const float* pt4_points;
+  int n_pts;
 } NaloLinInput;
 int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, float* energy, float* energy_with_outlier, float* center3,
                       float* projected16, float* rec_out);

@@ -72,7 +72,8 @@ class NaloBAProblem(C.Structure):
 class NaloLinInput(C.Structure):
     _fields_ = [("n_res", C.c_int), ("nf", C.c_int), ("pt4", _P), ("color", _P), ("weights", _P), ("pack", _P), ("point", _P),
                 ("state_in", _P), ("energy_in", _P), ("pairs", _P), ("rec_init", _P),
-                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("outlierTHSumComponent", C.c_float)]
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("outlierTHSumComponent", C.c_float),
+                ("pt4_points", _P), ("n_pts", C.c_int)]
 
 
 _lib = None
@@ -792,8 +793,11 @@ class BA:
         self.ctx._ck(self.L.nalo_ba_take_data(self.h_, _ptr(out)))
         return out[: self.prob["n_res"]]
 
-    def linearize(self, prob, slots, rec_init=None, want_proj=True, want_rec=True, outlierTHSumComponent=2500.0, reuse_static=False, want_center=True):
-        """nalo_ba_linearize on a synth.make_lin_problem dict; slots[k] = context frame slot holding frame k's pyramid."""
+    def linearize(self, prob, slots, rec_init=None, want_proj=True, want_rec=True, outlierTHSumComponent=2500.0, reuse_static=False, want_center=True,
+                  per_point=False, pinned=None):
+        """nalo_ba_linearize on a synth.make_lin_problem dict; slots[k] = context frame slot holding frame k's pyramid.
+        per_point: upload {u, v, idepth_zero, idepth} once per point (prob["pt4_points"]) instead of once per residual.
+        pinned: dict of pinned arrays (pt4_points / state_in / energy_in inputs, state / energy outputs) to use instead of pageable ones."""
         n, nf = prob["n_res"], prob["nf"]
         pairs = prob["pairs"].copy()
         pairs.view(np.int32)[:, 28] = np.asarray(slots, dtype=np.int32)[pairs.view(np.int32)[:, 28]]
@@ -803,18 +807,30 @@ class BA:
         I.pt4, I.color, I.weights, I.pack, I.point, I.state_in, I.energy_in, I.pairs = [a.ctypes.data for a in keep]
         if reuse_static:
             I.color = I.weights = I.pack = I.point = None
+        if per_point:
+            pp = (pinned or {}).get("pt4_points")
+            if pp is None:
+                pp = np.ascontiguousarray(prob["pt4_points"], dtype=_f32)
+            keep.append(pp)
+            I.pt4, I.pt4_points, I.n_pts = None, pp.ctypes.data, int(pp.shape[0])
+        if pinned:
+            for k_ in ("state_in", "energy_in"):
+                if k_ in pinned:
+                    setattr(I, k_, pinned[k_].ctypes.data)
         ri = None if rec_init is None else np.ascontiguousarray(rec_init, dtype=_f32)
         I.rec_init = None if ri is None else ri.ctypes.data
         I.fx, I.fy, I.cx, I.cy = prob["K"]
         I.outlierTHSumComponent = outlierTHSumComponent
-        st = np.zeros(max(n, 1), dtype=np.uint8)
-        en = np.zeros(max(n, 1), dtype=_f32)
-        eno = np.zeros(max(n, 1), dtype=_f32)
+        st = (pinned or {}).get("state", None)
+        en = (pinned or {}).get("energy", None)
+        st = np.zeros(max(n, 1), dtype=np.uint8) if st is None else st
+        en = np.zeros(max(n, 1), dtype=_f32) if en is None else en
+        eno = np.zeros(max(n, 1), dtype=_f32) if want_center else None
         ce = np.zeros((max(n, 1), 3), dtype=_f32) if want_center else None
         pr = np.zeros((max(n, 1), 16), dtype=_f32) if want_proj else None
         rec = np.zeros((max(n, 1), BA_RECORD_WORDS), dtype=_f32) if want_rec else None
-        self.ctx._ck(self.L.nalo_ba_linearize(self.h_, C.byref(I), _ptr(st), _ptr(en), _ptr(eno) if want_center else None, _ptr(ce), _ptr(pr), _ptr(rec)))
-        return dict(state=st[:n], energy=en[:n], energy_outlier=eno[:n], center=None if ce is None else ce[:n], proj=None if pr is None else pr[:n],
+        self.ctx._ck(self.L.nalo_ba_linearize(self.h_, C.byref(I), _ptr(st), _ptr(en), _ptr(eno), _ptr(ce), _ptr(pr), _ptr(rec)))
+        return dict(state=st[:n], energy=en[:n], energy_outlier=None if eno is None else eno[:n], center=None if ce is None else ce[:n], proj=None if pr is None else pr[:n],
                     rec=None if rec is None else rec[:n])
 
     def resubstitute(self, xc, xAd, useL=False):

@@ -973,7 +973,8 @@ __global__ void resubstitute_kernel(const float* __restrict__ rec, const float* 
 struct LinArgs {
   int n, nf, w, h;
   float fx, fy, cx, cy, huberTH, outlierTHSum, modeA, modeB;
-  const float4* pt4;
+  const float4* pt4;      // [n] per residual, or [n_pts] per point when ptPerPoint (indexed through `point`)
+  int ptPerPoint;
   const float4* color;    // [n][2]
   const float4* weights;  // [n][2]
   const uint32_t* pack;
@@ -1014,7 +1015,7 @@ __global__ void __launch_bounds__(128) linearize_kernel(const LinArgs A) {
   const float affLL0 = __ldg(P + 24), affLL1 = __ldg(P + 25), b0 = __ldg(P + 26), frameEnergyTH = __ldg(P + 27);
   const int tslot = __float_as_int(__ldg(P + 28));
   const float4* __restrict__ img = A.frames[tslot];
-  const float4 pt = __ldg(A.pt4 + i);
+  const float4 pt = __ldg(A.pt4 + (A.ptPerPoint ? A.point[i] : i));
   const float u_pt = pt.x, v_pt = pt.y, idepth_zero = pt.z, idepth = pt.w;
   float col[8], wts[8];
   {
@@ -1486,7 +1487,8 @@ int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, f
   nalo_ctx* ctx = ba->ctx;
   const int n = in->n_res, nf = in->nf;
   if (n < 0 || n > ba->maxRes || nf < 1 || nf > NALO_BA_MAX_FRAMES) return nalo_fail(ctx, NALO_E_ARG, "nalo_ba_linearize: n_res=%d nf=%d out of range", n, nf);
-  if (!in->pt4 || !in->pairs) return NALO_E_ARG;
+  if ((!in->pt4 && !in->pt4_points) || !in->pairs) return NALO_E_ARG;
+  if (in->pt4_points && (in->n_pts < 0 || in->n_pts > ba->maxRes)) return nalo_fail(ctx, NALO_E_ARG, "nalo_ba_linearize: n_pts=%d out of range", in->n_pts);
   // color / weights / pack / point are static per window: NULL = reuse what the previous call uploaded (same n_res)
   const bool reuse = !in->color || !in->weights || !in->pack || !in->point;
   if (reuse && (!ba->linAlloc || ba->linN != n)) return nalo_fail(ctx, NALO_E_STATE, "nalo_ba_linearize: static inputs omitted but none of matching size are resident");
@@ -1521,7 +1523,8 @@ int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, f
     A.frames[slot] = ctx->frames[slot].pix;
   }
   if (n > 0) {
-    NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPt4, in->pt4, sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    if (in->pt4_points) NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPt4, in->pt4_points, sizeof(float) * 4 * (size_t)in->n_pts, cudaMemcpyHostToDevice, st));
+    else NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPt4, in->pt4, sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice, st));
     if (!reuse) {
       NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linColor, in->color, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, st));
       NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linWeights, in->weights, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, st));
@@ -1541,6 +1544,7 @@ int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, f
   A.huberTH = ctx->params.huberTH; A.outlierTHSum = in->outlierTHSumComponent;
   A.modeA = ctx->params.affineOptModeA; A.modeB = ctx->params.affineOptModeB;
   A.pt4 = reinterpret_cast<const float4*>(ba->d_linPt4);
+  A.ptPerPoint = in->pt4_points ? 1 : 0;
   A.color = reinterpret_cast<const float4*>(ba->d_linColor);
   A.weights = reinterpret_cast<const float4*>(ba->d_linWeights);
   A.pack = ba->d_linPack; A.point = ba->d_linPoint; A.stateIn = ba->d_linStateIn; A.energyIn = ba->d_linEnergyIn; A.pairs = ba->d_linPairs;

@@ -108,3 +108,34 @@ def test_linearize_then_accumulate_on_device(oracle):
         ba.close()
     finally:
         ctx.close()
+
+
+def test_linearize_per_point_upload_and_pinned_buffers(oracle):
+    """NaloLinInput::pt4_points: {u, v, idepth_zero, idepth} uploaded once per point and indexed through `point`, with pinned
+    host buffers for the per-iteration inputs and outputs - bit-identical to the per-residual upload from pageable memory."""
+    w, h, L, nf = 640, 384, 4, 5
+    sc, P, ctx, dIs = _setup(oracle, w, h, L, nf, 900, seed=6)
+    try:
+        n, npts = P["n_res"], P["n_pts"]
+        pts = np.zeros((npts, 4), dtype=np.float32)
+        pts[P["point"]] = P["pt4"]                       # one value set per point (as PointHessian holds them)
+        P2 = dict(P, pt4=np.ascontiguousarray(pts[P["point"]]), pt4_points=pts)
+        P2["state_in"] = (np.random.default_rng(2).random(n) < 0.05).astype(np.uint8)   # some OOB residuals are skipped
+        P2["energy_in"] = np.random.default_rng(3).uniform(0, 50, n).astype(np.float32)
+        ba = capi.BA(ctx, n + 16, npts + 16)
+        zero = np.zeros((n, 76), dtype=np.float32)
+        a = ba.linearize(P2, list(range(nf)), rec_init=zero)
+        pin = dict(pt4_points=capi.pinned_array((npts, 4), np.float32), state_in=capi.pinned_array((n,), np.uint8),
+                   energy_in=capi.pinned_array((n,), np.float32), state=capi.pinned_array((n,), np.uint8), energy=capi.pinned_array((n,), np.float32))
+        pin["pt4_points"][...] = pts
+        pin["state_in"][...] = P2["state_in"]
+        pin["energy_in"][...] = P2["energy_in"]
+        b = ba.linearize(P2, list(range(nf)), rec_init=zero, per_point=True, pinned=pin)
+        for k in ("state", "energy", "energy_outlier", "center", "proj", "rec"):
+            assert np.array_equal(_bits(a[k]) if a[k].dtype == np.float32 else a[k], _bits(b[k]) if b[k].dtype == np.float32 else b[k]), k
+        ro = oracle.linearize(P2, dIs, rec_init=zero)
+        assert np.array_equal(b["state"], ro["state"]) and np.array_equal(_bits(b["rec"]), _bits(ro["rec"]))
+        assert (b["state"] == 1).sum() >= (P2["state_in"] == 1).sum() > 0
+        ba.close()
+    finally:
+        ctx.close()

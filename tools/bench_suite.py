@@ -418,6 +418,20 @@ def main():
         # algorithmic bytes: 16 (pt4) + 64 (color, weights) + 8 (pack, point) + 5 in + 8*4*16 texels (L2-resident images) ; out 304 + 21
         add(f"f1 linearize nres={nres} (7 keyframes)", d, wl, (16 + 64 + 8 + 5 + 304 + 21) * nres, nres, "residual", c, 1,
             "per iteration: H2D 21 B/res (pt4, state, energy) + D2H 5 B/res (new state, energy), pageable, static point data resident; records stay on the device")
+        # round 2: the four point values once per point (indexed through `point`) and pinned buffers for the per-iteration traffic
+        pts4 = np.zeros((Pl["n_pts"], 4), dtype=np.float32)
+        pts4[Pl["point"]] = Pl["pt4"]
+        Pl2 = dict(Pl, pt4=np.ascontiguousarray(pts4[Pl["point"]]), pt4_points=pts4)
+        pin = dict(pt4_points=capi.pinned_array((Pl["n_pts"], 4), np.float32), state_in=capi.pinned_array((nres,), np.uint8),
+                   energy_in=capi.pinned_array((nres,), np.float32), state=capi.pinned_array((nres,), np.uint8), energy=capi.pinned_array((nres,), np.float32))
+        pin["pt4_points"][...] = pts4
+        pin["state_in"][...] = Pl["state_in"]
+        pin["energy_in"][...] = Pl["energy_in"]
+        bal.linearize(Pl2, list(range(7)), want_proj=False, want_rec=False)
+        d, wl, _ = Tl.run(lambda i: bal.linearize(Pl2, list(range(7)), want_proj=False, want_rec=False, reuse_static=True, want_center=False,
+                                                  per_point=True, pinned=pin), reps=8)
+        add(f"f1 linearize nres={nres}, per-point upload + pinned buffers", d, wl, (16 + 64 + 8 + 5 + 304 + 21) * nres, nres, "residual", c, 1,
+            f"per iteration: H2D {16 * Pl['n_pts'] / nres + 5:.1f} B/res (pt4 per point, state, energy) + D2H 5 B/res, pinned; static point data resident")
         bal.close()
         ctxl.close()
 
