@@ -432,10 +432,22 @@ static int frames_enqueue(nalo_ctx* ctx, nalo_ctx::FramesBuf& B, int trk, int n,
     // the OTHER set's submission is still being tracked on the main stream.
     for (int part = 0; part < nParts; part++) {
       const int lo = partLo(part), hi = partLo(part + 1);
-      for (int i = lo; i < hi; i++) {
-        unsigned char* dst = reinterpret_cast<unsigned char*>(B.d_color) + (size_t)pixBytes * n0 * i;
-        NALO_CUDA(ctx, cudaMemcpyAsync(dst, colors_host[i], (size_t)pixBytes * n0, cudaMemcpyHostToDevice, ctx->copyStream));
-        srcs[i] = dst;
+      // images that lie back to back in host memory (a capture ring, one pinned block) go up in ONE copy per run: 148 copies
+      // of 0.47 MB cost ~0.3 ms of driver calls and DMA set-up on top of the transfer itself
+      const size_t imgBytes = (size_t)pixBytes * n0;
+      for (int i = lo; i < hi;) {
+        int j = i + 1;
+        while (j < hi && static_cast<const unsigned char*>(colors_host[j]) == static_cast<const unsigned char*>(colors_host[j - 1]) + imgBytes) j++;
+        unsigned char* dst = reinterpret_cast<unsigned char*>(B.d_color) + imgBytes * i;
+        if (j - i > 1 && cudaMemcpyAsync(dst, colors_host[i], imgBytes * (size_t)(j - i), cudaMemcpyHostToDevice, ctx->copyStream) != cudaSuccess) {
+          // adjacent addresses, but not one allocation (two pinned blocks that happen to touch): the driver refuses a copy
+          // that spans them. Nothing was enqueued; copy the images of the run one by one.
+          (void)cudaGetLastError();
+          j = i + 1;
+        }
+        if (j - i == 1) NALO_CUDA(ctx, cudaMemcpyAsync(dst, colors_host[i], imgBytes, cudaMemcpyHostToDevice, ctx->copyStream));
+        for (int k = i; k < j; k++) srcs[k] = reinterpret_cast<unsigned char*>(B.d_color) + imgBytes * k;
+        i = j;
       }
       NALO_CUDA(ctx, cudaEventRecord(B.evUpload[part], ctx->copyStream));
     }
