@@ -736,11 +736,29 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         k_ms = float(np.mean(kern_ms))
         achieved = float(np.mean(alg_bytes)) / (k_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM traffic and executed warp-instructions of one launch come from the round's ncu capture (tools/ncu_traffic.py ->
+        # profiles/ncu_traffic.json) and are only reported while that capture was taken from THIS kernel source.
+        traffic, issue = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("track_kernel_dram_bytes_per_launch")
-        except Exception:
-            pass
+            import hashlib
+
+            nt = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            src_sha = hashlib.sha256(open(os.path.join(ROOT, "nalo_slam_b200", "csrc", "nalo_track.cu"), "rb").read()).hexdigest()
+            if nt.get("track_kernel_source_sha256") == src_sha:
+                traffic = nt.get("track_kernel_dram_bytes_per_launch")
+                per32 = nt.get("track_kernel_warp_inst_per_32_residuals")
+                if per32 and clocks.get("sm_mhz"):
+                    n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                    inst = per32 * (tot_res / K) / 32.0                      # warp-instructions of one launch (this run's residual count)
+                    peak_issue = n_sm * 4 * clocks["sm_mhz"] * 1e6           # 4 schedulers per SM, one warp-instruction per cycle each
+                    issue = {"warp_inst_per_32_residuals": per32, "warp_inst_per_launch": inst, "sm_mhz": clocks["sm_mhz"],
+                             "frac_of_issue_peak": inst / (peak_issue * k_ms * 1e-3), "issue_floor_ms": 1e3 * inst / peak_issue,
+                             "lsu_data_pipe_pct_ncu": nt.get("track_kernel_lsu_data_pipe_pct_ncu"),
+                             "note": "instruction count per residual from the round's ncu capture, kernel time and SM clock from this run"}
+            else:
+                log("profiles/ncu_traffic.json was captured from another version of nalo_track.cu: roofline.traffic / issue not reported")
+        except Exception as e:  # noqa: BLE001
+            log(f"no ncu traffic record: {e}")
         line = {
             "metric": METRIC, "value": job_res / (total_ms * 1e-3), "unit": "residuals/s", "n_gpus": world, "steps": K, "warmup": Wu,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -763,6 +781,8 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "track_kernel", "kernel_ms": k_ms,
+                         "limiter": "instruction issue + L1 (LSU) data pipe, not HBM: see `issue`; DRAM traffic is below the algorithmic bytes (the reference cloud is shared by the frames and hits in L2)",
+                         "issue": issue,
                          "alg_bytes_per_launch": float(np.mean(alg_bytes)),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
         }

@@ -162,23 +162,28 @@ template <int R, class In>
 __device__ __noinline__ float wrap_value(const In in, int w0, int x, int y) { return value_at<R>(in, w0, x, y); }
 
 // gradient + store of one pixel of relative level R: c = its staged intensity (pitch rw), (X, Y) its position in the level
-template <int R, class In>
+// INTERIOR: the tile touches no border of any level it produces - no range tests, no wrap (three tiles in four at 1241x376).
+// USEB: the absSquaredGrad weighting by the response table is compiled in (as a run-time flag the compiler speculated the
+// table look-ups for every pixel).
+template <int R, bool INTERIOR, bool USEB, class In>
 __device__ __forceinline__ void staged_grad_store(const float* __restrict__ c, int rw, int X, int Y, const StageLevel& lv, const In& in, int w0,
-                                                  const float* __restrict__ B, int useB, float* __restrict__ exportStage, size_t exportTotal) {
+                                                  const float* __restrict__ B, float* __restrict__ exportStage, size_t exportTotal) {
   const int w = lv.w, h = lv.h;
-  if (X >= w || Y >= h) return;
+  if (!INTERIOR && (X >= w || Y >= h)) return;
   const float I = c[0];
   float dx = 0.f, dy = 0.f, ag = 0.f;
-  if (Y >= 1 && Y < h - 1) {  // idx in [w, w(h-1))
+  if (INTERIOR || (Y >= 1 && Y < h - 1)) {  // idx in [w, w(h-1))
     float left = c[-1], right = c[1];
-    if (__builtin_expect(X == 0, 0)) left = wrap_value<R>(in, w0, w - 1, Y - 1);
-    if (__builtin_expect(X == w - 1, 0)) right = wrap_value<R>(in, w0, 0, Y + 1);
+    if constexpr (!INTERIOR) {
+      if (__builtin_expect(X == 0, 0)) left = wrap_value<R>(in, w0, w - 1, Y - 1);
+      if (__builtin_expect(X == w - 1, 0)) right = wrap_value<R>(in, w0, 0, Y + 1);
+    }
     dx = __fmul_rn(0.5f, __fsub_rn(right, left));
     dy = __fmul_rn(0.5f, __fsub_rn(c[rw], c[-rw]));
     if (!isfinite(dx)) dx = 0.f;
     if (!isfinite(dy)) dy = 0.f;
     ag = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-    if (useB) {
+    if constexpr (USEB) {
       int cc = cvt_x86(__fadd_rn(I, 0.5f));
       if (cc < 5) cc = 5;
       if (cc > 250) cc = 250;
@@ -204,8 +209,8 @@ __device__ __forceinline__ void staged_grad_store(const float* __restrict__ c, i
 // relative level whose float4 pixels are written (stage B: 1, its input level already has them).
 // frameTable != nullptr: blockIdx.z selects a frame; frameTable[2z] = its input image, frameTable[2z+1] = its float4 pyramid
 // (many frames in ONE launch: nalo_track_frames). A stage whose input is the pyramid itself (InPix) reads frameTable[2z+1].
-template <class In, int NL, int FIRST>
-__global__ void __launch_bounds__(512, 4) pyr_stage_kernel(const void* __restrict__ input, int base, const float* __restrict__ B, int useB,
+template <class In, int NL, int FIRST, bool USEB>
+__global__ void __launch_bounds__(512, 4) pyr_stage_kernel(const void* __restrict__ input, int base, const float* __restrict__ B,
                                                            float4* __restrict__ pix, const __grid_constant__ PyrLevels L,
                                                            float* __restrict__ exportStage, int exportLevels,
                                                            const void* const* __restrict__ frameTable) {
@@ -225,6 +230,8 @@ __global__ void __launch_bounds__(512, 4) pyr_stage_kernel(const void* __restric
   const int tid = threadIdx.x;
   const int tx0 = blockIdx.x * FT_W, ty0 = blockIdx.y * FT_H;
   const int w0 = L.w[base], h0 = L.h[base];
+  // a tile with this much room on every side touches no border of any level the stage produces (CTA-uniform)
+  const bool interior = tx0 >= 2 * M0 && ty0 >= 2 * M0 && tx0 + FT_W + 2 * M0 + 4 <= w0 && ty0 + FT_H + 2 * M0 + 4 <= h0;
   // stage the RW x RH neighbourhood, element e = tid + 512 q (consecutive threads, consecutive columns). The position of
   // e advances by (512 / RW rows, 512 % RW columns) per step: no division in the loop. All loads of a thread are issued
   // before its first store (one memory round trip, not several).
@@ -233,12 +240,21 @@ __global__ void __launch_bounds__(512, 4) pyr_stage_kernel(const void* __restric
     float v[kPer];
     int ry = tid / RW, rx = tid - ry * RW;
     int g = (ty0 - M0 + ry) * w0 + (tx0 - M0 + rx);
+    if (interior) {
 #pragma unroll
-    for (int q = 0; q < kPer; q++) {
-      const int gx = tx0 - M0 + rx, gy = ty0 - M0 + ry;
-      v[q] = ((tid + 512 * q < kN) && (unsigned)gx < (unsigned)w0 && (unsigned)gy < (unsigned)h0) ? in.ld(g) : 0.f;
-      rx += kDx; ry += kDy; g += kDy * w0 + kDx;
-      if (rx >= RW) { rx -= RW; ry += 1; g += w0 - RW; }
+      for (int q = 0; q < kPer; q++) {
+        v[q] = (tid + 512 * q < kN) ? in.ld(g) : 0.f;
+        rx += kDx; g += kDy * w0 + kDx;
+        if (rx >= RW) { rx -= RW; g += w0 - RW; }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kPer; q++) {
+        const int gx = tx0 - M0 + rx, gy = ty0 - M0 + ry;
+        v[q] = ((tid + 512 * q < kN) && (unsigned)gx < (unsigned)w0 && (unsigned)gy < (unsigned)h0) ? in.ld(g) : 0.f;
+        rx += kDx; ry += kDy; g += kDy * w0 + kDx;
+        if (rx >= RW) { rx -= RW; ry += 1; g += w0 - RW; }
+      }
     }
 #pragma unroll
     for (int q = 0; q < kPer; q++)
@@ -269,51 +285,63 @@ __global__ void __launch_bounds__(512, 4) pyr_stage_kernel(const void* __restric
     }
     __syncthreads();
   }
-  float* ex = nullptr;  // (export: single-frame asynchronous host copies only)
   // gradients of every produced level for this tile: relative level 0 = 64 x 32 (4 rows per thread), 1 = 32 x 16 (1 per
   // thread), 2 = 16 x 8
-  if constexpr (FIRST == 0) {
-    const StageLevel lv{L.w[base], L.h[base], pix + L.pixOff[base], (size_t)L.denseOff[base]};
-    ex = (exportStage != nullptr && base < exportLevels) ? exportStage : nullptr;
-    const int lx = tid & 63, lyb = tid >> 6;
-    const float* c = s0 + (lyb + M0) * RW + (lx + M0);
+  auto gradients = [&](auto interiorTag) {
+    constexpr bool IN_ = decltype(interiorTag)::value;
+    float* ex = nullptr;  // (export: single-frame asynchronous host copies only)
+    if constexpr (FIRST == 0) {
+      const StageLevel lv{L.w[base], L.h[base], pix + L.pixOff[base], (size_t)L.denseOff[base]};
+      ex = (exportStage != nullptr && base < exportLevels) ? exportStage : nullptr;
+      const int lx = tid & 63, lyb = tid >> 6;
+      const float* c = s0 + (lyb + M0) * RW + (lx + M0);
 #pragma unroll
-    for (int r = 0; r < 4; r++) staged_grad_store<0>(c + 8 * r * RW, RW, tx0 + lx, ty0 + lyb + 8 * r, lv, in, w0, B, useB, ex, (size_t)L.total);
-  }
-  if constexpr (NL > 1) {
-    const StageLevel lv{L.w[base + 1], L.h[base + 1], pix + L.pixOff[base + 1], (size_t)L.denseOff[base + 1]};
-    ex = (exportStage != nullptr && base + 1 < exportLevels) ? exportStage : nullptr;
-    constexpr int rw = RW / 2, m = M0 / 2;
-    const int lx = tid & 31, ly = tid >> 5;
-    staged_grad_store<1>(s1 + (ly + m) * rw + (lx + m), rw, (tx0 >> 1) + lx, (ty0 >> 1) + ly, lv, in, w0, B, useB, ex, (size_t)L.total);
-  }
-  if constexpr (NL > 2) {
-    if (tid < 128) {
-      const StageLevel lv{L.w[base + 2], L.h[base + 2], pix + L.pixOff[base + 2], (size_t)L.denseOff[base + 2]};
-      ex = (exportStage != nullptr && base + 2 < exportLevels) ? exportStage : nullptr;
-      constexpr int rw = RW / 4, m = M0 / 4;
-      const int lx = tid & 15, ly = tid >> 4;
-      staged_grad_store<2>(s2 + (ly + m) * rw + (lx + m), rw, (tx0 >> 2) + lx, (ty0 >> 2) + ly, lv, in, w0, B, useB, ex, (size_t)L.total);
+      for (int r = 0; r < 4; r++)
+        staged_grad_store<0, IN_, USEB>(c + 8 * r * RW, RW, tx0 + lx, ty0 + lyb + 8 * r, lv, in, w0, B, ex, (size_t)L.total);
     }
-  }
+    if constexpr (NL > 1) {
+      const StageLevel lv{L.w[base + 1], L.h[base + 1], pix + L.pixOff[base + 1], (size_t)L.denseOff[base + 1]};
+      ex = (exportStage != nullptr && base + 1 < exportLevels) ? exportStage : nullptr;
+      constexpr int rw = RW / 2, m = M0 / 2;
+      const int lx = tid & 31, ly = tid >> 5;
+      staged_grad_store<1, IN_, USEB>(s1 + (ly + m) * rw + (lx + m), rw, (tx0 >> 1) + lx, (ty0 >> 1) + ly, lv, in, w0, B, ex, (size_t)L.total);
+    }
+    if constexpr (NL > 2) {
+      if (tid < 128) {
+        const StageLevel lv{L.w[base + 2], L.h[base + 2], pix + L.pixOff[base + 2], (size_t)L.denseOff[base + 2]};
+        ex = (exportStage != nullptr && base + 2 < exportLevels) ? exportStage : nullptr;
+        constexpr int rw = RW / 4, m = M0 / 4;
+        const int lx = tid & 15, ly = tid >> 4;
+        staged_grad_store<2, IN_, USEB>(s2 + (ly + m) * rw + (lx + m), rw, (tx0 >> 2) + lx, (ty0 >> 2) + ly, lv, in, w0, B, ex, (size_t)L.total);
+      }
+    }
+  };
+  if (interior) gradients(std::true_type{});
+  else gradients(std::false_type{});
 }
 
+template <class In, bool USEB>
+static void launch_stages_b(const nalo_ctx* ctx, const void* input, const float* d_B, float4* pix, const PyrLevels& L, float* exportStage,
+                            int exportLevels, const void* const* frameTable, int nFrames, cudaStream_t stream) {
+  const int z = nFrames > 0 ? nFrames : 1;
+  const dim3 gA((ctx->w0 + FT_W - 1) / FT_W, (ctx->h0 + FT_H - 1) / FT_H, z);
+  const int nA = L.levels < 3 ? L.levels : 3;
+  if (nA == 1) pyr_stage_kernel<In, 1, 0, USEB><<<gA, 512, 0, stream>>>(input, 0, d_B, pix, L, exportStage, exportLevels, frameTable);
+  else if (nA == 2) pyr_stage_kernel<In, 2, 0, USEB><<<gA, 512, 0, stream>>>(input, 0, d_B, pix, L, exportStage, exportLevels, frameTable);
+  else pyr_stage_kernel<In, 3, 0, USEB><<<gA, 512, 0, stream>>>(input, 0, d_B, pix, L, exportStage, exportLevels, frameTable);
+  if (L.levels > 3) {  // stage B: levels 3.. from the level-2 plane of the frame
+    const dim3 gB((L.w[2] + FT_W - 1) / FT_W, (L.h[2] + FT_H - 1) / FT_H, z);
+    if (L.levels == 4) pyr_stage_kernel<InPix, 2, 1, USEB><<<gB, 512, 0, stream>>>(pix, 2, d_B, pix, L, exportStage, exportLevels, frameTable);
+    else pyr_stage_kernel<InPix, 3, 1, USEB><<<gB, 512, 0, stream>>>(pix, 2, d_B, pix, L, exportStage, exportLevels, frameTable);
+  }
+}
 // Launches stage A (and stage B for 4- and 5-level pyramids) on `stream`. nFrames = 0: single frame (input / pix given);
 // else blockIdx.z = frame through frameTable.
 template <class In>
 static void launch_stages(const nalo_ctx* ctx, const void* input, const float* d_B, int useB, float4* pix, const PyrLevels& L, float* exportStage,
                           int exportLevels, const void* const* frameTable, int nFrames, cudaStream_t stream) {
-  const int z = nFrames > 0 ? nFrames : 1;
-  const dim3 gA((ctx->w0 + FT_W - 1) / FT_W, (ctx->h0 + FT_H - 1) / FT_H, z);
-  const int nA = L.levels < 3 ? L.levels : 3;
-  if (nA == 1) pyr_stage_kernel<In, 1, 0><<<gA, 512, 0, stream>>>(input, 0, d_B, useB, pix, L, exportStage, exportLevels, frameTable);
-  else if (nA == 2) pyr_stage_kernel<In, 2, 0><<<gA, 512, 0, stream>>>(input, 0, d_B, useB, pix, L, exportStage, exportLevels, frameTable);
-  else pyr_stage_kernel<In, 3, 0><<<gA, 512, 0, stream>>>(input, 0, d_B, useB, pix, L, exportStage, exportLevels, frameTable);
-  if (L.levels > 3) {  // stage B: levels 3.. from the level-2 plane of the frame
-    const dim3 gB((L.w[2] + FT_W - 1) / FT_W, (L.h[2] + FT_H - 1) / FT_H, z);
-    if (L.levels == 4) pyr_stage_kernel<InPix, 2, 1><<<gB, 512, 0, stream>>>(pix, 2, d_B, useB, pix, L, exportStage, exportLevels, frameTable);
-    else pyr_stage_kernel<InPix, 3, 1><<<gB, 512, 0, stream>>>(pix, 2, d_B, useB, pix, L, exportStage, exportLevels, frameTable);
-  }
+  if (useB) launch_stages_b<In, true>(ctx, input, d_B, pix, L, exportStage, exportLevels, frameTable, nFrames, stream);
+  else launch_stages_b<In, false>(ctx, input, d_B, pix, L, exportStage, exportLevels, frameTable, nFrames, stream);
 }
 
 // float4 frame -> reference host layout: stage[0 .. 3*total) = AoS {I,dx,dy}, stage[3*total ..) = absgrad
