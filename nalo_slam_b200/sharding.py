@@ -88,10 +88,22 @@ def all_gather_device_records(dev_ptr: int, n_local: int, n_total: int, device, 
     world = dist.get_world_size()
     sizes = shard_sizes(n_total, world)
     m = max(sizes)
-    buf = torch.zeros((m, width), dtype=torch.float64, device=device)
+    # send / receive / pinned host buffers are kept between calls (a gather per step must not pay three allocations)
+    key = (m, width, world, str(device))
+    bufs = _gather_cache.get(key)
+    if bufs is None:
+        bufs = (torch.zeros((m, width), dtype=torch.float64, device=device), torch.empty((world * m, width), dtype=torch.float64, device=device),
+                torch.empty((world * m, width), dtype=torch.float64).pin_memory())
+        _gather_cache.clear()
+        _gather_cache[key] = bufs
+    buf, out, host_t = bufs
     if n_local:
-        buf[:n_local] = torch.as_tensor(_DevArray(dev_ptr, (n_local, width)), device=device)
-    out = torch.empty((world * m, width), dtype=torch.float64, device=device)
+        buf[:n_local].copy_(torch.as_tensor(_DevArray(dev_ptr, (n_local, width)), device=device))
     dist.all_gather_into_tensor(out, buf)
-    host = out.cpu().numpy().reshape(world, m, width)
+    host_t.copy_(out, non_blocking=True)
+    torch.cuda.current_stream(device).synchronize()
+    host = host_t.numpy().reshape(world, m, width)
     return np.concatenate([host[r, : sizes[r]] for r in range(world)], axis=0)
+
+
+_gather_cache = {}
