@@ -289,10 +289,10 @@ class Context:
         self._ck(self.L.nalo_selector_make_hists(self.h_, C.c_int(slot), _ptr(ths), _ptr(thsS), C.byref(nb)))
         return ths[: nb.value], thsS[: nb.value]
 
-    def selector_select(self, slot, pot, thFactor=1.0):
-        m = np.zeros(self.w * self.h, dtype=_f32)
+    def selector_select(self, slot, pot, thFactor=1.0, want_map=True):
+        m = np.zeros(self.w * self.h, dtype=_f32) if want_map else None
         n3 = np.zeros(3, dtype=np.int32)
-        self._ck(self.L.nalo_selector_select(self.h_, C.c_int(slot), C.c_int(pot), C.c_float(thFactor), _ptr(m), _ptr(n3)))
+        self._ck(self.L.nalo_selector_select(self.h_, C.c_int(slot), C.c_int(pot), C.c_float(thFactor), _ptr(m) if want_map else None, _ptr(n3)))
         return m, n3
 
     # ---- makeK + a5

@@ -198,6 +198,34 @@ int nalo_fail(nalo_ctx* ctx, int code, const char* fmt, ...);
                                              cudaGetErrorString(e__));                             \
   } while (0)
 
+#ifdef __CUDACC__
+// Inclusive scan of one value per thread over a 1024-thread CTA: shuffles inside the warps, one shared-memory hop for
+// the 32 warp totals (two barriers).
+template <typename T>
+__device__ __forceinline__ T cta_scan_1024(T v, T* warpSums) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  T incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const T t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warpSums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    T w = warpSums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const T t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    warpSums[lane] = w;
+  }
+  __syncthreads();
+  return incl + ((wid > 0) ? warpSums[wid - 1] : T(0));
+}
+#endif
+
 // internal cross-file entry points
 int nalo_images_run(nalo_ctx* ctx, int slot, const void* color_dev, const float* B256_host, float* exportStage = nullptr, int exportLevels = 0,
                     bool u8 = false);  // u8: color_dev holds 8-bit samples instead of floats

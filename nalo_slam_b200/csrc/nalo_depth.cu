@@ -194,34 +194,25 @@ __global__ void __launch_bounds__(256) finish_kernel(const float* __restrict__ t
   if (threadIdx.x == 0) blockCount[blockIdx.x] = cnt;
 }
 
-// one CTA: exclusive scan of blockCount within each level's CTA range; writes pc_n per level.
+// one CTA per level: exclusive scan of blockCount within the level's CTA range; writes pc_n of the level.
 __global__ void __launch_bounds__(1024) scan_kernel(int* __restrict__ blockCount, DepthLevels L, int* __restrict__ pc_n) {
-  __shared__ int sh[1024];
+  __shared__ int warpSums[32];
   __shared__ int carry;
-  for (int lvl = 0; lvl < L.levels; lvl++) {
-    const int b0 = L.blockOff[lvl], b1 = L.blockOff[lvl + 1];
-    if (threadIdx.x == 0) carry = 0;
+  const int lvl = blockIdx.x;
+  const int b0 = L.blockOff[lvl], b1 = L.blockOff[lvl + 1];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = b0; base < b1; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = (i < b1) ? blockCount[i] : 0;
+    const int incl = cta_scan_1024(v, warpSums);
+    const int c = carry;
+    if (i < b1) blockCount[i] = c + incl - v;
     __syncthreads();
-    for (int base = b0; base < b1; base += 1024) {
-      const int i = base + threadIdx.x;
-      const int v = (i < b1) ? blockCount[i] : 0;
-      sh[threadIdx.x] = v;
-      __syncthreads();
-      for (int ofs = 1; ofs < 1024; ofs <<= 1) {
-        int t = (threadIdx.x >= ofs) ? sh[threadIdx.x - ofs] : 0;
-        __syncthreads();
-        sh[threadIdx.x] += t;
-        __syncthreads();
-      }
-      const int incl = sh[threadIdx.x];
-      if (i < b1) blockCount[i] = carry + incl - v;
-      __syncthreads();
-      if (threadIdx.x == 1023) carry += incl;
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) pc_n[lvl] = carry;
+    if (threadIdx.x == 1023) carry = c + incl;
     __syncthreads();
   }
+  if (threadIdx.x == 0) pc_n[lvl] = carry;
 }
 
 __global__ void __launch_bounds__(256) compact_kernel(const uint8_t* __restrict__ flags, const int* __restrict__ blockOffset,
@@ -289,7 +280,7 @@ int nalo_depth_finish(nalo_ctx* ctx, int trk, int ref_slot) {
   int* blockCount = ctx->d_scan;  // >= nBlocks ints
   finish_kernel<<<nBlocks, 256, 0, ctx->stream>>>(tmpI, tmpW, ctx->frames[ref_slot].pix, P, L, ctx->d_mask_all, blockCount);
   NALO_CHECK_LAUNCH(ctx);
-  scan_kernel<<<1, 1024, 0, ctx->stream>>>(blockCount, L, ctx->d_counts);
+  scan_kernel<<<L.levels, 1024, 0, ctx->stream>>>(blockCount, L, ctx->d_counts);
   NALO_CHECK_LAUNCH(ctx);
   compact_kernel<<<nBlocks, 256, 0, ctx->stream>>>(ctx->d_mask_all, blockCount, ctx->frames[ref_slot].pix, P, L);
   NALO_CHECK_LAUNCH(ctx);

@@ -10,11 +10,14 @@
 //         block_mask_kernel : per pot-block, for all 16 directions at once, "would this block select anything"
 //                             (bit d set iff some pixel above threshold has |grad.dir_d| > 0). Almost every block
 //                             is all-ones or zero, i.e. independent of the direction.
-//         exclusive scan    : n2 at the start of every pot-block, assuming direction-independent blocks.
-//         resolve_kernel    : the rare direction-dependent blocks are replayed sequentially (one thread, in
-//                             order, a handful of entries), then the scan is redone with their true outcome.
-//         select_kernel     : one thread per 4pot block replays the reference's inner loops verbatim (same
-//                             sentinels, same tie-breaking) with the now-known n2 of each of its pot-blocks.
+//         exclusive scan    : n2 at the start of every pot-block, assuming direction-independent blocks (one packed
+//                             64-bit scan also ranks the direction-dependent blocks into a list).
+//         resolve_kernel    : the direction-dependent blocks (rare on float images, a few hundred on 8-bit valued
+//                             ones) are settled in order by one warp, 32 at a time with every load issued up front;
+//                             then the scan is redone with their true outcome (device-gated: no host round trip).
+//         select_warp_kernel: a group of 1 / 4 / 8 warps per 4pot block evaluates the closed form of the reference's
+//                             sentinel state machine with the now-known n2 of each pot-block (select_kernel, one
+//                             thread per 4pot block replaying the loops verbatim, is the cross-check).
 //   makeMaps (:144-291)  host logic (potential adaptation, one recursion) + subsample_kernel for the
 //       random drop, whose running index `rn` is again an exclusive scan.
 // Arithmetic that feeds a comparison is un-contracted fp32 in the reference's order, so the selection map is
@@ -31,68 +34,81 @@ __constant__ float kDir[16][2] = {{0.f, 1.0000f},      {0.3827f, 0.9239f},  {0.1
                                   {0.5556f, -0.8315f}, {0.9808f, 0.1951f},  {0.9239f, -0.3827f}, {0.7071f, -0.7071f},
                                   {0.5556f, 0.8315f},  {0.9808f, -0.1951f}, {1.0000f, 0.0000f},  {0.1951f, -0.9808f}};
 
-// ---------------------------------------------------------------------------------------------- generic int scan
-__global__ void __launch_bounds__(1024) scan_block_kernel(const int* __restrict__ in, int* __restrict__ out, int* __restrict__ blockSums, int n) {
-  __shared__ int warpSums[32];
+// ---------------------------------------------------------------------------------------------- scans
+// Three-kernel exclusive scan (CTA scan, scan of the CTA totals, add). `Load` maps an index to the value scanned, so the
+// flag arrays of the callers never exist in memory; `gate`, when given, makes every kernel of the scan a no-op while
+// *gate == 0 (the rescan after resolve_kernel is enqueued unconditionally: no host round trip to decide).
+struct LoadNonzero {  // makeMaps random drop: map != 0
+  const float* map;
+  __device__ __forceinline__ int operator()(int i) const { return (map[i] != 0.f) ? 1 : 0; }
+};
+// pot-block masks: low word counts blocks that select under every direction, high word the direction-dependent ones
+struct LoadMaskPair {
+  const unsigned short* masks;
+  __device__ __forceinline__ unsigned long long operator()(int i) const {
+    const unsigned m = masks[i];
+    return (m == 0xFFFFu) ? 1ull : ((m != 0u) ? (1ull << 32) : 0ull);
+  }
+};
+template <typename T, typename Load>
+__global__ void __launch_bounds__(1024) scan_block_kernel(Load load, T* __restrict__ out, T* __restrict__ blockSums, int n, const int* __restrict__ gate) {
+  __shared__ T warpSums[32];
+  if (gate && *gate == 0) return;
   const int i = blockIdx.x * 1024 + threadIdx.x;
-  const int v = (i < n) ? in[i] : 0;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int incl = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) warpSums[wid] = incl;
-  __syncthreads();
-  if (wid == 0) {
-    int w = warpSums[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += t;
-    }
-    warpSums[lane] = w;
-  }
-  __syncthreads();
-  const int base = (wid > 0) ? warpSums[wid - 1] : 0;
-  if (i < n) out[i] = base + incl - v;
-  if (threadIdx.x == 1023) blockSums[blockIdx.x] = base + incl;
+  const T v = (i < n) ? load(i) : T(0);
+  const T incl = cta_scan_1024(v, warpSums);
+  if (i < n) out[i] = incl - v;
+  if (threadIdx.x == 1023) blockSums[blockIdx.x] = incl;
 }
-__global__ void __launch_bounds__(1024) scan_sums_kernel(int* __restrict__ blockSums, int nb, int* __restrict__ total) {
-  __shared__ int sh[1024];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
+// `split`, when given, receives the low / high 32-bit words of the grand total in split[1] / split[0]
+template <typename T>
+__global__ void __launch_bounds__(1024) scan_sums_kernel(T* __restrict__ blockSums, int nb, T* __restrict__ total, const int* __restrict__ gate,
+                                                         int* __restrict__ split = nullptr) {
+  __shared__ T warpSums[32];
+  __shared__ T carry;
+  if (gate && *gate == 0) return;
+  if (threadIdx.x == 0) carry = T(0);
   __syncthreads();
   for (int base = 0; base < nb; base += 1024) {
     const int i = base + threadIdx.x;
-    const int v = (i < nb) ? blockSums[i] : 0;
-    sh[threadIdx.x] = v;
+    const T v = (i < nb) ? blockSums[i] : T(0);
+    const T incl = cta_scan_1024(v, warpSums);
+    const T c = carry;
+    if (i < nb) blockSums[i] = c + incl - v;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
-    }
-    const int incl = sh[threadIdx.x];
-    if (i < nb) blockSums[i] = carry + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += incl;
+    if (threadIdx.x == 1023) carry = c + incl;
     __syncthreads();
   }
   if (threadIdx.x == 0 && total) *total = carry;
+  if (threadIdx.x == 0 && split) {
+    const unsigned long long c = (unsigned long long)carry;
+    split[1] = (int)(unsigned)(c & 0xFFFFFFFFull);
+    split[0] = (int)(c >> 32);
+  }
 }
 __global__ void __launch_bounds__(1024) scan_add_kernel(int* __restrict__ out, const int* __restrict__ blockSums, int n) {
   const int i = blockIdx.x * 1024 + threadIdx.x;
   if (i < n) out[i] += blockSums[blockIdx.x];
 }
-
-int exclusive_scan(nalo_ctx* ctx, const int* in, int* out, int n, int* blockSums, int* total) {
+// last kernel of the packed scan: prefix[slot] = label-1 selections before the slot; the direction-dependent slots are
+// written, in order, to ambList (their rank is the high word)
+__global__ void __launch_bounds__(1024) scan_add_pair_kernel(const unsigned long long* __restrict__ scanned, const unsigned long long* __restrict__ blockSums,
+                                                             const unsigned short* __restrict__ masks, int n, int* __restrict__ prefix,
+                                                             int* __restrict__ ambList, const int* __restrict__ gate) {
+  if (gate && *gate == 0) return;
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long v = scanned[i] + blockSums[blockIdx.x];
+  prefix[i] = (int)(unsigned)(v & 0xFFFFFFFFull);
+  const unsigned m = masks[i];
+  if (ambList && m != 0u && m != 0xFFFFu) ambList[(int)(v >> 32)] = i;
+}
+template <typename Load>
+int exclusive_scan(nalo_ctx* ctx, Load load, int* out, int n, int* blockSums, int* total) {
   const int nb = (n + 1023) / 1024;
-  scan_block_kernel<<<nb, 1024, 0, ctx->stream>>>(in, out, blockSums, n);
+  scan_block_kernel<int, Load><<<nb, 1024, 0, ctx->stream>>>(load, out, blockSums, n, nullptr);
   NALO_CHECK_LAUNCH(ctx);
-  scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(blockSums, nb, total);
+  scan_sums_kernel<int><<<1, 1024, 0, ctx->stream>>>(blockSums, nb, total, nullptr);
   NALO_CHECK_LAUNCH(ctx);
   scan_add_kernel<<<nb, 1024, 0, ctx->stream>>>(out, blockSums, n);
   NALO_CHECK_LAUNCH(ctx);
@@ -163,73 +179,91 @@ struct SelGeom {
 
 __device__ __forceinline__ bool border_skip(const SelGeom& g, int xf, int yf) { return xf < 4 || xf >= g.w - 5 || yf < 4 || yf > g.h - 4; }
 
-// slot = b4*16 + ((y3i*2 + x3i)*2 + y2i)*2 + x2i ; returns false when the sub-block does not exist (image edge)
-__device__ __forceinline__ bool slot_rect(const SelGeom& g, int slot, int& x0, int& y0, int& mx1, int& my1) {
-  const int b4 = slot >> 4, loc = slot & 15;
-  const int x2i = loc & 1, y2i = (loc >> 1) & 1, x3i = (loc >> 2) & 1, y3i = (loc >> 3) & 1;
-  const int x4 = (b4 % g.nX4) * 4 * g.pot, y4 = (b4 / g.nX4) * 4 * g.pot;
-  const int x34 = x4 + x3i * 2 * g.pot, y34 = y4 + y3i * 2 * g.pot;
-  if (x34 >= g.w || y34 >= g.h) return false;
-  x0 = x34 + x2i * g.pot;
-  y0 = y34 + y2i * g.pot;
-  if (x0 >= g.w || y0 >= g.h) return false;
-  mx1 = min(g.pot, g.w - x0);
-  my1 = min(g.pot, g.h - y0);
-  return true;
+// pot-block slot of a 4pot block b4: slot = b4*16 + ((y3i*2 + x3i)*2 + y2i)*2 + x2i
+// A group of WPB warps works on one 4pot block (kSelWarps / WPB blocks per CTA); barriers are per group.
+constexpr int kSelWarps = 8;
+template <int WPB>
+__device__ __forceinline__ void group_sync(int grp) {
+  if (WPB == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(WPB * 32) : "memory");
 }
+__host__ __device__ inline int sel_group_warps(int pot) { return (16 * pot * pot <= 128) ? 1 : ((16 * pot * pot <= 1024) ? 4 : 8); }
 
-// per pot-block: bit d set iff the block would make a label-1 selection under direction d
-__global__ void __launch_bounds__(256) block_mask_kernel(const float4* __restrict__ pix, const float* __restrict__ thsSmoothed, SelGeom g,
-                                                         int nSlots, int* __restrict__ selUnamb, int* __restrict__ amb,
-                                                         unsigned short* __restrict__ masks) {
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= nSlots) return;
-  int x0, y0, mx1, my1;
-  unsigned m = 0;
-  if (slot_rect(g, slot, x0, y0, mx1, my1)) {
-    for (int y1 = 0; y1 < my1; y1++)
-      for (int x1 = 0; x1 < mx1; x1++) {
-        const int xf = x0 + x1, yf = y0 + y1;
-        if (border_skip(g, xf, yf)) continue;
-        const float th0 = thsSmoothed[(xf >> 5) + (yf >> 5) * g.thsStep];
-        const float4 p = pix[xf + g.w * yf];
-        if (p.w > __fmul_rn(th0, g.thFactor)) {
-          if (!g.dirDist) {
-            if (p.w > 0.f) m = 0xFFFFu;
-          } else {
+// per pot-block: bit d set iff the block would make a label-1 selection under direction d. The pixels of the 4pot block
+// are walked in raster order (rows of 4pot contiguous texels) by the group's lanes; the 16 masks are OR-reduced in shared
+// memory.
+template <int WPB>
+__global__ void __launch_bounds__(kSelWarps * 32) block_mask_kernel(const float4* __restrict__ pix, const float* __restrict__ thsSmoothed, SelGeom g,
+                                                                   unsigned short* __restrict__ masks) {
+  constexpr int GPC = kSelWarps / WPB;  // groups per CTA
+  __shared__ unsigned sm[GPC][16];
+  const int grp = (threadIdx.x >> 5) / WPB, t = threadIdx.x - grp * WPB * 32;
+  const int b4 = blockIdx.x * GPC + grp;
+  if (b4 >= g.nX4 * g.nY4) return;  // whole groups leave together
+  if (t < 16) sm[grp][t] = 0u;
+  group_sync<WPB>(grp);
+  const int pot = g.pot;
+  const int x4 = (b4 % g.nX4) * 4 * pot, y4 = (b4 / g.nX4) * 4 * pot;
+  const int mx = min(4 * pot, g.w - x4), my = min(4 * pot, g.h - y4);
+  for (int v = t; v < mx * my; v += WPB * 32) {
+    const int y = v / mx, x = v - y * mx;
+    const int xf = x4 + x, yf = y4 + y;
+    if (border_skip(g, xf, yf)) continue;
+    const float th0 = thsSmoothed[(xf >> 5) + (yf >> 5) * g.thsStep];
+    const float4 p = pix[xf + g.w * yf];
+    if (!(p.w > __fmul_rn(th0, g.thFactor))) continue;
+    unsigned m = 0;
+    if (!g.dirDist) {
+      if (p.w > 0.f) m = 0xFFFFu;
+    } else {
 #pragma unroll
-            for (int d = 0; d < 16; d++) {
-              const float dn = fabsf(__fadd_rn(__fmul_rn(p.y, kDir[d][0]), __fmul_rn(p.z, kDir[d][1])));
-              if (dn > 0.f) m |= 1u << d;
-            }
-          }
-        }
+      for (int d = 0; d < 16; d++) {
+        const float dn = fabsf(__fadd_rn(__fmul_rn(p.y, kDir[d][0]), __fmul_rn(p.z, kDir[d][1])));
+        if (dn > 0.f) m |= 1u << d;
       }
+    }
+    if (m) {
+      const int xq = x / pot, yq = y / pot;  // pot-block coordinates 0..3 inside the 4pot block
+      const int loc = (((yq >> 1) * 2 + (xq >> 1)) * 2 + (yq & 1)) * 2 + (xq & 1);
+      atomicOr(&sm[grp][loc], m);
+    }
   }
-  masks[slot] = (unsigned short)m;
-  selUnamb[slot] = (m == 0xFFFFu) ? 1 : 0;
-  amb[slot] = (m != 0 && m != 0xFFFFu) ? 1 : 0;
+  group_sync<WPB>(grp);
+  if (t < 16) masks[b4 * 16 + t] = (unsigned short)sm[grp][t];
 }
 
-// compact the ambiguous slots in order (ambPos = exclusive scan of amb)
-__global__ void amb_compact_kernel(const int* __restrict__ amb, const int* __restrict__ ambPos, int nSlots, int* __restrict__ ambList) {
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot < nSlots && amb[slot]) ambList[ambPos[slot]] = slot;
-}
-// one thread: replay the direction-dependent blocks in order; selFinal[slot] gets their true outcome
-__global__ void resolve_kernel(const int* __restrict__ ambList, const int* __restrict__ nAmb, const int* __restrict__ prefixUnamb,
-                               const unsigned short* __restrict__ masks, const unsigned char* __restrict__ randomPattern,
-                               int* __restrict__ selFinal) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  int offset = 0;
+// One warp: replay the direction-dependent blocks in order. n2 of entry k is prefix[slot_k] + (selections made by the
+// entries before it), and an entry's outcome is bit (randomPattern[n2] & 15) of its mask. 32 entries at a time: lane k
+// fetches its entry and, for each possible number j <= k of selections made inside the batch before it, the outcome it
+// would have (one bit per j), all loads independent; the in-order walk that picks the true j is then 32 shuffle steps
+// in registers. The resolved outcome overwrites the mask (0xFFFF / 0), so the rescan reads the same array.
+__global__ void __launch_bounds__(32) resolve_kernel(const int* __restrict__ ambList, const int* __restrict__ nAmb, const int* __restrict__ prefixUnamb,
+                                                     unsigned short* __restrict__ masks, const unsigned char* __restrict__ randomPattern, int nPattern) {
+  const int lane = threadIdx.x;
   const int n = *nAmb;
-  for (int k = 0; k < n; k++) {
-    const int slot = ambList[k];
-    const int n2 = prefixUnamb[slot] + offset;
-    const int d = randomPattern[n2] & 0xF;
-    const int sel = (masks[slot] >> d) & 1;
-    selFinal[slot] = sel;
-    offset += sel;
+  int offset = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int k = base + lane;
+    int slot = -1;
+    unsigned outcomes = 0;
+    if (k < n) {
+      slot = ambList[k];
+      const int n2 = prefixUnamb[slot] + offset;
+      const unsigned m = masks[slot];
+      for (int j = 0; j <= lane; j++) {
+        const int idx = min(n2 + j, nPattern - 1);
+        outcomes |= ((m >> (randomPattern[idx] & 0xF)) & 1u) << j;
+      }
+    }
+    int made = 0, mine = 0;
+    for (int e = 0; e < 32; e++) {
+      const unsigned oe = __shfl_sync(0xffffffffu, outcomes, e);
+      const int sel = (oe >> made) & 1u;
+      if (e == lane) mine = sel;
+      made += sel;
+    }
+    if (slot >= 0) masks[slot] = mine ? (unsigned short)0xFFFFu : (unsigned short)0;
+    offset += made;
   }
 }
 
@@ -320,10 +354,9 @@ __global__ void __launch_bounds__(128) select_kernel(const float4* __restrict__ 
 //                            ever recorded — a candidate is recorded at pixel x of a 2pot block iff x comes before that
 //                            block's first trigger and passes the level-1 test with dirNorm_3 > 0: the first arg-max of
 //                            dirNorm_4 over pixels with absgrad2 > TH2 (and dirNorm_4 > 0).
-// One WARP per 4pot block: lanes stride over the block's pixels in visit order; arg-max-first reductions are 64-bit
+// One group of WPB warps per 4pot block (WPB by block size, sel_group_warps): lanes stride over the block's pixels in visit order; arg-max-first reductions are 64-bit
 // atomicMax in shared memory on {float bits, ~visit index}. Two sweeps (the second needs each 2pot block's first
 // trigger). Bit-identical to select_kernel (tests/test_gpu_selector.py compares both with the oracle).
-constexpr int kSelWarps = 8;
 struct SelWarpScratch {
   unsigned long long best1[16];
   unsigned long long best3[4];
@@ -335,14 +368,17 @@ struct SelWarpScratch {
 __device__ __forceinline__ unsigned long long sel_key(float val, int v) {
   return ((unsigned long long)__float_as_uint(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)v);
 }
+template <int WPB>
 __global__ void __launch_bounds__(kSelWarps * 32) select_warp_kernel(const float4* __restrict__ pix, const float* __restrict__ thsSmoothed, SelGeom g,
                                                                     const int* __restrict__ n2Prefix, const unsigned char* __restrict__ randomPattern,
                                                                     float* __restrict__ map_out, int* __restrict__ counts) {
-  __shared__ SelWarpScratch scr[kSelWarps];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int b4 = blockIdx.x * kSelWarps + wid;
-  if (b4 >= g.nX4 * g.nY4) return;  // whole warps leave together; no block-wide barrier below
-  SelWarpScratch& S = scr[wid];
+  constexpr int GPC = kSelWarps / WPB;
+  constexpr int GT = WPB * 32;  // threads of a group
+  __shared__ SelWarpScratch scr[GPC];
+  const int grp = (threadIdx.x >> 5) / WPB, lane = threadIdx.x - grp * GT;
+  const int b4 = blockIdx.x * GPC + grp;
+  if (b4 >= g.nX4 * g.nY4) return;  // whole groups leave together; barriers below are per group
+  SelWarpScratch& S = scr[grp];
   const int pot = g.pot, w = g.w, h = g.h, pot2 = pot * pot;
   const int x4 = (b4 % g.nX4) * 4 * pot, y4 = (b4 / g.nX4) * 4 * pot;
   const float4* pix1 = pix + g.off1;
@@ -356,10 +392,10 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_warp_kernel(const float
   else if (lane < 20) dsel = randomPattern[n2Prefix[b4 * 16 + (lane - 16) * 4]] & 0xF;
   else if (lane == 20) dsel = randomPattern[n2Prefix[b4 * 16]] & 0xF;
   if (lane <= 20) { S.dir[lane][0] = kDir[dsel][0]; S.dir[lane][1] = kDir[dsel][1]; }
-  __syncwarp();
+  group_sync<WPB>(grp);
   const int nV = 16 * pot2;
   for (int sweep = 0; sweep < 2; sweep++) {
-    for (int v = lane; v < nV; v += 32) {
+    for (int v = lane; v < nV; v += GT) {
       const int B = v / (4 * pot2), r = v - B * 4 * pot2;
       const int p = r / pot2, q = r - p * pot2;
       const int y1 = q / pot, x1 = q - y1 * pot;
@@ -405,8 +441,9 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_warp_kernel(const float
         }
       }
     }
-    __syncwarp();
+    group_sync<WPB>(grp);
   }
+  if (lane >= 32) return;  // the write-out is one warp's work
   // decode a visit index back to the pixel index
   auto idx_of = [&](unsigned long long key) {
     const int v = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
@@ -438,10 +475,6 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_warp_kernel(const float
 }
 
 // makeMaps random drop (:231-249): rn = exclusive scan of (map != 0)
-__global__ void nonzero_kernel(const float* __restrict__ map, int n, int* __restrict__ flags) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flags[i] = (map[i] != 0.f) ? 1 : 0;
-}
 __global__ void subsample_kernel(float* __restrict__ map, const int* __restrict__ rn, int n, const unsigned char* __restrict__ randomPattern,
                                  int charTH, int* __restrict__ dropped) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,12 +499,6 @@ void glibc_rand_bytes(unsigned seed, int n, unsigned char* out) {
   for (size_t i = 34; i < 344 + (size_t)n; i++) r[i] = (int32_t)((uint32_t)r[i - 31] + (uint32_t)r[i - 3]);
   for (int k = 0; k < n; k++) out[k] = (unsigned char)((((uint32_t)r[344 + k]) >> 1) & 0xFF);
 }
-
-struct SelBuffers {
-  int nSlots;
-  int *selUnamb, *amb, *prefix, *ambPos, *ambList, *blockSums, *flags;
-  unsigned short* masks;
-};
 
 SelGeom make_geom(const nalo_ctx* ctx, int pot, float thFactor) {
   SelGeom g;
@@ -511,42 +538,50 @@ int run_select(nalo_ctx* ctx, int slot, int pot, float thFactor, int n3[3]) {
   const int nSlots = nB4 * 16;
   const size_t need = (size_t)nSlots * 6 + 4096;
   if (need > ctx->selScratchInts) return nalo_fail(ctx, NALO_E_ARG, "selector scratch too small for pot %d", pot);
+  // scratch (ints): prefix [nSlots] | ambList [nSlots] | masks [nSlots/2] | scanned pairs [2 nSlots] | CTA sums
   int* base = ctx->d_selScratch;
-  int* selUnamb = base;
-  int* amb = base + nSlots;
-  int* prefix = base + 2 * (size_t)nSlots;
-  int* ambPos = base + 3 * (size_t)nSlots;
-  int* ambList = base + 4 * (size_t)nSlots;
-  unsigned short* masks = reinterpret_cast<unsigned short*>(base + 5 * (size_t)nSlots);
-  int* blockSums = base + 6 * (size_t)nSlots;
-  int* counts = ctx->d_counts + 32;  // [0..2] n2,n3,n4 ; [3] nAmb ; [4] total
+  int* prefix = base;
+  int* ambList = base + nSlots;
+  unsigned short* masks = reinterpret_cast<unsigned short*>(base + 2 * (size_t)nSlots);
+  unsigned long long* scanned = reinterpret_cast<unsigned long long*>(base + 3 * (size_t)nSlots);
+  unsigned long long* blockSums = reinterpret_cast<unsigned long long*>(base + 5 * (size_t)nSlots);  // <= nSlots/1024 + 1 entries, 8-byte aligned
+  int* counts = ctx->d_counts + 32;  // [0..2] n2,n3,n4 ; [3] direction-dependent slots ; [4] label-1 total ; [6..7] 64-bit scan total
+  unsigned long long* total = reinterpret_cast<unsigned long long*>(counts + 6);
   const float4* pix = ctx->frames[slot].pix;
   const size_t n0 = (size_t)ctx->w0 * ctx->h0;
   NALO_CUDA(ctx, cudaMemsetAsync(ctx->d_map, 0, sizeof(float) * n0, ctx->stream));
   NALO_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(int) * 8, ctx->stream));
-  block_mask_kernel<<<(nSlots + 255) / 256, 256, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, nSlots, selUnamb, amb, masks);
+  const int wpb = sel_group_warps(pot);
+  const int gridB4 = (nB4 * wpb + kSelWarps - 1) / kSelWarps;
+  if (wpb == 1) block_mask_kernel<1><<<gridB4, kSelWarps * 32, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, masks);
+  else if (wpb == 4) block_mask_kernel<4><<<gridB4, kSelWarps * 32, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, masks);
+  else block_mask_kernel<8><<<gridB4, kSelWarps * 32, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, masks);
   NALO_CHECK_LAUNCH(ctx);
-  int rc = exclusive_scan(ctx, selUnamb, prefix, nSlots, blockSums, counts + 4);
-  if (rc != NALO_OK) return rc;
-  rc = exclusive_scan(ctx, amb, ambPos, nSlots, blockSums, counts + 3);
-  if (rc != NALO_OK) return rc;
-  NALO_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts + 32, counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const int nAmb = ctx->h_counts[32 + 3];
-  if (nAmb > 0) {  // rare: direction-dependent blocks — replay them in order, then rescan with their true outcome
-    amb_compact_kernel<<<(nSlots + 255) / 256, 256, 0, ctx->stream>>>(amb, ambPos, nSlots, ambList);
+  // n2 at the start of every pot block. Pass 0 counts the direction-independent selections and lists the dependent
+  // slots; resolve_kernel settles those in order; pass 1 (a no-op on the device when there were none) redoes the scan.
+  const int nb = (nSlots + 1023) / 1024;
+  for (int pass = 0; pass < 2; pass++) {
+    const int* gate = pass ? counts + 3 : nullptr;
+    scan_block_kernel<unsigned long long, LoadMaskPair><<<nb, 1024, 0, ctx->stream>>>(LoadMaskPair{masks}, scanned, blockSums, nSlots, gate);
     NALO_CHECK_LAUNCH(ctx);
-    resolve_kernel<<<1, 32, 0, ctx->stream>>>(ambList, counts + 3, prefix, masks, ctx->d_randomPattern, selUnamb);
+    scan_sums_kernel<unsigned long long><<<1, 1024, 0, ctx->stream>>>(blockSums, nb, total, gate, pass ? nullptr : counts + 3);
     NALO_CHECK_LAUNCH(ctx);
-    rc = exclusive_scan(ctx, selUnamb, prefix, nSlots, blockSums, counts + 4);
-    if (rc != NALO_OK) return rc;
+    scan_add_pair_kernel<<<nb, 1024, 0, ctx->stream>>>(scanned, blockSums, masks, nSlots, prefix, pass ? nullptr : ambList, gate);
+    NALO_CHECK_LAUNCH(ctx);
+    if (pass == 0) {
+      resolve_kernel<<<1, 32, 0, ctx->stream>>>(ambList, counts + 3, prefix, masks, ctx->d_randomPattern, (int)n0);
+      NALO_CHECK_LAUNCH(ctx);
+    }
   }
   static const bool serialSelect = getenv("NALO_SELECT_SERIAL") != nullptr;  // the verbatim one-thread-per-block replay (kept as a cross-check)
   if (serialSelect)
     select_kernel<<<(nB4 + 127) / 128, 128, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, prefix, ctx->d_randomPattern, ctx->d_map, counts);
+  else if (wpb == 1)
+    select_warp_kernel<1><<<gridB4, kSelWarps * 32, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, prefix, ctx->d_randomPattern, ctx->d_map, counts);
+  else if (wpb == 4)
+    select_warp_kernel<4><<<gridB4, kSelWarps * 32, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, prefix, ctx->d_randomPattern, ctx->d_map, counts);
   else
-    select_warp_kernel<<<(nB4 + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, prefix, ctx->d_randomPattern,
-                                                                                          ctx->d_map, counts);
+    select_warp_kernel<8><<<gridB4, kSelWarps * 32, 0, ctx->stream>>>(pix, ctx->d_thsSmoothed, g, prefix, ctx->d_randomPattern, ctx->d_map, counts);
   NALO_CHECK_LAUNCH(ctx);
   NALO_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts + 32, counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, ctx->stream));
   NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -667,14 +702,11 @@ int nalo_select_pixels(nalo_ctx* ctx, int slot, float density, int recursionsLef
   const int n0 = ctx->w0 * ctx->h0;
   if (quotia < 0.95) {
     const unsigned char charTH = (unsigned char)(255 * quotia);
-    int* flags = ctx->d_selScratch;
-    int* rn = ctx->d_selScratch + n0;
+    int* rn = ctx->d_selScratch;
     int* blockSums = ctx->d_scan;
     int* dropped = ctx->d_counts + 48;
     NALO_CUDA(ctx, cudaMemsetAsync(dropped, 0, sizeof(int), ctx->stream));
-    nonzero_kernel<<<(n0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_map, n0, flags);
-    NALO_CHECK_LAUNCH(ctx);
-    rc = exclusive_scan(ctx, flags, rn, n0, blockSums, nullptr);
+    rc = exclusive_scan(ctx, LoadNonzero{ctx->d_map}, rn, n0, blockSums, nullptr);
     if (rc != NALO_OK) return rc;
     subsample_kernel<<<(n0 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_map, rn, n0, ctx->d_randomPattern, (int)charTH, dropped);
     NALO_CHECK_LAUNCH(ctx);
