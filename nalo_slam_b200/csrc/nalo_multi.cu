@@ -178,15 +178,21 @@ static int track_multi_impl(nalo_ctx* ctx, int trk, int new_slot, float exposure
   NALO_CUDA(ctx, cudaMemcpyAsync(ctx->d_problems, ctx->h_problems, sizeof(NaloTrackProblem) * nHyp, cudaMemcpyHostToDevice, ctx->stream));
   if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evA, ctx->stream));
   // Group size: every evaluation costs a fixed ~9 us (grid-wide exchange + serial LM step) on top of its share of the
-  // points, so few large groups that each run several candidates one after the other beat one small group per candidate
-  // (measured on 31 candidates: see profiles/r01_suite.md). NALO_MULTI_G / NALO_MULTI_HELP are measurement switches.
+  // points, so few large groups that each run several candidates one after the other beat one small group per candidate:
+  // ~three candidates per group when every candidate runs to completion. With abort thresholds most candidates leave at
+  // the coarsest levels and free their group for the next one in the queue, so more, smaller groups win: 0.8 groups per
+  // candidate (30 tries with thresholds on 148 SMs: G = 14 / 8 / 6 / 5 / 4 -> 1.34 / 1.03 / 0.78 / 0.87 / 0.98 ms; to
+  // completion G = 10 / 14 / 18 / 24 -> 4.00 / 3.95 / 3.96 / 4.08 ms). Groups of <= 24 CTAs have enough points per thread
+  // for the staged (cp.async) loop to pay even though the frame pair is L2-resident (-10 % / -20 %).
+  // NALO_MULTI_G / NALO_MULTI_HELP / NALO_MULTI_STREAMED are measurement switches.
   static const int envG = getenv("NALO_MULTI_G") ? atoi(getenv("NALO_MULTI_G")) : 0;
   static const bool envHelp = getenv("NALO_MULTI_HELP") != nullptr;
   int G = ctx->maxGroups / nHyp;
-  if (nHyp > 8) G = ctx->maxGroups / ((nHyp + 2) / 3);  // ~three candidates per group, handed out through the dynamic queue
+  if (nHyp > 8) G = ctx->maxGroups / (minRes5 ? (4 * nHyp + 4) / 5 : (nHyp + 2) / 3);  // the rest is handed out through the dynamic queue
   if (envG > 0) G = envG;
   if (G < 1) G = 1;
-  static const bool envStreamed = getenv("NALO_MULTI_STREAMED") != nullptr;
+  static const char* envS = getenv("NALO_MULTI_STREAMED");
+  const bool envStreamed = envS ? atoi(envS) != 0 : (G <= 24);
   rc = nalo_track_launch(ctx, nHyp, G, ctx->d_problems, ctx->d_results, /*streamed=*/envStreamed, /*helpAll=*/envHelp);
   if (rc != NALO_OK) return rc;
   if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));

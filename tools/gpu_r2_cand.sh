@@ -1,0 +1,37 @@
+# 31 candidates as the reference's loop runs them (no early break): group size / help mode of the second launch
+cat > /tmp/cand.py <<P
+import sys, time, numpy as np
+sys.path.insert(0, '.')
+import bench
+from nalo_slam_b200 import capi, synth
+sc, ref, news, gts = bench.make_workload()
+W, H = bench.W, bench.H
+ctx = capi.Context(W, H, bench.LEVELS, device=0, max_frames=3)
+ctx.set_params(affineOptModeA=0.0, affineOptModeB=0.0)
+_, ag = ctx.make_images(0, ref, want_host=True)
+idw, ws = synth.dense_reference_maps(sc, ag[:W * H], bench.KEEP)
+ctx.make_k(0, *sc.K); ctx.set_ref_dense(0, 0, idw, ws); ctx.make_images(1, news[0])
+p_id = synth.pose_identity()
+slast = synth.se3_exp(-0.5 * np.asarray(bench.make_workload.xis[0]))
+tries = capi.motion_candidates(p_id, slast, p_id)
+aff0 = np.zeros(2)
+best = 1e9
+for rep in range(6):
+    ctx.flush_l2(); ctx.sync()
+    t0 = time.perf_counter()
+    got = ctx.track_candidates(0, 1, tries, aff0, np.zeros(5))
+    dt = (time.perf_counter() - t0) * 1e3
+    if rep: best = min(best, dt)
+if __import__('os').environ.get('MODE') == 'all':
+    best = 1e9
+    for rep in range(5):
+        ctx.flush_l2(); ctx.sync()
+        t0 = time.perf_counter()
+        res = ctx.track_multi(0, 1, tries, np.zeros((len(tries), 2)))
+        dt = (time.perf_counter() - t0) * 1e3
+        if rep: best = min(best, dt)
+    print('all: wall %.3f ms kernel %.3f' % (best, res['stats']['kernel_ms'])); sys.exit(0)
+print('wall %.3f ms  kernel %.3f ms tries %d good %d launches %d' % (best, got['stats']['kernel_ms'], got['tries'], got['good'], got['stats']['launches']))
+P
+for g in 4 5 6 7 8 10 14; do echo "== thr streamed G=$g"; NALO_MULTI_G=$g NALO_MULTI_STREAMED=1 timeout 120 python /tmp/cand.py 2>&1 | tail -1; done
+for g in 10 14 18 24; do for st in 0 1; do echo "== all-to-completion G=$g streamed=$st"; if [ $st = 1 ]; then export NALO_MULTI_STREAMED=1; else unset NALO_MULTI_STREAMED; fi; NALO_MULTI_G=$g MODE=all timeout 120 python /tmp/cand.py 2>&1 | tail -1; done; done
