@@ -342,9 +342,25 @@ typedef struct NaloLinInput {
    * PCIe rate instead of 21 + 5 B through pageable staging. */
   const float* pt4_points;
   int n_pts;
+  /* 1: state_in / energy_in are ignored; the committed state_state / state_energy of every residual stay on the device
+   * between the calls of an optimisation (uploaded by the first call of the window with state_resident = 0, advanced by
+   * nalo_ba_linearize_commit). With pt4_points, NULL per-residual outputs and nalo_ba_linearize_energy an iteration then
+   * moves ~2.8 B per residual up and 32 B down. */
+  int state_resident;
 } NaloLinInput;
 int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, float* energy, float* energy_with_outlier, float* center3,
                       float* projected16, float* rec_out);
+
+/* PointFrameResidual::applyRes (FullSystem/Residuals.cpp:306-328), the state half, on the device-resident state: residuals
+ * whose committed state is OOB keep it, all others take state_NewState / state_NewEnergy of the last nalo_ba_linearize
+ * (what applyRes_Reductor does after an accepted step, FullSystemOptimize.cpp:90-94). Asynchronous. */
+int nalo_ba_linearize_commit(nalo_ba* ba);
+
+/* Sum over all residuals of the energy the last nalo_ba_linearize returned (stats[0] of linearizeAll_Reductor,
+ * FullSystemOptimize.cpp:52-58,161-163) and the number of residuals per new state (IN, OOB, OUTLIER), summed on the device in fp64
+ * in a fixed order; counts3 nullable. (setNewFrameEnergyTH, :95-150, still wants state_NewEnergyWithOutlier of the newest
+ * frame's residuals: pass energy_with_outlier to the linearize call it follows.) */
+int nalo_ba_linearize_energy(nalo_ba* ba, double* energy_sum, int counts3[3]);
 
 /* ---- f3 (SURVEY.md §8 f, "next"): CoarseInitializer::calcResAndGS (FullSystem/CoarseInitializer.cpp:336-608) --------
  * The initializer's point set of ONE pyramid level (`Pnt`, CoarseInitializer.h:43-77) lives on the device between the

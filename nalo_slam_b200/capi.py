@@ -73,7 +73,7 @@ class NaloLinInput(C.Structure):
     _fields_ = [("n_res", C.c_int), ("nf", C.c_int), ("pt4", _P), ("color", _P), ("weights", _P), ("pack", _P), ("point", _P),
                 ("state_in", _P), ("energy_in", _P), ("pairs", _P), ("rec_init", _P),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("outlierTHSumComponent", C.c_float),
-                ("pt4_points", _P), ("n_pts", C.c_int)]
+                ("pt4_points", _P), ("n_pts", C.c_int), ("state_resident", C.c_int)]
 
 
 _lib = None
@@ -794,7 +794,7 @@ class BA:
         return out[: self.prob["n_res"]]
 
     def linearize(self, prob, slots, rec_init=None, want_proj=True, want_rec=True, outlierTHSumComponent=2500.0, reuse_static=False, want_center=True,
-                  per_point=False, pinned=None):
+                  per_point=False, pinned=None, state_resident=False, want_state=True):
         """nalo_ba_linearize on a synth.make_lin_problem dict; slots[k] = context frame slot holding frame k's pyramid.
         per_point: upload {u, v, idepth_zero, idepth} once per point (prob["pt4_points"]) instead of once per residual.
         pinned: dict of pinned arrays (pt4_points / state_in / energy_in inputs, state / energy outputs) to use instead of pageable ones."""
@@ -821,6 +821,10 @@ class BA:
         I.rec_init = None if ri is None else ri.ctypes.data
         I.fx, I.fy, I.cx, I.cy = prob["K"]
         I.outlierTHSumComponent = outlierTHSumComponent
+        I.state_resident = 1 if state_resident else 0
+        if not want_state:  # device-resident iteration: nothing per residual comes back (linearize_energy has the sum)
+            self.ctx._ck(self.L.nalo_ba_linearize(self.h_, C.byref(I), None, None, None, None, None, None))
+            return None
         st = (pinned or {}).get("state", None)
         en = (pinned or {}).get("energy", None)
         st = np.zeros(max(n, 1), dtype=np.uint8) if st is None else st
@@ -832,6 +836,15 @@ class BA:
         self.ctx._ck(self.L.nalo_ba_linearize(self.h_, C.byref(I), _ptr(st), _ptr(en), _ptr(eno), _ptr(ce), _ptr(pr), _ptr(rec)))
         return dict(state=st[:n], energy=en[:n], energy_outlier=None if eno is None else eno[:n], center=None if ce is None else ce[:n], proj=None if pr is None else pr[:n],
                     rec=None if rec is None else rec[:n])
+
+    def linearize_commit(self):
+        self.ctx._ck(self.L.nalo_ba_linearize_commit(self.h_))
+
+    def linearize_energy(self):
+        e = C.c_double(0.0)
+        c3 = np.zeros(3, dtype=np.int32)
+        self.ctx._ck(self.L.nalo_ba_linearize_energy(self.h_, C.byref(e), _ptr(c3)))
+        return float(e.value), c3
 
     def resubstitute(self, xc, xAd, useL=False):
         nP = self.prob["n_pts"]

@@ -49,6 +49,9 @@ struct nalo_ba {
   // f1 (nalo_ba_linearize) inputs/outputs, allocated on first use
   bool linAlloc = false;
   int linN = -1;                 // n_res of the static inputs (color, weights, pack, point) resident on the device
+  int linStateN = -1;            // n_res of the committed state / energy resident on the device (state_resident calls)
+  int linOutN = -1;              // n_res of the last linearize outputs (d_linState / d_linEnergy)
+  double* d_linSum = nullptr;    // [1 + CTA partials] energy sum of the last linearize
   float *d_linPt4 = nullptr, *d_linColor = nullptr, *d_linWeights = nullptr, *d_linEnergyIn = nullptr, *d_linPairs = nullptr;
   uint32_t* d_linPack = nullptr;
   int* d_linPoint = nullptr;
@@ -970,6 +973,61 @@ __global__ void resubstitute_kernel(const float* __restrict__ rec, const float* 
 // handle's device records: the accumulators that follow never see a host copy (removes the
 // 304 B/residual upload per iteration). Partial-write semantics of the reference are kept: a residual that leaves the
 // image at pattern pixel k has J's geometric part and the entries of pixels < k overwritten, the rest untouched.
+// applyRes, state half (see nalo_ba_linearize_commit)
+__global__ void lin_commit_kernel(int n, const uint8_t* __restrict__ newState, const float* __restrict__ newEnergy, uint8_t* __restrict__ state,
+                                  float* __restrict__ energy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || state[i] == 1) return;  // ResState::OOB stays
+  state[i] = newState[i];
+  energy[i] = newEnergy[i];
+}
+// {sum of energies, #IN, #OOB, #OUTLIER}: each CTA sums a contiguous range (thread-strided, then a fixed shuffle / shared tree)
+__global__ void __launch_bounds__(256) lin_energy_partial_kernel(int n, const float* __restrict__ energy, const uint8_t* __restrict__ state,
+                                                                 double* __restrict__ partial) {
+  __shared__ double sh[8][4];
+  const int per = (n + gridDim.x - 1) / gridDim.x;
+  const int lo = blockIdx.x * per, hi = min(n, lo + per);
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = lo + threadIdx.x; i < hi; i += 256) {
+    v[0] += (double)energy[i];
+    const int s = state[i];
+    v[1] += (s == 0) ? 1.0 : 0.0;
+    v[2] += (s == 1) ? 1.0 : 0.0;
+    v[3] += (s == 2) ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 4; k++) sh[threadIdx.x >> 5][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+    for (int w = 0; w < 8; w++) s += sh[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(256) lin_energy_final_kernel(int nb, const double* __restrict__ partial, double* __restrict__ out) {
+  __shared__ double sh[8][4];
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int b = threadIdx.x; b < nb; b += 256)
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] += partial[(size_t)b * 4 + k];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 4; k++) sh[threadIdx.x >> 5][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+    for (int w = 0; w < 8; w++) s += sh[w][threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+}
+
 struct LinArgs {
   int n, nf, w, h;
   float fx, fy, cx, cy, huberTH, outlierTHSum, modeA, modeB;
@@ -1240,7 +1298,7 @@ int nalo_ba_destroy(nalo_ba* ba) {
   cudaFree(ba->d_counter); cudaFree(ba->d_itemRange);
   cudaFree(ba->d_accA); cudaFree(ba->d_accL); cudaFree(ba->d_solve); cudaFree(ba->d_xs); if (ba->h_solve) cudaFreeHost(ba->h_solve);
   cudaFree(ba->d_linPt4); cudaFree(ba->d_linColor); cudaFree(ba->d_linWeights); cudaFree(ba->d_linEnergyIn); cudaFree(ba->d_linPairs);
-  cudaFree(ba->d_linPack); cudaFree(ba->d_linPoint); cudaFree(ba->d_linStateIn); cudaFree(ba->d_linState); cudaFree(ba->d_linEnergy);
+  cudaFree(ba->d_linPack); cudaFree(ba->d_linPoint); cudaFree(ba->d_linSum); cudaFree(ba->d_linStateIn); cudaFree(ba->d_linState); cudaFree(ba->d_linEnergy);
   cudaFree(ba->d_linEnergyOut); cudaFree(ba->d_linCenter); cudaFree(ba->d_linProj);
   delete ba;
   return NALO_OK;
@@ -1492,6 +1550,8 @@ int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, f
   // color / weights / pack / point are static per window: NULL = reuse what the previous call uploaded (same n_res)
   const bool reuse = !in->color || !in->weights || !in->pack || !in->point;
   if (reuse && (!ba->linAlloc || ba->linN != n)) return nalo_fail(ctx, NALO_E_STATE, "nalo_ba_linearize: static inputs omitted but none of matching size are resident");
+  if (in->state_resident && (!ba->linAlloc || ba->linStateN != n))
+    return nalo_fail(ctx, NALO_E_STATE, "nalo_ba_linearize: state_resident, but no state / energy of %d residuals is resident (run a call with state_in first)", n);
   NALO_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   if (!ba->linAlloc) {
@@ -1532,10 +1592,13 @@ int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, f
       NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPoint, in->point, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
       ba->linN = n;
     }
-    if (in->state_in) NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linStateIn, in->state_in, (size_t)n, cudaMemcpyHostToDevice, st));
-    else NALO_CUDA(ctx, cudaMemsetAsync(ba->d_linStateIn, 0, (size_t)n, st));
-    if (in->energy_in) NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linEnergyIn, in->energy_in, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
-    else NALO_CUDA(ctx, cudaMemsetAsync(ba->d_linEnergyIn, 0, sizeof(float) * (size_t)n, st));
+    if (!in->state_resident) {  // (resident: the committed state_state / state_energy of the previous calls stay where they are)
+      if (in->state_in) NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linStateIn, in->state_in, (size_t)n, cudaMemcpyHostToDevice, st));
+      else NALO_CUDA(ctx, cudaMemsetAsync(ba->d_linStateIn, 0, (size_t)n, st));
+      if (in->energy_in) NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linEnergyIn, in->energy_in, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+      else NALO_CUDA(ctx, cudaMemsetAsync(ba->d_linEnergyIn, 0, sizeof(float) * (size_t)n, st));
+      ba->linStateN = n;
+    }
   }
   NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_linPairs, in->pairs, sizeof(float) * 32 * nf * nf, cudaMemcpyHostToDevice, st));
   if (in->rec_init && n > 0) NALO_CUDA(ctx, cudaMemcpyAsync(ba->d_rec, in->rec_init, sizeof(float) * REC * (size_t)n, cudaMemcpyHostToDevice, st));
@@ -1561,8 +1624,48 @@ int nalo_ba_linearize(nalo_ba* ba, const NaloLinInput* in, uint8_t* new_state, f
     if (rec_out) NALO_CUDA(ctx, cudaMemcpyAsync(rec_out, ba->d_rec, sizeof(float) * REC * (size_t)n, cudaMemcpyDeviceToHost, st));
   }
   NALO_CUDA(ctx, cudaStreamSynchronize(st));
+  ba->linOutN = n;
   // the records changed under the accumulators: per-point sums, JpJdF have to be recomputed
   ba->haveA = ba->haveL = ba->haveJpJd = ba->haveJpJdDev = ba->haveSC = ba->haveX = false;
+  return NALO_OK;
+}
+
+// PointFrameResidual::applyRes (Residuals.cpp:306-328), the state half: residuals whose committed state is OOB keep it
+// ("can never go back from OOB"), all others take state_NewState / state_NewEnergy of the last nalo_ba_linearize.
+int nalo_ba_linearize_commit(nalo_ba* ba) {
+  if (!ba) return NALO_E_ARG;
+  nalo_ctx* ctx = ba->ctx;
+  if (!ba->linAlloc || ba->linOutN < 0 || ba->linStateN != ba->linOutN)
+    return nalo_fail(ctx, NALO_E_STATE, "nalo_ba_linearize_commit: no linearize outputs matching the resident state");
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int n = ba->linOutN;
+  if (n > 0) {
+    lin_commit_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ba->d_linState, ba->d_linEnergy, ba->d_linStateIn, ba->d_linEnergyIn);
+    NALO_CHECK_LAUNCH(ctx);
+  }
+  return NALO_OK;
+}
+
+// Sum of the energies the last nalo_ba_linearize returned per residual (what linearizeAll_Reductor adds up in stats[0],
+// FullSystemOptimize.cpp:52-58,161-163) and the number of residuals per new state, without reading the per-residual arrays back.
+// fp64, fixed summation tree (CTA partials in index order) => the same bits on every run.
+int nalo_ba_linearize_energy(nalo_ba* ba, double* energy_sum, int counts3[3]) {
+  if (!ba || !energy_sum) return NALO_E_ARG;
+  nalo_ctx* ctx = ba->ctx;
+  if (!ba->linAlloc || ba->linOutN < 0) return nalo_fail(ctx, NALO_E_STATE, "nalo_ba_linearize_energy before nalo_ba_linearize");
+  NALO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int n = ba->linOutN;
+  const int nb = std::max(1, std::min(1024, (n + 1023) / 1024));
+  if (!ba->d_linSum) NALO_CUDA(ctx, cudaMalloc(&ba->d_linSum, sizeof(double) * 4 * (1024 + 1)));
+  lin_energy_partial_kernel<<<nb, 256, 0, ctx->stream>>>(n, ba->d_linEnergy, ba->d_linState, ba->d_linSum + 4);
+  NALO_CHECK_LAUNCH(ctx);
+  lin_energy_final_kernel<<<1, 256, 0, ctx->stream>>>(nb, ba->d_linSum + 4, ba->d_linSum);
+  NALO_CHECK_LAUNCH(ctx);
+  double out[4];
+  NALO_CUDA(ctx, cudaMemcpyAsync(out, ba->d_linSum, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
+  NALO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *energy_sum = out[0];
+  if (counts3) for (int k = 0; k < 3; k++) counts3[k] = (int)out[1 + k];
   return NALO_OK;
 }
 

@@ -139,3 +139,80 @@ def test_linearize_per_point_upload_and_pinned_buffers(oracle):
         ba.close()
     finally:
         ctx.close()
+
+
+def test_linearize_resident_state_across_iterations(oracle):
+    """An optimisation as FullSystem::optimize drives it (FullSystemOptimize.cpp:52-94,161-163): linearizeAll, a step on the
+    inverse depths, linearizeAll again, applyRes after the accepted step, a third linearizeAll. With state_resident the
+    committed state_state / state_energy never leave the device (nalo_ba_linearize_commit = applyRes's state half) and only
+    the energy sum comes back (nalo_ba_linearize_energy) - bit-identical to carrying the state through the host, and equal
+    to the CPU oracle fed the same way."""
+    w, h, L, nf = 640, 384, 4, 5
+    sc, P, ctx, dIs = _setup(oracle, w, h, L, nf, 900, seed=8)
+    try:
+        n, npts = P["n_res"], P["n_pts"]
+        pts = np.zeros((npts, 4), dtype=np.float32)
+        pts[P["point"]] = P["pt4"]
+        rng = np.random.default_rng(4)
+        state0 = (rng.random(n) < 0.05).astype(np.uint8)            # some residuals start OOB ("can never go back")
+        energy0 = rng.uniform(0, 50, n).astype(np.float32)
+        zero = np.zeros((n, 76), dtype=np.float32)
+
+        def problem(pts_k, st, en):
+            return dict(P, pt4=np.ascontiguousarray(pts_k[P["point"]]), pt4_points=pts_k, state_in=st, energy_in=en)
+
+        def apply_res(st, en, out):  # Residuals.cpp:306-328
+            keep = st == 1
+            return np.where(keep, st, out["state"]).astype(np.uint8), np.where(keep, en, out["energy"]).astype(np.float32)
+
+        steps = [pts]
+        for k in range(2):  # two steps on idepth (column 3), as doStep applies them
+            q = steps[-1].copy()
+            q[:, 3] = (q[:, 3] * (1.0 + 0.02 * rng.standard_normal(npts))).astype(np.float32)
+            steps.append(q)
+
+        # ---- host-carried reference sequence on the device and on the oracle
+        ba = capi.BA(ctx, n + 16, npts + 16)
+        st, en = state0, energy0
+        host_out, orc_out = [], []
+        for k, q in enumerate(steps):
+            Pk = problem(q, st, en)
+            a = ba.linearize(Pk, list(range(nf)), rec_init=zero if k == 0 else None, per_point=True, reuse_static=k > 0)
+            host_out.append(a)
+            orc_out.append(oracle.linearize(Pk, dIs, rec_init=zero if k == 0 else orc_out[-1]["rec"]))
+            if k >= 1:  # the step that led to iteration k is accepted
+                st, en = apply_res(st, en, a)
+        ba.close()
+
+        # ---- the same with the state resident on the device
+        ba = capi.BA(ctx, n + 16, npts + 16)
+        sums = []
+        for k, q in enumerate(steps):
+            Pk = problem(q, state0, energy0)
+            if k < len(steps) - 1:
+                ba.linearize(Pk, list(range(nf)), rec_init=zero if k == 0 else None, per_point=True, reuse_static=k > 0, state_resident=k > 0,
+                             want_state=False)
+                b = None
+            else:  # last iteration: read everything back for the comparison
+                b = ba.linearize(Pk, list(range(nf)), per_point=True, reuse_static=True, state_resident=True)
+            e, c3 = ba.linearize_energy()
+            sums.append((e, c3))
+            if k >= 1:
+                ba.linearize_commit()
+        for k in ("state", "energy", "energy_outlier", "center", "rec"):
+            x, y = host_out[-1][k], b[k]
+            assert np.array_equal(_bits(x) if x.dtype == np.float32 else x, _bits(y) if y.dtype == np.float32 else y), k
+        assert np.array_equal(b["state"], orc_out[-1]["state"]) and np.array_equal(_bits(b["rec"]), _bits(orc_out[-1]["rec"]))
+        for k, (e, c3) in enumerate(sums):
+            ref = host_out[k]
+            assert abs(e - float(np.sum(ref["energy"].astype(np.float64)))) <= 1e-9 * max(1.0, abs(e)), k
+            assert [int((ref["state"] == s).sum()) for s in (0, 1, 2)] == list(c3), k
+        assert (b["state"] == 1).sum() >= (state0 == 1).sum() > 0
+        # a resident call without a resident state of that size is refused
+        ba2 = capi.BA(ctx, n + 16, npts + 16)
+        with pytest.raises(capi.NaloError):
+            ba2.linearize(problem(pts, state0, energy0), list(range(nf)), rec_init=zero, per_point=True, state_resident=True)
+        ba2.close()
+        ba.close()
+    finally:
+        ctx.close()

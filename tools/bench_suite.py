@@ -432,6 +432,19 @@ def main():
                                                   per_point=True, pinned=pin), reps=8)
         add(f"f1 linearize nres={nres}, per-point upload + pinned buffers", d, wl, (16 + 64 + 8 + 5 + 304 + 21) * nres, nres, "residual", c, 1,
             f"per iteration: H2D {16 * Pl['n_pts'] / nres + 5:.1f} B/res (pt4 per point, state, energy) + D2H 5 B/res, pinned; static point data resident")
+        # the committed state / energy stay on the device (state_resident), only the energy sum comes back
+        pinr = dict(pt4_points=pin["pt4_points"])
+
+        def f_res(i):
+            bal.linearize(Pl2, list(range(7)), want_proj=False, want_rec=False, reuse_static=True, want_center=False, per_point=True, pinned=pinr,
+                          state_resident=True, want_state=False)
+            e, _ = bal.linearize_energy()
+            bal.linearize_commit()
+            return e
+
+        d, wl, _ = Tl.run(f_res, reps=8)
+        add(f"f1 linearize nres={nres}, state resident on the device + energy sum + applyRes", d, wl, (16 + 64 + 8 + 5 + 304 + 21) * nres, nres, "residual", c, 1,
+            f"per iteration: H2D {16 * Pl['n_pts'] / nres:.1f} B/res (pt4 per point, pinned), D2H 32 B in total")
         bal.close()
         ctxl.close()
 
