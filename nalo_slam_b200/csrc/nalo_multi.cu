@@ -182,8 +182,9 @@ static int track_multi_impl(nalo_ctx* ctx, int trk, int new_slot, float exposure
   // ~three candidates per group when every candidate runs to completion. With abort thresholds most candidates leave at
   // the coarsest levels and free their group for the next one in the queue, so more, smaller groups win: 0.8 groups per
   // candidate (30 tries with thresholds on 148 SMs: G = 14 / 8 / 6 / 5 / 4 -> 1.34 / 1.03 / 0.78 / 0.87 / 0.98 ms; to
-  // completion G = 10 / 14 / 18 / 24 -> 4.00 / 3.95 / 3.96 / 4.08 ms). Groups of <= 24 CTAs have enough points per thread
-  // for the staged (cp.async) loop to pay even though the frame pair is L2-resident (-10 % / -20 %).
+  // completion G = 10 / 14 / 18 / 24 -> 4.00 / 3.95 / 3.96 / 4.08 ms). Groups of up to ~56 CTAs have enough points per thread
+  // for the staged (cp.async) loop to pay even though the frame pair is L2-resident (one candidate, plain / staged loop:
+  // G = 18: 0.418 / 0.359 ms, 37: 0.306 / 0.290, 56: 0.275 / 0.269, 74: 0.259 / 0.261, 148: 0.241 / 0.254).
   // NALO_MULTI_G / NALO_MULTI_HELP / NALO_MULTI_STREAMED are measurement switches.
   static const int envG = getenv("NALO_MULTI_G") ? atoi(getenv("NALO_MULTI_G")) : 0;
   static const bool envHelp = getenv("NALO_MULTI_HELP") != nullptr;
@@ -192,7 +193,7 @@ static int track_multi_impl(nalo_ctx* ctx, int trk, int new_slot, float exposure
   if (envG > 0) G = envG;
   if (G < 1) G = 1;
   static const char* envS = getenv("NALO_MULTI_STREAMED");
-  const bool envStreamed = envS ? atoi(envS) != 0 : (G <= 24);
+  const bool envStreamed = envS ? atoi(envS) != 0 : (G <= 56);
   rc = nalo_track_launch(ctx, nHyp, G, ctx->d_problems, ctx->d_results, /*streamed=*/envStreamed, /*helpAll=*/envHelp);
   if (rc != NALO_OK) return rc;
   if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));
