@@ -472,7 +472,8 @@ static int frames_enqueue(nalo_ctx* ctx, nalo_ctx::FramesBuf& B, int trk, int n,
     static const char* envG = getenv("NALO_FRAMES_G");        // measurement switches
     static const char* envH = getenv("NALO_FRAMES_HELP");
     if (envG && atoi(envG) > 0) G = atoi(envG);
-    rc = nalo_track_launch(ctx, cnt, G, B.d_prob + lo, B.d_res + lo, streamed, /*helpAll=*/envH && atoi(envH) > 0);
+    // (groups of up to ~56 CTAs: the staged loop pays even for L2-resident frames, see track_multi_impl)
+    rc = nalo_track_launch(ctx, cnt, G, B.d_prob + lo, B.d_res + lo, streamed || G <= 56, /*helpAll=*/envH && atoi(envH) > 0);
     if (rc != NALO_OK) return rc;
   }
   if (timing) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));
