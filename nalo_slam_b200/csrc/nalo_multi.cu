@@ -180,16 +180,18 @@ static int track_multi_impl(nalo_ctx* ctx, int trk, int new_slot, float exposure
   // Group size: every evaluation costs a fixed ~9 us (grid-wide exchange + serial LM step) on top of its share of the
   // points, so few large groups that each run several candidates one after the other beat one small group per candidate:
   // ~three candidates per group when every candidate runs to completion. With abort thresholds most candidates leave at
-  // the coarsest levels and free their group for the next one in the queue, so more, smaller groups win: 0.8 groups per
-  // candidate (30 tries with thresholds on 148 SMs: G = 14 / 8 / 6 / 5 / 4 -> 1.34 / 1.03 / 0.78 / 0.87 / 0.98 ms; to
-  // completion G = 10 / 14 / 18 / 24 -> 4.00 / 3.95 / 3.96 / 4.08 ms). Groups of up to ~56 CTAs have enough points per thread
+  // the coarsest levels, where an evaluation is pure exchange latency, so every candidate gets its own group at once as
+  // long as that leaves the group >= 6 CTAs for the survivors' fine levels (30 tries with thresholds on 148 SMs:
+  // G = 14 / 8 / 6 / 5 / 4 -> 1.34 / 1.03 / 0.78 / 0.87 / 0.98 ms; 15 tries: G = 12 / 10 / 9 / 8 / 6 -> 0.98 / 0.73 / 0.65 /
+  // 0.69 / 0.78; 10 tries: G = 14 / 12 / 10 / 8 -> 0.55 / 0.57 / 0.61 / 0.68; to completion G = 10 / 14 / 18 / 24 ->
+  // 4.00 / 3.95 / 3.96 / 4.08 ms). Groups of up to ~56 CTAs have enough points per thread
   // for the staged (cp.async) loop to pay even though the frame pair is L2-resident (one candidate, plain / staged loop:
   // G = 18: 0.418 / 0.359 ms, 37: 0.306 / 0.290, 56: 0.275 / 0.269, 74: 0.259 / 0.261, 148: 0.241 / 0.254).
   // NALO_MULTI_G / NALO_MULTI_HELP / NALO_MULTI_STREAMED are measurement switches.
   static const int envG = getenv("NALO_MULTI_G") ? atoi(getenv("NALO_MULTI_G")) : 0;
   static const bool envHelp = getenv("NALO_MULTI_HELP") != nullptr;
   int G = ctx->maxGroups / nHyp;
-  if (nHyp > 8) G = ctx->maxGroups / (minRes5 ? (4 * nHyp + 4) / 5 : (nHyp + 2) / 3);  // the rest is handed out through the dynamic queue
+  if (nHyp > 8) G = minRes5 ? std::max(6, ctx->maxGroups / nHyp) : ctx->maxGroups / ((nHyp + 2) / 3);  // the rest is handed out through the dynamic queue
   if (envG > 0) G = envG;
   if (G < 1) G = 1;
   static const char* envS = getenv("NALO_MULTI_STREAMED");

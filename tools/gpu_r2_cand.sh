@@ -22,6 +22,18 @@ for rep in range(6):
     got = ctx.track_candidates(0, 1, tries, aff0, np.zeros(5))
     dt = (time.perf_counter() - t0) * 1e3
     if rep: best = min(best, dt)
+if __import__('os').environ.get('MODE', '').startswith('t'):
+    k = int(__import__('os').environ['MODE'][1:])
+    r0 = ctx.track_multi(0, 1, tries[:1], np.zeros((1, 2)))
+    w0 = capi.winner_rule(r0, aff0, np.zeros(5))
+    best = 1e9
+    for rep in range(6):
+        ctx.flush_l2(); ctx.sync()
+        t0 = time.perf_counter()
+        res = ctx.track_multi_thr(0, 1, tries[1:1 + k], np.zeros((k, 2)), w0['achievedRes'])
+        dt = (time.perf_counter() - t0) * 1e3
+        if rep: best = min(best, dt)
+    print('%d tries with thresholds: wall %.3f ms kernel %.3f' % (k, best, res['stats']['kernel_ms'])); sys.exit(0)
 if __import__('os').environ.get('MODE', '').startswith('n'):
     k = int(__import__('os').environ['MODE'][1:])
     best = 1e9
@@ -43,4 +55,5 @@ if __import__('os').environ.get('MODE') == 'all':
     print('all: wall %.3f ms kernel %.3f' % (best, res['stats']['kernel_ms'])); sys.exit(0)
 print('wall %.3f ms  kernel %.3f ms tries %d good %d launches %d' % (best, got['stats']['kernel_ms'], got['tries'], got['good'], got['stats']['launches']))
 P
-for g in 148 111 74 56 49 37 30 24 18; do for st in 0 1; do echo "== 1 try G=$g streamed=$st"; NALO_MULTI_G=$g NALO_MULTI_STREAMED=$st MODE=n1 timeout 120 python /tmp/cand.py 2>&1 | tail -1; done; done
+for k in 15 10; do for g in 6 8 9 10 12 14; do echo "== $k tries thr G=$g"; NALO_MULTI_G=$g MODE=t$k timeout 120 python /tmp/cand.py 2>&1 | tail -1; done; done
+for g in 4 5 6 7 8; do echo "== 30 tries thr G=$g"; NALO_MULTI_G=$g MODE=t30 timeout 120 python /tmp/cand.py 2>&1 | tail -1; done
