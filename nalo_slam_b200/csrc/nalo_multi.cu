@@ -191,7 +191,10 @@ static int track_multi_impl(nalo_ctx* ctx, int trk, int new_slot, float exposure
   static const int envG = getenv("NALO_MULTI_G") ? atoi(getenv("NALO_MULTI_G")) : 0;
   static const bool envHelp = getenv("NALO_MULTI_HELP") != nullptr;
   int G = ctx->maxGroups / nHyp;
-  if (nHyp > 8) G = minRes5 ? std::max(6, ctx->maxGroups / nHyp) : ctx->maxGroups / ((nHyp + 2) / 3);  // the rest is handed out through the dynamic queue
+  if (nHyp > 8) {
+    if (minRes5) G = std::max(6, G);
+    else if (G < 9) G = ctx->maxGroups / ((nHyp + 2) / 3);  // (16 tries to completion: G = 9 / 12 / 18 / 24 -> 1.15 / 1.42 / 1.26 / 1.44 ms)
+  }  // the candidates beyond the number of groups are handed out through the dynamic queue
   if (envG > 0) G = envG;
   if (G < 1) G = 1;
   static const char* envS = getenv("NALO_MULTI_STREAMED");

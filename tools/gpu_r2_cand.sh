@@ -55,5 +55,5 @@ if __import__('os').environ.get('MODE') == 'all':
     print('all: wall %.3f ms kernel %.3f' % (best, res['stats']['kernel_ms'])); sys.exit(0)
 print('wall %.3f ms  kernel %.3f ms tries %d good %d launches %d' % (best, got['stats']['kernel_ms'], got['tries'], got['good'], got['stats']['launches']))
 P
-for k in 15 10; do for g in 6 8 9 10 12 14; do echo "== $k tries thr G=$g"; NALO_MULTI_G=$g MODE=t$k timeout 120 python /tmp/cand.py 2>&1 | tail -1; done; done
-for g in 4 5 6 7 8; do echo "== 30 tries thr G=$g"; NALO_MULTI_G=$g MODE=t30 timeout 120 python /tmp/cand.py 2>&1 | tail -1; done
+for g in 4 5 6 8 10 14; do echo "== 31 to completion G=$g"; NALO_MULTI_G=$g MODE=all timeout 120 python /tmp/cand.py 2>&1 | tail -1; done
+for g in 9 12 18 24; do echo "== 16 to completion G=$g"; NALO_MULTI_G=$g MODE=n16 timeout 120 python /tmp/cand.py 2>&1 | tail -1; done
