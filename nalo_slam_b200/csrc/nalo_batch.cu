@@ -133,6 +133,7 @@ int store_pair(nalo_batch* b, int i, float fx, float fy, float cx, float cy) {
   float4* img = b->d_img + (size_t)i * ctx->totPix;
   NALO_CUDA(ctx, cudaMemcpyAsync(img, ctx->frames[1].pix, sizeof(float4) * (size_t)ctx->totPix, cudaMemcpyDeviceToDevice, ctx->stream));
   P.img = img;
+  P.streamPts = 1;
   P.refAff[0] = P.refAff[1] = 0.0;
   P.refExposure = P.newExposure = 1.f;
   P.useAbort = 0;

@@ -69,7 +69,7 @@ struct NaloTrackProblem {
   //  levelCutoffRepeat, |inc|}
   double* trace;
   int traceCap;
-  int padTrace;
+  int streamPts;  // 1: this problem's reference cloud is its own (batched pairs) and streams from HBM: prefetch it into L2 ahead of the ring
 };
 
 struct NaloTrackResult {
