@@ -184,9 +184,10 @@ static int track_multi_impl(nalo_ctx* ctx, int trk, int new_slot, float exposure
   // long as that leaves the group >= 6 CTAs for the survivors' fine levels (30 tries with thresholds on 148 SMs:
   // G = 14 / 8 / 6 / 5 / 4 -> 1.34 / 1.03 / 0.78 / 0.87 / 0.98 ms; 15 tries: G = 12 / 10 / 9 / 8 / 6 -> 0.98 / 0.73 / 0.65 /
   // 0.69 / 0.78; 10 tries: G = 14 / 12 / 10 / 8 -> 0.55 / 0.57 / 0.61 / 0.68; to completion G = 10 / 14 / 18 / 24 ->
-  // 4.00 / 3.95 / 3.96 / 4.08 ms). Groups of up to ~56 CTAs have enough points per thread
-  // for the staged (cp.async) loop to pay even though the frame pair is L2-resident (one candidate, plain / staged loop:
-  // G = 18: 0.418 / 0.359 ms, 37: 0.306 / 0.290, 56: 0.275 / 0.269, 74: 0.259 / 0.261, 148: 0.241 / 0.254).
+  // 4.00 / 3.95 / 3.96 / 4.08 ms). Groups of up to ~20 CTAs have enough points per thread
+  // for the staged (cp.async) loop to pay even though the frame pair is L2-resident (plain / staged kernel, final code:
+  // 30 tries with thresholds G = 6: 0.95 / 0.79 ms, 15 tries G = 9: 0.76 / 0.67, 10 tries G = 14: 0.61 / 0.58, 8 tries to
+  // completion G = 18: 0.51 / 0.49, 6 tries G = 24: 0.46 / 0.47, one try G = 37: 0.29 / 0.31, 148: 0.22 / 0.28).
   // NALO_MULTI_G / NALO_MULTI_HELP / NALO_MULTI_STREAMED are measurement switches.
   static const int envG = getenv("NALO_MULTI_G") ? atoi(getenv("NALO_MULTI_G")) : 0;
   static const bool envHelp = getenv("NALO_MULTI_HELP") != nullptr;
@@ -198,7 +199,7 @@ static int track_multi_impl(nalo_ctx* ctx, int trk, int new_slot, float exposure
   if (envG > 0) G = envG;
   if (G < 1) G = 1;
   static const char* envS = getenv("NALO_MULTI_STREAMED");
-  const bool envStreamed = envS ? atoi(envS) != 0 : (G <= 56);
+  const bool envStreamed = envS ? atoi(envS) != 0 : (G <= 20);
   rc = nalo_track_launch(ctx, nHyp, G, ctx->d_problems, ctx->d_results, /*streamed=*/envStreamed, /*helpAll=*/envHelp);
   if (rc != NALO_OK) return rc;
   if (stats) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));
@@ -477,8 +478,8 @@ static int frames_enqueue(nalo_ctx* ctx, nalo_ctx::FramesBuf& B, int trk, int n,
     static const char* envG = getenv("NALO_FRAMES_G");        // measurement switches
     static const char* envH = getenv("NALO_FRAMES_HELP");
     if (envG && atoi(envG) > 0) G = atoi(envG);
-    // (groups of up to ~56 CTAs: the staged loop pays even for L2-resident frames, see track_multi_impl)
-    rc = nalo_track_launch(ctx, cnt, G, B.d_prob + lo, B.d_res + lo, streamed || G <= 56, /*helpAll=*/envH && atoi(envH) > 0);
+    // (groups of up to ~20 CTAs: the staged loop pays even for L2-resident frames, see track_multi_impl)
+    rc = nalo_track_launch(ctx, cnt, G, B.d_prob + lo, B.d_res + lo, streamed || G <= 20, /*helpAll=*/envH && atoi(envH) > 0);
     if (rc != NALO_OK) return rc;
   }
   if (timing) NALO_CUDA(ctx, cudaEventRecord(ctx->evB, ctx->stream));

@@ -55,5 +55,12 @@ if __import__('os').environ.get('MODE') == 'all':
     print('all: wall %.3f ms kernel %.3f' % (best, res['stats']['kernel_ms'])); sys.exit(0)
 print('wall %.3f ms  kernel %.3f ms tries %d good %d launches %d' % (best, got['stats']['kernel_ms'], got['tries'], got['good'], got['stats']['launches']))
 P
-for g in 4 5 6 8 10 14; do echo "== 31 to completion G=$g"; NALO_MULTI_G=$g MODE=all timeout 120 python /tmp/cand.py 2>&1 | tail -1; done
-for g in 9 12 18 24; do echo "== 16 to completion G=$g"; NALO_MULTI_G=$g MODE=n16 timeout 120 python /tmp/cand.py 2>&1 | tail -1; done
+for st in 0 1; do
+echo "== streamed=$st: 30 thr G=6"; NALO_MULTI_G=6 NALO_MULTI_STREAMED=$st MODE=t30 timeout 120 python /tmp/cand.py 2>&1 | tail -1
+echo "== streamed=$st: 15 thr G=9"; NALO_MULTI_G=9 NALO_MULTI_STREAMED=$st MODE=t15 timeout 120 python /tmp/cand.py 2>&1 | tail -1
+echo "== streamed=$st: 10 thr G=14"; NALO_MULTI_G=14 NALO_MULTI_STREAMED=$st MODE=t10 timeout 120 python /tmp/cand.py 2>&1 | tail -1
+echo "== streamed=$st: 8 to completion G=18"; NALO_MULTI_G=18 NALO_MULTI_STREAMED=$st MODE=n8 timeout 120 python /tmp/cand.py 2>&1 | tail -1
+echo "== streamed=$st: 6 to completion G=24"; NALO_MULTI_G=24 NALO_MULTI_STREAMED=$st MODE=n6 timeout 120 python /tmp/cand.py 2>&1 | tail -1
+echo "== streamed=$st: 31 to completion G=13"; NALO_MULTI_G=13 NALO_MULTI_STREAMED=$st MODE=all timeout 120 python /tmp/cand.py 2>&1 | tail -1
+echo "== streamed=$st: 16 to completion G=9"; NALO_MULTI_G=9 NALO_MULTI_STREAMED=$st MODE=n16 timeout 120 python /tmp/cand.py 2>&1 | tail -1
+done
