@@ -12,6 +12,7 @@
 //   nalo::AccumulatedTopHessian           setZero / addPointsInternal<mode> / stitchDoubleMT-shaped calls (a9)
 //   nalo::AccumulatedSCHessian            setZero / addPointsInternal / stitchDoubleMT-shaped calls (a10)
 //   nalo::BAWindow                        owns the nalo_ba handle and the flattened problem of one window
+//   nalo::linearizeInputs / linearizeAll  f1: FullSystem::linearizeAll on the device (inputs read through the same graph)
 // Everything is templated on the reference's own types (dso::EFFrame, EFPoint, EFResidual, RawResidualJacobian, Mat88,
 // MatXX, VecX ...), so the header needs neither Eigen nor the reference to be included itself: it only uses member
 // names, operator[] / operator()(r, c) and, for the dynamic outputs, T::Zero(rows, cols) / T::Zero(n).
@@ -157,6 +158,149 @@ class BAWindow {
   nalo_ba* ba_ = nullptr;
   FlatEF<EFResidualT, EFPointT> flat_;
 };
+
+// ---- f1: FullSystem::linearizeAll (FullSystemOptimize.cpp:52-94,141-200) on the device ---------------------------------
+// linearizeAll_Reductor calls PointFrameResidual::linearize (Residuals.cpp:78-274) for every active residual; the inputs it
+// reads through the pointer graph are flattened here in the RECORD ORDER of the FlatEF the window was uploaded with
+// (EFResidual::data -> PointFrameResidual, EFPoint::data -> PointHessian, EFFrame::data -> FrameHessian), so the records
+// nalo_ba_linearize writes on the device are the ones the accumulators of this header read next.
+//   PointHessian           u, v, idepth_zero_scaled, idepth_scaled, color[8], weights[8]            HessianBlocks.h:402-456
+//   PointFrameResidual     state_state, state_energy (in); state_NewState, state_NewEnergy,
+//                          state_NewEnergyWithOutlier, centerProjectedTo, projectedTo[8] (out)      Residuals.h:52-90
+//   FrameHessian           idx, frameEnergyTH, targetPrecalc[target->idx].{PRE_RTll_0, PRE_tTll_0,
+//                          PRE_KRKiTll, PRE_KtTll, PRE_aff_mode, PRE_b0_mode}                       HessianBlocks.h:84-110,192-222
+template <class EFResidualT, class EFPointT>
+struct FlatLin {
+  int nf = 0;
+  std::vector<float> pt4_points;   // [n_pts][4]
+  std::vector<float> color, weights;  // [n_res][8]
+  std::vector<uint32_t> pack;      // [n_res]
+  std::vector<int> point;          // [n_res]
+  std::vector<uint8_t> state_in;   // [n_res]
+  std::vector<float> energy_in;    // [n_res]
+  std::vector<float> pairs;        // [nf*nf][32]
+  float fx = 0, fy = 0, cx = 0, cy = 0, outlierTHSumComponent = 50.f * 50.f;
+  bool staticResident = false, stateResident = false;  // what the device already holds (set by BAWindow-level calls below)
+  NaloLinInput input() const {
+    NaloLinInput in;
+    std::memset(&in, 0, sizeof(in));
+    in.n_res = (int)pack.size(); in.nf = nf;
+    in.pt4_points = pt4_points.data(); in.n_pts = (int)(pt4_points.size() / 4);
+    if (!staticResident) { in.color = color.data(); in.weights = weights.data(); in.pack = pack.data(); in.point = point.data(); }
+    in.state_in = state_in.data(); in.energy_in = energy_in.data();
+    in.state_resident = stateResident ? 1 : 0;
+    in.pairs = pairs.data();
+    in.fx = fx; in.fy = fy; in.cx = cx; in.cy = cy; in.outlierTHSumComponent = outlierTHSumComponent;
+    return in;
+  }
+};
+
+// The per-iteration part of the inputs: point values (doStepFromBackup changed idepth_scaled), the FrameFramePrecalc table
+// (setPrecalcValues after every step) and, unless they stay on the device, state_state / state_energy.
+// slot_of_frame[k]: context frame slot that holds the pyramid of window frame k (FrameHessian::idx == k).
+template <class EFResidualT, class EFPointT, class EFFrameT>
+inline void refreshLinearizeInputs(FlatLin<EFResidualT, EFPointT>& L, const FlatEF<EFResidualT, EFPointT>& F, const std::vector<EFFrameT*>& frames,
+                                   const int* slot_of_frame) {
+  const int nf = F.nf;
+  for (int p = 0; p < F.n_pts(); p++) {
+    const auto* ph = F.points[p]->data;
+    float* o = L.pt4_points.data() + 4 * (size_t)p;
+    o[0] = ph->u; o[1] = ph->v; o[2] = ph->idepth_zero_scaled; o[3] = ph->idepth_scaled;
+  }
+  for (int i = 0; i < F.n_res(); i++) {
+    const auto* r = F.residual_of_record[i]->data;
+    L.state_in[i] = (uint8_t)r->state_state;
+    L.energy_in[i] = (float)r->state_energy;
+  }
+  for (int h = 0; h < nf; h++) {
+    const auto* host = frames[h]->data;
+    for (int t = 0; t < nf; t++) {
+      const auto* target = frames[t]->data;
+      const auto& pc = host->targetPrecalc[target->idx];
+      float* P = L.pairs.data() + (size_t)(h + t * nf) * 32;
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) { P[3 * r + c] = pc.PRE_RTll_0(r, c); P[12 + 3 * r + c] = pc.PRE_KRKiTll(r, c); }
+      for (int r = 0; r < 3; r++) { P[9 + r] = pc.PRE_tTll_0[r]; P[21 + r] = pc.PRE_KtTll[r]; }
+      P[24] = pc.PRE_aff_mode[0]; P[25] = pc.PRE_aff_mode[1];
+      P[26] = pc.PRE_b0_mode;
+      P[27] = host->frameEnergyTH > target->frameEnergyTH ? host->frameEnergyTH : target->frameEnergyTH;  // Residuals.cpp:88
+      const int32_t slot = slot_of_frame[t];
+      std::memcpy(P + 28, &slot, 4);
+    }
+  }
+}
+
+// Everything linearize reads, in the record order of F. HCalibT: fxl() / fyl() / cxl() / cyl() (CalibHessian, HessianBlocks.h:353-379).
+template <class EFResidualT, class EFPointT, class EFFrameT, class HCalibT>
+inline FlatLin<EFResidualT, EFPointT> linearizeInputs(const FlatEF<EFResidualT, EFPointT>& F, const std::vector<EFFrameT*>& frames,
+                                                       const int* slot_of_frame, HCalibT& HCalib, float outlierTHSumComponent) {  // (the reference's fxl() ... are non-const)
+  FlatLin<EFResidualT, EFPointT> L;
+  if ((int)frames.size() != F.nf) throw std::runtime_error("linearizeInputs: frame list does not match the flattened window");
+  L.nf = F.nf;
+  const int nRes = F.n_res(), nPts = F.n_pts();
+  L.pt4_points.assign((size_t)nPts * 4, 0.f);
+  L.color.assign((size_t)nRes * 8, 0.f);
+  L.weights.assign((size_t)nRes * 8, 0.f);
+  L.pack.assign(nRes, 0u);
+  L.point.assign(nRes, 0);
+  L.state_in.assign(nRes, 0);
+  L.energy_in.assign(nRes, 0.f);
+  L.pairs.assign((size_t)F.nf * F.nf * 32, 0.f);
+  for (int p = 0; p < nPts; p++) {
+    const auto* ph = F.points[p]->data;
+    for (int q = F.pt_begin[p]; q < F.pt_begin[p + 1]; q++) {
+      const int i = F.pt_res[q];
+      for (int k = 0; k < 8; k++) { L.color[(size_t)i * 8 + k] = ph->color[k]; L.weights[(size_t)i * 8 + k] = ph->weights[k]; }
+      L.point[i] = p;
+      std::memcpy(&L.pack[i], F.rec.data() + (size_t)i * NALO_BA_RECORD_WORDS + 73, 4);  // host | target << 8 | flags << 16
+    }
+  }
+  L.fx = (float)HCalib.fxl(); L.fy = (float)HCalib.fyl(); L.cx = (float)HCalib.cxl(); L.cy = (float)HCalib.cyl();
+  L.outlierTHSumComponent = outlierTHSumComponent;
+  refreshLinearizeInputs(L, F, frames, slot_of_frame);
+  return L;
+}
+
+// linearizeAll(false): every residual of the window linearised on the device, state_New* / centerProjectedTo / projectedTo
+// written back into the PointFrameResiduals; returns what linearizeAll_Reductor sums up in stats[0].
+// wantOutputs = false: nothing per residual comes back (the state stays on the device, see NaloLinInput::state_resident).
+template <class EFResidualT, class EFPointT>
+inline double linearizeAll(BAWindow<EFResidualT, EFPointT>& w, FlatLin<EFResidualT, EFPointT>& L, bool wantOutputs = true) {
+  auto& F = w.flat();
+  const int n = F.n_res();
+  if ((int)L.pack.size() != n) throw std::runtime_error("linearizeAll: inputs do not match the uploaded window");
+  const NaloLinInput in = L.input();
+  std::vector<uint8_t> st;
+  std::vector<float> en, eo, ce, pr;
+  if (wantOutputs) { st.assign((size_t)n + 1, 0); en.assign((size_t)n + 1, 0.f); eo.assign((size_t)n + 1, 0.f); ce.assign((size_t)n * 3 + 3, 0.f); pr.assign((size_t)n * 16 + 16, 0.f); }
+  w.ck(nalo_ba_linearize(w.handle(), &in, wantOutputs ? st.data() : nullptr, wantOutputs ? en.data() : nullptr, wantOutputs ? eo.data() : nullptr,
+                         wantOutputs ? ce.data() : nullptr, wantOutputs ? pr.data() : nullptr, nullptr),
+       "nalo_ba_linearize");
+  L.staticResident = true;
+  if (wantOutputs)
+    for (int i = 0; i < n; i++) {
+      auto* r = F.residual_of_record[i]->data;
+      typedef decltype(r->state_NewState) StateT;
+      r->state_NewState = (StateT)st[i];
+      r->state_NewEnergyWithOutlier = eo[i];  // (-1 on every path that ends OOB, Residuals.cpp:80)
+      if (st[i] != 1) {  // a residual that is or goes OOB returns early: state_NewEnergy and the projections keep their values (Residuals.cpp:82-83,110,187,200)
+        r->state_NewEnergy = en[i];
+        for (int k = 0; k < 3; k++) r->centerProjectedTo[k] = ce[(size_t)i * 3 + k];
+        for (int k = 0; k < 8; k++) { r->projectedTo[k][0] = pr[(size_t)i * 16 + 2 * k]; r->projectedTo[k][1] = pr[(size_t)i * 16 + 2 * k + 1]; }
+      }
+    }
+  double e = 0;
+  w.ck(nalo_ba_linearize_energy(w.handle(), &e, nullptr), "nalo_ba_linearize_energy");
+  return e;
+}
+
+// applyRes_Reductor (FullSystemOptimize.cpp:90-94) on the device-resident state after an accepted step; the host graph is
+// brought up to date by the last linearizeAll(wantOutputs = true) + the reference's own applyRes.
+template <class EFResidualT, class EFPointT>
+inline void applyResOnDevice(BAWindow<EFResidualT, EFPointT>& w, FlatLin<EFResidualT, EFPointT>& L) {
+  w.ck(nalo_ba_linearize_commit(w.handle()), "nalo_ba_linearize_commit");
+  L.stateResident = true;
+}
 
 // Window geometry / priors the stitch needs (EnergyFunctional::adHost / adTarget :47-86, cPrior, EFFrame::prior / delta_prior),
 // read out of the reference's objects into the row-major arrays of NaloBASolveInput.
