@@ -9,7 +9,8 @@
 // The structs below mock the members the facade touches, under the reference's names (HessianBlocks.h:84-110,192-222,402-456;
 // Residuals.h:52-90; EnergyFunctionalStructs.h:51-166); tests/cpp/lin_facade_real_check.cpp instantiates the same templates
 // against the reference's real headers where the reference exists.
-// usage: lin_facade_test <problem.bin> <out.bin>
+// usage: lin_facade_test <problem.bin> <out.bin> [--inputs-only]
+//   --inputs-only : no device needed; checks linearizeInputs(flattenEF(graph(problem))) against the problem itself and exits.
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -112,12 +113,13 @@ int main(int argc, char** argv) {
   const auto energyIn = rd<float>(f, nRes);
   fclose(f);
 
+  const bool inputsOnly = argc > 3 && std::string(argv[3]) == "--inputs-only";
   nalo_ctx* ctx = nullptr;
-  if (nalo_create(w, h, levels, 0, nf, &ctx) != NALO_OK) { fprintf(stderr, "nalo_create: %s\n", nalo_last_error(nullptr)); return 3; }
+  if (!inputsOnly && nalo_create(w, h, levels, 0, nf, &ctx) != NALO_OK) { fprintf(stderr, "nalo_create: %s\n", nalo_last_error(nullptr)); return 3; }
   std::vector<int> slotOf(nf);
   for (int k = 0; k < nf; k++) {
     slotOf[k] = nf - 1 - k;  // (any assignment of window frames to context slots)
-    if (nalo_make_images(ctx, slotOf[k], images[k].data(), nullptr, nullptr, nullptr) != NALO_OK) {
+    if (!inputsOnly && nalo_make_images(ctx, slotOf[k], images[k].data(), nullptr, nullptr, nullptr) != NALO_OK) {
       fprintf(stderr, "nalo_make_images: %s\n", nalo_last_error(ctx));
       return 3;
     }
@@ -178,6 +180,31 @@ int main(int argc, char** argv) {
   CalibHessian HCalib;
   for (int k = 0; k < 4; k++) HCalib.f[k] = K[k];
 
+  if (inputsOnly) {
+    // ---- no device: linearizeInputs(flattenEF(graph)) against the flat problem the graph was built from
+    auto F = nalo::flattenEF<EFResidual, EFPoint>(frames, adHT.data(), cDelta);
+    auto L = nalo::linearizeInputs(F, frames, slotOf.data(), HCalib, 50.f * 50.f);
+    if (F.n_res() != nRes || F.n_pts() != nPts || (int)L.pack.size() != nRes) { fprintf(stderr, "inputs: sizes differ\n"); return 1; }
+    for (int i = 0; i < nRes; i++) {
+      const int j = F.residual_of_record[i]->data->origIndex;
+      const int pNew = L.point[i], pOld = point[j];
+      if (F.points[pNew] != efp[pOld]) { fprintf(stderr, "inputs: record %d names the wrong point\n", i); return 1; }
+      if (L.pack[i] != pack[j] || L.state_in[i] != stateIn[j] || L.energy_in[i] != energyIn[j]) { fprintf(stderr, "inputs: record %d pack / state / energy\n", i); return 1; }
+      if (memcmp(&L.color[(size_t)i * 8], &colorP[(size_t)pOld * 8], 32) != 0 || memcmp(&L.weights[(size_t)i * 8], &weightsP[(size_t)pOld * 8], 32) != 0 ||
+          memcmp(&L.pt4_points[(size_t)pNew * 4], &pt4[(size_t)pOld * 4], 16) != 0) { fprintf(stderr, "inputs: record %d point data\n", i); return 1; }
+    }
+    for (int b = 0; b < nf * nf; b++) {
+      const float* A = &L.pairs[(size_t)b * 32];
+      const float* B = &pairs[(size_t)b * 32];
+      int32_t slot;
+      memcpy(&slot, A + 28, 4);
+      if (memcmp(A, B, 27 * 4) != 0 || A[27] != B[27] || slot != slotOf[b / nf]) { fprintf(stderr, "inputs: precalc table entry %d\n", b); return 1; }
+    }
+    const NaloLinInput in = L.input();
+    if (in.n_res != nRes || in.n_pts != nPts || in.nf != nf || !in.color || in.state_resident) { fprintf(stderr, "inputs: NaloLinInput\n"); return 1; }
+    printf("inputs ok: %d frames, %d points, %d residuals\n", nf, nPts, nRes);
+    return 0;
+  }
   int rcode = 0;
   try {
     nalo::BAWindow<EFResidual, EFPoint> win(ctx, nRes + 16, nPts + 16);

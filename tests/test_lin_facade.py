@@ -53,9 +53,7 @@ def _read_out(path):
     return out
 
 
-@pytest.mark.gpu
-def test_linearize_facade_matches_oracle(oracle, tmp_path):
-    _ensure_built()
+def _problem(tmp_path):
     w, h, L, nf = 320, 192, 4, 4
     sc = synth.make_scene(w, h, seed=12)
     P = synth.make_lin_problem(sc, nf=nf, pts_per_frame=350, seed=12)
@@ -82,6 +80,23 @@ def test_linearize_facade_matches_oracle(oracle, tmp_path):
         for a, dt in ((P["pairs"], np.float32), (pts, np.float32), (colorP, np.float32), (weightsP, np.float32), (hostP, np.int32),
                       (P["pack"], np.uint32), (P["point"], np.int32), (P["state_in"], np.uint8), (P["energy_in"], np.float32)):
             np.ascontiguousarray(a, dtype=dt).tofile(f)
+    return w, h, L, nf, n, npts, P, pts, prob
+
+
+def test_linearize_inputs_round_trip(tmp_path):
+    """nalo::linearizeInputs on the flattened pointer graph gives the flat problem back: point data through the point index,
+    pack / state / energy per record, the precalc table with the frame slots (no device needed)."""
+    _ensure_built()
+    w, h, L, nf, n, npts, P, pts, prob = _problem(tmp_path)
+    r = subprocess.run([BIN, prob, str(tmp_path / "unused.bin"), "--inputs-only"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert f"inputs ok: {nf} frames, {npts} points, {n} residuals" in r.stdout
+
+
+@pytest.mark.gpu
+def test_linearize_facade_matches_oracle(oracle, tmp_path):
+    _ensure_built()
+    w, h, L, nf, n, npts, P, pts, prob = _problem(tmp_path)
     out_path = str(tmp_path / "lin_out.bin")
     r = subprocess.run([BIN, prob, out_path], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout, r.stderr)
